@@ -1,0 +1,109 @@
+"""Deterministic synthetic inputs for the render + SR path: tri-planes, look-at cameras, jitter
+uniforms and random-init decoder / SR parameters.  Everything is drawn on the CPU from seeded generators so the
+CPU oracle, the golden fixtures and the GPU path see identical bits; callers upload with `.cuda()`.
+
+Camera convention follows the reference's pose sampler (modules/eg3ds/camera_utils/pose_sampler.py:28-36,
+94-131,174-204): camera on a sphere of radius 2.7 around `lookat`, y up, 25-vector = row-major c2w (16) +
+row-major normalised intrinsics (9) with focal 4.2647 and principal point 0.5."""
+from __future__ import annotations
+
+import math
+from typing import Dict, Tuple
+
+import torch
+
+FOCAL = 4.2647
+SR_CHANNELS = {'block0': (32, 256), 'block1': (256, 128)}
+
+
+def lookat_camera(pitch: torch.Tensor, yaw: torch.Tensor, lookat=(0.0, 0.0, 0.2), radius: float = 2.7) -> torch.Tensor:
+    """pitch[N], yaw[N] (radians) -> camera[N,25]."""
+    pitch = pitch.float().reshape(-1)
+    yaw = yaw.float().reshape(-1)
+    n = pitch.shape[0]
+    theta = yaw + math.pi / 2
+    v = (pitch + math.pi / 2).clamp(1e-5, math.pi - 1e-5) / math.pi
+    phi = torch.arccos(1 - 2 * v)
+    origin = torch.stack([radius * torch.sin(phi) * torch.cos(math.pi - theta),
+                          radius * torch.cos(phi),
+                          radius * torch.sin(phi) * torch.sin(math.pi - theta)], dim=1)
+    look = torch.tensor(lookat, dtype=torch.float32).expand(n, 3)
+    fwd = torch.nn.functional.normalize(look - origin, dim=1)
+    up0 = torch.tensor([0.0, 1.0, 0.0]).expand(n, 3)
+    right = -torch.nn.functional.normalize(torch.cross(up0, fwd, dim=1), dim=1)
+    up = torch.nn.functional.normalize(torch.cross(fwd, right, dim=1), dim=1)
+    c2w = torch.eye(4).repeat(n, 1, 1)
+    c2w[:, :3, 0], c2w[:, :3, 1], c2w[:, :3, 2], c2w[:, :3, 3] = right, up, fwd, origin
+    K = torch.tensor([[FOCAL, 0, 0.5], [0, FOCAL, 0.5], [0, 0, 1.0]]).reshape(1, 9).repeat(n, 1)
+    return torch.cat([c2w.reshape(n, 16), K], dim=1)
+
+
+def make_cameras(n: int, seed: int = 1) -> torch.Tensor:
+    """pitch ~ U[-0.2,0.4], yaw ~ U[-0.6,0.6] (all 64^2 rays hit the box for this range)."""
+    g = torch.Generator().manual_seed(seed)
+    pitch = torch.rand(n, generator=g) * 0.6 - 0.2
+    yaw = torch.rand(n, generator=g) * 1.2 - 0.6
+    return lookat_camera(pitch, yaw)
+
+
+def split_camera(camera: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    return camera[:, :16].reshape(-1, 4, 4), camera[:, 16:25].reshape(-1, 3, 3)
+
+
+def make_planes(n: int, c: int = 32, h: int = 256, w: int = 256, seed: int = 0) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n, 3, c, h, w, generator=g)
+
+
+def make_jitter(n: int, m: int, s: int, s_imp: int = 0, seed: int = 2):
+    g = torch.Generator().manual_seed(seed)
+    u_c = torch.rand(n, m, s, 1, generator=g)
+    u_f = torch.rand(n * m, s_imp, generator=torch.Generator().manual_seed(seed + 1)) if s_imp > 0 else None
+    return u_c, u_f
+
+
+def make_decoder_params(seed: int = 4, n_features: int = 32, hidden: int = 64, out_dim: int = 32) -> Dict[str, torch.Tensor]:
+    """OSGDecoder state_dict (modules/img2plane/triplane.py:123-131): N(0,1) weights, small random biases."""
+    g = torch.Generator().manual_seed(seed)
+    return {
+        'net.0.weight': torch.randn(hidden, n_features, generator=g),
+        'net.0.bias': 0.1 * torch.randn(hidden, generator=g),
+        'net.2.weight': torch.randn(1 + out_dim, hidden, generator=g),
+        'net.2.bias': 0.1 * torch.randn(1 + out_dim, generator=g),
+    }
+
+
+def make_sr_params(seed: int = 5, channels: int = 32, w_dim: int = 512) -> Dict[str, torch.Tensor]:
+    """SuperresolutionHybrid8XDC state_dict incl. buffers (networks_stylegan2.py:286-321,352-363,377-427)."""
+    g = torch.Generator().manual_seed(seed)
+    f = torch.tensor([1.0, 3.0, 3.0, 1.0])
+    f = torch.outer(f, f)
+    f = f / f.sum()
+    p: Dict[str, torch.Tensor] = {}
+    for blk, res in (('block0', 256), ('block1', 512)):
+        cin, cout = SR_CHANNELS[blk]
+        if blk == 'block0':
+            cin = channels
+        p[f'{blk}.resample_filter'] = f.clone()
+        for name, ci in (('conv0', cin), ('conv1', cout)):
+            pre = f'{blk}.{name}.'
+            p[pre + 'weight'] = torch.randn(cout, ci, 3, 3, generator=g)
+            p[pre + 'bias'] = 0.1 * torch.randn(cout, generator=g)
+            p[pre + 'affine.weight'] = torch.randn(ci, w_dim, generator=g)
+            p[pre + 'affine.bias'] = 1.0 + 0.1 * torch.randn(ci, generator=g)
+            p[pre + 'noise_strength'] = torch.zeros([])
+            p[pre + 'noise_const'] = torch.randn(res, res, generator=g)
+            p[pre + 'resample_filter'] = f.clone()
+        pre = f'{blk}.torgb.'
+        p[pre + 'weight'] = torch.randn(3, cout, 1, 1, generator=g)
+        p[pre + 'bias'] = 0.1 * torch.randn(3, generator=g)
+        p[pre + 'affine.weight'] = torch.randn(cout, w_dim, generator=g)
+        p[pre + 'affine.bias'] = 1.0 + 0.1 * torch.randn(cout, generator=g)
+    return p
+
+
+RENDERING_OPTIONS = {
+    'ray_start': 'auto', 'ray_end': 'auto', 'box_warp': 1.0, 'depth_resolution': 48,
+    'depth_resolution_importance': 0, 'disparity_space_sampling': False, 'clamp_mode': 'softplus',
+    'white_back': False,
+}

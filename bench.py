@@ -1,0 +1,247 @@
+"""bench.py — headline benchmark of the render + SR hot path (BASELINE.json: rendered frames/sec @512^2, 64^2 NeRF,
+48 samples/ray).  One "step" = one batch of `--batch` frames per GPU: tri-planes (resident in HBM, reference NCHW
+layout) -> channels-last repack -> fused render -> SR -> 512^2 fp32 frames [-> NCCL all-gather of the step's frames when
+N > 1].  Prints ONE JSON line on rank 0.  See DESIGN.md §Measurement for every field.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR_GFLOP_PER_FRAME = 197.63          # SURVEY.md §8d (FlopCounter probe of the reference SR, exact)
+SAMPLE_BYTES_PER_FRAME = 103.0e6     # stand-alone sample_from_planes op, S=48
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'tf_burst': d['bf16_tflops'], 'tf_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                'src': 'measured'}
+    return {'hbm_gbs': 6650.0, 'tf_burst': 1590.0, 'tf_sustained': 1400.0, 'src': 'fallback'}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith('active')})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(self.rows)}
+
+
+def cpu_frame_fn(n_frames):
+    """The oracle (port of the reference's PyTorch CPU path: same library ops) on `n_frames` frames of the workload."""
+    from oracle import real3d_oracle as orc
+    from real3dportrait_b200 import synthetic as syn
+    planes, cam = syn.make_planes(n_frames, seed=0), syn.make_cameras(n_frames, seed=1)
+    u_c, _ = syn.make_jitter(n_frames, 4096, 48, 0, seed=2)
+    mlp, srp = syn.make_decoder_params(seed=4), syn.make_sr_params(seed=5)
+    c2w, K = syn.split_camera(cam)
+    def run():
+        with torch.no_grad():
+            return orc.frame(planes, mlp, srp, c2w, K, u_coarse=u_c, lib=True)['image']
+    return run
+
+
+def time_cpu(n_frames, reps, warm=1):
+    torch.set_num_threads(os.cpu_count())
+    fn = cpu_frame_fn(n_frames)
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        t = time.perf_counter(); fn(); ts.append(time.perf_counter() - t)
+    ts.sort()
+    return n_frames / ts[len(ts) // 2], ts
+
+
+def config_of(args, extra=None):
+    c = {'workload': f'BASELINE configs[2]: batch={args.batch} frames/step/GPU, 64x64 rays x 48 samples on 3x32x256x256 fp32 '
+                     f'tri-planes + SR 64^2->512^2 (197.63 GFLOP/frame), random-init weights',
+         'frames_per_step_per_gpu': args.batch, 'samples_per_ray': 48, 'render_res': 64, 'out_res': 512,
+         'parallelism': f'frames sharded over {args.gpus} GPU(s), no data-path collective except the frame all-gather'}
+    c.update(extra or {})
+    return c
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path for this workload (oracle port; /root/reference cannot travel to the box)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
+    fps, ts = time_cpu(1, steps, warm)
+    line = {'impl': 'reference', 'metric': 'rendered frames/sec @512^2 (64^2 NeRF, 48 samples/ray)', 'value': fps, 'unit': 'frames/s',
+            'n_gpus': args.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * ts[len(ts) // 2], 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': config_of(args, {'note': 'each step = ONE frame of the batch on the host CPU (bounded sample)'}),
+            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'port',
+                             'sample': f'{steps} x 1 frame (render 64^2x48 + SR), torch CPU threads={os.cpu_count()}'},
+            'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=32)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=4)
+    ap.add_argument('--pool', type=int, default=32, help='distinct resident frames per GPU (32 x 25 MB = 805 MB > L2)')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--sr-mode', default=None, choices=[None, 'fp32', 'tc'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import ctypes as C
+    import real3dportrait_b200 as r3
+    from real3dportrait_b200 import _capi, synthetic as syn, engine
+
+    rank, world, local = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('LOCAL_RANK', '0'))
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    L = _capi.lib()
+    _capi.check(L.r3dp_device_info(None, None, None))
+
+    sr_mode = args.sr_mode or engine.default_sr_mode()
+    eng = engine.FrameEngine(batch=args.batch, sr_mode=sr_mode, device=dev, world=world, rank=rank, dist=dist)
+    eng.load_params(syn.make_decoder_params(seed=4), syn.make_sr_params(seed=5))
+    B, P = args.batch, max(args.pool, args.batch)
+    # resident inputs: every rank owns its own shard of the clip (different seeds per rank)
+    planes = syn.make_planes(P, seed=100 + rank).to(dev)
+    cams = syn.make_cameras(P, seed=200 + rank).to(dev)
+    u_c = syn.make_jitter(P, 4096, 48, 0, seed=300 + rank)[0].to(dev)
+    sl = lambda i: slice((i * B) % (P - B + 1), (i * B) % (P - B + 1) + B)
+
+    def step(i):
+        s = sl(i)
+        return eng.step(planes[s], cams[s], u_c[s])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    launches0 = L.r3dp_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = L.r3dp_launch_count() - launches0
+    clocks = sampler.summary()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    fps = world * B * args.steps / (ms / 1e3)
+
+    # ---- dominant kernel live timing (SR convolutions) over the same steps, CUDA events on the launching stream
+    prof = eng.profile_steps(lambda i: (planes[sl(i)], cams[sl(i)], u_c[sl(i)]), args.warmup, args.steps)
+    barrier()
+
+    # ---- end-to-end through the public call with HOST buffers (pinned), H2D + D2H inside the timed region
+    h_planes = planes[:B].cpu().pin_memory(); h_cams = cams[:B].cpu().pin_memory(); h_u = u_c[:B].cpu().pin_memory()
+    h_out = torch.empty(B, 3, 512, 512, dtype=torch.float32).pin_memory()
+    def e2e_step():
+        dp, dc, du = h_planes.to(dev, non_blocking=True), h_cams.to(dev, non_blocking=True), h_u.to(dev, non_blocking=True)
+        out = eng.step(dp, dc, du)
+        h_out.copy_(out[:B] if out.shape[0] >= B else out, non_blocking=True)
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ksteps = max(4, min(args.steps, 16))
+    for _ in range(ksteps):
+        e2e_step()
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_fps = world * B * ksteps / (float(te.item()) / 1e3)
+    h2d = h_planes.numel() * 4 + h_cams.numel() * 4 + h_u.numel() * 4
+    d2h = h_out.numel() * 4
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    sr_ms_per_step = prof['sr_conv_ms'] / args.steps
+    sr_tflops = SR_GFLOP_PER_FRAME * B / sr_ms_per_step                  # GFLOP / ms == TFLOP/s
+    line = {
+        'metric': 'rendered frames/sec @512^2 (64^2 NeRF, 48 samples/ray)', 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32 render; SR ' + ('f16 operands / f32 accumulate (tcgen05)' if sr_mode == 'tc' else 'f32'),
+        'data': 'synthetic',
+        'config': config_of(args, {'sr_mode': sr_mode, 'l2_policy': f'inputs larger than L2: {P} distinct resident frames/GPU '
+                                   f'({P * 25.2:.0f} MB) cycled', 'timing': 'CUDA events on the launch stream, barrier+sync both sides, max over ranks'}),
+        'clocks': clocks, 'gpu_launches': int(launches),
+        'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': ksteps},
+        'roofline': {'bound': 'tensor', 'achieved': sr_tflops, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
+                     'frac': sr_tflops / pk['tf_sustained'], 'traffic': None, 'kernel': prof['sr_kernel'],
+                     'peak_source': pk['src'] + ' bf16 sustained', 'algorithmic': f'{SR_GFLOP_PER_FRAME} GFLOP/frame x {B} frames/step',
+                     'share_of_step': sr_ms_per_step / (prof['total_ms'] / args.steps)},
+        'stage_ms_per_step': {k: v / args.steps for k, v in prof['stages'].items()},
+    }
+    if not args.no_cpu_baseline:
+        cpu_fps, ts = time_cpu(1, 5, 1)
+        line['cpu_baseline'] = {'value': cpu_fps, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'port',
+                                'sample': f'5 x 1 frame of the same workload (oracle, torch CPU, {os.cpu_count()} threads), median'}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,144 @@
+/*
+ * r3dp_b200.h — C ABI of libr3dp_b200.so: the B200 (sm_100a) implementation of Real3D-Portrait's per-frame
+ * volumetric render + super-resolution hot path.
+ *
+ * The reference has no C ABI for this path: its boundary is Python `torch.nn.Module.forward` signatures
+ * (SURVEY.md §8b).  The host-side mirror of those signatures lives in `real3dportrait_b200/*.py` and binds THIS
+ * header through ctypes; each entry point below names the reference interface it stands behind (paths relative
+ * to the reference tree).  Conventions:
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless the name ends in `_host`;
+ *   - tensors are dense row-major fp32 unless stated; shapes are given in brackets;
+ *   - `stream` is a cudaStream_t (0 = legacy default stream); all work is enqueued asynchronously on it and
+ *     nothing synchronises the device;
+ *   - return value 0 = success, non-zero = error; `r3dp_last_error()` returns a thread-local message
+ *     (the Python mirror raises RuntimeError with it, like the reference's TORCH_CHECK in bias_act.cpp:39-55);
+ *   - inputs are never written; outputs / workspaces must not alias inputs.
+ * There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef R3DP_B200_H
+#define R3DP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R3DP_ABI_VERSION 1
+
+typedef void* r3dp_stream_t; /* cudaStream_t */
+
+/* OSGDecoder parameters (modules/img2plane/triplane.py:122-146; FullyConnectedLayer networks_stylegan2.py:99-131).
+ * Raw (unscaled) state_dict tensors; the 1/sqrt(fan_in) weight gains are applied by the library. */
+typedef struct r3dp_mlp {
+    const float* w1; /* net.0.weight [hidden, in_features]      */
+    const float* b1; /* net.0.bias   [hidden]                   */
+    const float* w2; /* net.2.weight [1 + out_dim, hidden]      */
+    const float* b2; /* net.2.bias   [1 + out_dim]              */
+    int in_features; /* 32 */
+    int hidden;      /* 64 */
+    int out_dim;     /* 32 (colour channels; +1 density)        */
+} r3dp_mlp_t;
+
+int         r3dp_abi_version(void);
+const char* r3dp_last_error(void);
+/* SM count and compute capability of the current device; fails unless it is sm_100. */
+int r3dp_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Running total of CUDA kernels this library has launched in the process (bench.py's `gpu_launches`). */
+unsigned long long r3dp_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------- rays ---
+ * RaySampler.forward (modules/eg3ds/volumetric_rendering/ray_sampler.py:24-63).
+ * cam2world [N,4,4], intrinsics [N,3,3]  ->  ray_o [N,res*res,3], ray_d [N,res*res,3]; ray m = row*res + col. */
+int r3dp_gen_rays(const float* cam2world, const float* intrinsics, int N, int res, float* ray_o, float* ray_d,
+                  r3dp_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------------- planes ---
+ * Layout change done once per frame before sampling: reference tri-planes are [N,3,C,H,W]
+ * (secc_img2plane.py:105-110); the gather kernels read channels-last [N,3,H,W,C] so one bilinear tap is one
+ * 128-byte line.  C must be 32. */
+int r3dp_planes_to_channels_last(const float* planes_nchw, int N, int C, int H, int W, float* planes_cl,
+                                 r3dp_stream_t stream);
+
+/* sample_from_planes (renderer.py:65-75): planes_cl [N,3,H,W,C], coords [N,P,3] -> out [N,3,P,C]
+ * (bilinear, zero padding, align_corners=False, coords scaled by 2/box_warp; plane axes of generate_planes()). */
+int r3dp_triplane_sample(const float* planes_cl, int N, int C, int H, int W, const float* coords, int P,
+                         float box_warp, float* out, r3dp_stream_t stream);
+
+/* ImportanceRenderer.run_model (renderer.py:169-188) with an OSGDecoder: gather + mean over planes + MLP.
+ * -> rgb [N,P,out_dim], sigma [N,P,1]. */
+int r3dp_run_model(const float* planes_cl, int N, int C, int H, int W, const float* coords, int P, float box_warp,
+                   const r3dp_mlp_t* mlp, float* rgb, float* sigma, r3dp_stream_t stream);
+
+/* OSGDecoder.forward (modules/img2plane/triplane.py:133-146) on caller-supplied features:
+ * feat [N,K,P,C], K = 3 (mean over the planes) or K = 1 (already aggregated) -> rgb [N,P,out_dim], sigma [N,P,1]. */
+int r3dp_decode(const float* feat, int N, int K, int P, int C, const r3dp_mlp_t* mlp, float* rgb, float* sigma,
+                r3dp_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------------- render ---
+ * ImportanceRenderer.forward with ray_start = ray_end = 'auto' (renderer.py:118-167), fused: box limits
+ * (math_utils.py:46-98) -> stratified depths (renderer.py:209-232) -> tri-plane gather -> OSGDecoder ->
+ * MipRayMarcher2 (ray_marcher.py:25-57) [-> importance resampling (renderer.py:234-297) -> second gather/MLP ->
+ * depth merge (renderer.py:197-207) -> final march].
+ *   ray_o, ray_d [N,M,3]          rays; if ray_o == NULL they are generated in-kernel from `camera` [N,25]
+ *                                 (row-major c2w then row-major K, secc_img2plane.py:95-96) with M = res*res
+ *   u_coarse [N,M,S]              the uniforms the reference draws with torch.rand_like (renderer.py:226)
+ *   u_fine   [N*M,S_imp] or NULL  the uniforms of torch.rand (renderer.py:281); required when S_imp > 0
+ *   res                           image side if the M rays form a res x res image (enables 2-D ray tiles), else 0
+ * outputs: rgb [N,M,out_dim] (already scaled to [-1,1]), depth [N,M,1], weights_sum [N,M,1], is_ray_valid [N,M]
+ * (uint8 0/1).  Batch-global quirks are reproduced per call: invalid rays inherit min/max of the valid ray starts
+ * (renderer.py:123-126) and depth is clamped to the call-wide [min,max] sample depth (ray_marcher.py:50).
+ * workspace: r3dp_render_workspace_bytes(N, M) bytes of scratch. */
+size_t r3dp_render_workspace_bytes(int N, int M);
+int r3dp_render(const float* planes_cl, int N, int C, int H, int W,
+                const float* ray_o, const float* ray_d, const float* camera, int M, int res,
+                int S, int S_imp, float box_warp, int white_back,
+                const float* u_coarse, const float* u_fine, const r3dp_mlp_t* mlp,
+                float* rgb, float* depth, float* weights_sum, uint8_t* is_ray_valid,
+                void* workspace, size_t workspace_bytes, r3dp_stream_t stream);
+
+/* MipRayMarcher2.run_forward (ray_marcher.py:25-57) stand-alone: colors [N,M,S,C], sigmas [N,M,S,1],
+ * depths [N,M,S,1] -> rgb [N,M,C], depth [N,M,1], weights [N,M,S-1,1].  workspace: 16 bytes. */
+int r3dp_ray_march(const float* colors, const float* sigmas, const float* depths, int N, int M, int S, int C,
+                   int white_back, float* rgb, float* depth, float* weights, void* workspace,
+                   r3dp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------- super-resolution ---
+ * Building blocks of SuperresolutionHybrid8XDC.forward (modules/eg3ds/models/superresolution.py:331-359) with
+ * noise_mode='none', fp32 parameters.  Activations are NCHW fp32 at the boundary.
+ *
+ * r3dp_sr_styles: FullyConnectedLayer(w_dim, Cin, bias_init=1) (networks_stylegan2.py:113-127,314):
+ *   styles[N,Cin] = w_lat[N,w_dim] @ (A[Cin,w_dim]/sqrt(w_dim))^T + a[Cin], then * post_scale
+ *   (post_scale = 1/sqrt(Cin) for ToRGB, networks_stylegan2.py:362,366).
+ * r3dp_sr_fold_weights: the per-sample weights of modulated_conv2d (networks_stylegan2.py:63-70):
+ *   wf[N,O,I,k,k] = W[O,I,k,k] * styles[N,I]  (* rsqrt(sum_{I,k,k} (.)^2 + 1e-8) if demodulate). */
+int r3dp_sr_styles(const float* w_lat, const float* affine_w, const float* affine_b, int N, int w_dim, int Cin,
+                   float post_scale, float* styles, r3dp_stream_t stream);
+int r3dp_sr_fold_weights(const float* weight, const float* styles, int N, int O, int I, int k, int demodulate,
+                         float* wf, r3dp_stream_t stream);
+
+/* F.interpolate(size, bilinear, align_corners=False, antialias=True) for UP-scaling (superresolution.py:351-355;
+ * antialias is the identity when scale >= 1).  x [N,C,h,w] -> y [N,C,size,size]. */
+int r3dp_sr_resize_bilinear(const float* x, int N, int C, int h, int w, int size, float* y, r3dp_stream_t stream);
+
+/* Exact-fp32 SynthesisLayer (networks_stylegan2.py:322-342 -> conv2d_resample.py:116-138 -> bias_act lrelu):
+ *   up == 1: y = lrelu(conv3x3(x, wf[n], pad 1) + bias) * sqrt(2)                       x,y [N,*,H,W]
+ *   up == 2: y = lrelu(FIR4x4(conv_transpose2d(x, wf[n]^T, stride 2), pad 1, gain 4) + bias) * sqrt(2)
+ *            x [N,I,H,W] -> y [N,O,2H,2W]; scratch holds the (2H+1)x(2W+1) intermediate:
+ *            r3dp_sr_layer_scratch_bytes(N,O,H,W) bytes (0 needed for up == 1). */
+size_t r3dp_sr_layer_scratch_bytes(int N, int O, int H, int W);
+int r3dp_sr_layer_fp32(const float* x, const float* wf, const float* bias, int N, int I, int O, int H, int W, int up,
+                       float* y, void* scratch, r3dp_stream_t stream);
+
+/* ToRGB + skip (networks_stylegan2.py:365-370,463-469):
+ *   img_out[N,3,H,W] = upsample2d(img_in[N,3,H/2,W/2]) + conv1x1(x[N,I,H,W], wf_rgb[N,3,I]) + bias[3]
+ * upsample2d = zero-insert x2, pad (2,1,2,1), FIR [1,3,3,1]^2/64, gain 4 (upfirdn2d.py:317-354).
+ * img_in may be NULL (no skip). */
+int r3dp_sr_torgb_fp32(const float* x, const float* wf_rgb, const float* bias, const float* img_in, int N, int I,
+                       int H, int W, float* img_out, r3dp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R3DP_B200_H */

@@ -1,0 +1,419 @@
+// Fused volumetric renderer: ImportanceRenderer.forward with 'auto' limits (renderer.py:118-167) as three launches
+//   1. ray_limits_kernel   rays (given or generated from cameras) -> (t0,t1,valid) + call-wide min/max of valid t0
+//   2. render_kernel       depths -> tri-plane gather -> OSG decoder -> ray march [-> importance pass -> merge -> march]
+//   3. depth_clamp_kernel  NaN->inf, clamp depth to the call-wide [min,max] sample depth (ray_marcher.py:49-50)
+// plus gen_rays (RaySampler.forward) and a stand-alone ray marcher.
+#include "render_core.cuh"
+
+namespace r3dp {
+
+struct RenderWs {          // lives at the start of the caller's workspace
+    unsigned t0_min, t0_max;   // ordered-uint encoded floats over valid rays
+    unsigned d_min, d_max;     // over every sample depth of the call
+    unsigned n_valid;
+    unsigned pad[3];
+};
+static_assert(sizeof(RenderWs) == 32, "ws header");
+
+__global__ void init_ws_kernel(RenderWs* ws) {
+    ws->t0_min = 0xffffffffu; ws->t0_max = 0u; ws->d_min = 0xffffffffu; ws->d_max = 0u; ws->n_valid = 0u;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void gen_rays_kernel(const float* __restrict__ c2w, const float* __restrict__ K, int N, int res,
+                                float* __restrict__ ray_o, float* __restrict__ ray_d) {
+    const int M = res * res;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * M) return;
+    const int n = idx / M, m = idx - n * M;
+    Ray r = make_ray(c2w + n * 16, K + n * 9, res, m);
+    float* o = ray_o + (size_t)idx * 3; float* d = ray_d + (size_t)idx * 3;
+    o[0] = r.ox; o[1] = r.oy; o[2] = r.oz; d[0] = r.dx; d[1] = r.dy; d[2] = r.dz;
+}
+
+__device__ __forceinline__ Ray fetch_ray(const float* __restrict__ ray_o, const float* __restrict__ ray_d,
+                                         const float* __restrict__ camera, int res, int n, int M, int m) {
+    if (ray_o != nullptr) {
+        const float* o = ray_o + ((size_t)n * M + m) * 3; const float* d = ray_d + ((size_t)n * M + m) * 3;
+        Ray r; r.ox = o[0]; r.oy = o[1]; r.oz = o[2]; r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
+        return r;
+    }
+    return make_ray(camera + n * 25, camera + n * 25 + 16, res, m);
+}
+
+__global__ void ray_limits_kernel(const float* __restrict__ ray_o, const float* __restrict__ ray_d,
+                                  const float* __restrict__ camera, int res, int N, int M, float box,
+                                  float2* __restrict__ limits, uint8_t* __restrict__ valid_out, RenderWs* ws) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    float t0 = 0.f, t1 = 0.f; bool valid = false;
+    if (idx < N * M) {
+        const int n = idx / M, m = idx - n * M;
+        Ray r = fetch_ray(ray_o, ray_d, camera, res, n, M, m);
+        ray_box(r, box, t0, t1);
+        valid = t1 > t0;                                 // renderer.py:122
+        limits[idx] = make_float2(t0, t1);
+        valid_out[idx] = valid ? 1 : 0;
+    }
+    // call-wide min / max of the valid ray starts (renderer.py:124-126)
+    const unsigned mask = __ballot_sync(0xffffffffu, valid);
+    if (mask) {
+        float lo = warp_min(valid ? t0 : __int_as_float(0x7f800000));
+        float hi = warp_max(valid ? t0 : __int_as_float(0xff800000));
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&ws->t0_min, f2ord(lo));
+            atomicMax(&ws->t0_max, f2ord(hi));
+            atomicAdd(&ws->n_valid, (unsigned)__popc(mask));
+        }
+    }
+}
+
+__global__ void depth_clamp_kernel(float* __restrict__ depth, int n, const RenderWs* __restrict__ ws) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    float d = depth[idx];
+    if (d != d) d = __int_as_float(0x7f800000);         // nan_to_num(nan=inf); +-inf are then clamped below
+    const float lo = ord2f(ws->d_min), hi = ord2f(ws->d_max);
+    depth[idx] = fminf(fmaxf(d, lo), hi);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct RenderArgs {
+    const float* planes; int N, H, W;
+    const float* ray_o; const float* ray_d; const float* camera; int M, res;
+    int S, S_imp; float box_warp; int white_back;
+    const float* u_coarse; const float* u_fine;
+    r3dp_mlp_t mlp;
+    float* rgb; float* depth; float* wsum;
+    const float2* limits; const uint8_t* valid; RenderWs* ws;
+    int tiles_per_frame, tile_cols;     // ray tiling (see ray_of)
+};
+
+constexpr int kRenderThreads = 192;
+
+// R rays per CTA.  If the rays form a res x res image we take them as a COLUMN strip (R rows, 1 col): planes 1 and 2
+// are indexed by (x,z)/(z,x) only, so rays that differ only in image row share their footprints in L1.
+template <int R>
+__device__ __forceinline__ int ray_of(const RenderArgs& a, int tile, int r) {
+    if (a.tile_cols > 0) {
+        const int col = tile % a.tile_cols, band = tile / a.tile_cols;
+        return (band * R + r) * a.res + col;
+    }
+    return tile * R + r;
+}
+
+template <int R>
+__global__ void __launch_bounds__(kRenderThreads, 2) render_kernel(const RenderArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int ST = a.S + a.S_imp;                         // samples per ray after the optional importance pass
+    MlpSmem& mlp = *reinterpret_cast<MlpSmem*>(smem);
+    float* rows = smem + sizeof(MlpSmem) / 4;              // [R*ST][kRow]   features -> (sigma, colours)
+    float* dep = rows + R * ST * kRow;                     // [R*ST]          sample depths
+    float* wts = dep + R * ST;                             // [R*ST]          coarse interval weights
+    float* cdf = wts + R * ST;                             // [R*ST]          importance cdf
+    float* rayf = cdf + R * ST;                            // [R][8]          ox oy oz dx dy dz t0 t1
+    int* ord = reinterpret_cast<int*>(rayf + R * 8);       // [R*ST]          depth order of the merged samples
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kRenderThreads / 32;
+    const int n = blockIdx.y, tile = blockIdx.x;
+
+    load_mlp_smem(mlp, a.mlp, tid, kRenderThreads);
+
+    // ---- rays + limits -------------------------------------------------------------------------------------
+    if (tid < R) {
+        const int m = ray_of<R>(a, tile, tid);
+        float* rf = rayf + tid * 8;
+        if (m < a.M) {
+            Ray r = fetch_ray(a.ray_o, a.ray_d, a.camera, a.res, n, a.M, m);
+            float2 lim = a.limits[(size_t)n * a.M + m];
+            if (!a.valid[(size_t)n * a.M + m] && a.ws->n_valid > 0) {      // renderer.py:125-126 (far end from ray_START, sic)
+                lim.x = ord2f(a.ws->t0_min); lim.y = ord2f(a.ws->t0_max);
+            }
+            rf[0] = r.ox; rf[1] = r.oy; rf[2] = r.oz; rf[3] = r.dx; rf[4] = r.dy; rf[5] = r.dz; rf[6] = lim.x; rf[7] = lim.y;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) rf[q] = 0.f;
+        }
+    }
+    __syncthreads();
+
+    // ---- coarse depths (renderer.py:223-226, math_utils.py:101-118) -----------------------------------------
+    float dmin = __int_as_float(0x7f800000), dmax = __int_as_float(0xff800000);
+    for (int q = tid; q < R * a.S; q += kRenderThreads) {
+        const int r = q / a.S, k = q - r * a.S;
+        const int m = ray_of<R>(a, tile, r);
+        float d = 0.f;
+        if (m < a.M) {
+            const float t0 = rayf[r * 8 + 6], t1 = rayf[r * 8 + 7];
+            const float u = a.u_coarse[((size_t)n * a.M + m) * a.S + k];
+            const float step = __fdiv_rn((float)k, (float)(a.S - 1));
+            d = __fadd_rn(t0, __fmul_rn(step, __fsub_rn(t1, t0)));
+            d = __fadd_rn(d, __fmul_rn(u, __fdiv_rn(__fsub_rn(t1, t0), (float)(a.S - 1))));
+            dmin = fminf(dmin, d); dmax = fmaxf(dmax, d);
+        }
+        dep[r * ST + k] = d;
+    }
+    __syncthreads();
+
+    PlaneView pv; pv.base = a.planes + (size_t)n * 3 * a.H * a.W * kC; pv.H = a.H; pv.W = a.W; pv.scale = 2.0f / a.box_warp;
+
+    // One "pass" = gather + decode for samples k in [k0, k0+kn) of every ray.
+    auto run_pass = [&](int k0, int kn) {
+        const int nsamp = R * kn;
+        // gather: each warp takes 4 samples per iteration, 8 lanes x float4 per sample
+        const int sub = lane >> 3, cq = lane & 7;
+        for (int q4 = warp * 4; q4 < nsamp; q4 += kWarps * 4) {
+            const int q = q4 + sub;
+            if (q < nsamp) {
+                const int r = q / kn, k = k0 + (q - r * kn);
+                const float* rf = rayf + r * 8;
+                const float d = dep[r * ST + k];
+                const float x = __fadd_rn(rf[0], __fmul_rn(d, rf[3]));
+                const float y = __fadd_rn(rf[1], __fmul_rn(d, rf[4]));
+                const float z = __fadd_rn(rf[2], __fmul_rn(d, rf[5]));
+                float4 f0, f1, f2;
+                gather3(pv, x, y, z, cq, f0, f1, f2);
+                float* row = rows + (size_t)(r * ST + k) * kRow + cq * 4;
+                const float third = 1.0f / 3.0f;
+                row[0] = (f0.x + f1.x + f2.x) * third; row[1] = (f0.y + f1.y + f2.y) * third;
+                row[2] = (f0.z + f1.z + f2.z) * third; row[3] = (f0.w + f1.w + f2.w) * third;
+            }
+        }
+        __syncthreads();
+        // decode: two samples per thread
+        const int half = (nsamp + 1) >> 1;
+        for (int p = tid; p < half; p += kRenderThreads) {
+            const int qa = p, qb = p + half;
+            const int ra = qa / kn, ka = k0 + (qa - ra * kn);
+            const bool has_b = qb < nsamp;
+            const int rb = has_b ? qb / kn : ra, kb = has_b ? k0 + (qb - rb * kn) : ka;
+            decode_pair(mlp, rows + (size_t)(ra * ST + ka) * kRow, rows + (size_t)(rb * ST + kb) * kRow, has_b);
+        }
+        __syncthreads();
+    };
+
+    // Ray march over `cnt` samples of ray r taken in the order idx[0..cnt) (ray_marcher.py:26-57); lane = colour channel.
+    auto march = [&](int r, int cnt, const int* idx, bool write_out, float* wout) {
+        const float* rr = rows + (size_t)r * ST * kRow;
+        const float* dd = dep + r * ST;
+        float T = 1.0f, acc = 0.f, wsum = 0.f, dsum = 0.f;
+        int ia = idx ? idx[0] : 0;
+        float da = dd[ia], sa = rr[ia * kRow], ca = rr[ia * kRow + 1 + lane];
+        for (int i = 0; i + 1 < cnt; ++i) {
+            const int ib = idx ? idx[i + 1] : i + 1;
+            const float db = dd[ib], sb = rr[ib * kRow], cb = rr[ib * kRow + 1 + lane];
+            const float delta = db - da;
+            const float smid = softplus_fast((sa + sb) * 0.5f - 1.0f);          // ray_marcher.py:33
+            const float alpha = 1.0f - __expf(-(smid * delta));
+            const float w = alpha * T;
+            T *= (1.0f - alpha + 1e-10f);
+            acc = fmaf(w, (ca + cb) * 0.5f, acc);
+            wsum += w; dsum = fmaf(w, (da + db) * 0.5f, dsum);
+            if (wout && lane == 0) wout[i] = w;
+            da = db; sa = sb; ca = cb;
+        }
+        if (write_out) {
+            const int m = ray_of<R>(a, tile, r);
+            if (m < a.M) {
+                const size_t o = (size_t)n * a.M + m;
+                if (a.white_back) acc = acc + 1.0f - wsum;
+                a.rgb[o * (kOut - 1) + lane] = acc * 2.0f - 1.0f;
+                if (lane == 0) { a.wsum[o] = wsum; a.depth[o] = dsum / wsum; }   // 0/0 -> NaN, fixed by depth_clamp_kernel
+            }
+        }
+    };
+
+    run_pass(0, a.S);
+
+    if (a.S_imp == 0) {
+        for (int r = warp; r < R; r += kWarps) march(r, a.S, nullptr, true, nullptr);
+    } else {
+        const int S = a.S, Ni = a.S_imp;
+        for (int r = warp; r < R; r += kWarps) {
+            float* w = wts + r * ST; float* cd = cdf + r * ST; float* dd = dep + r * ST;
+            march(r, S, nullptr, false, w);                                   // coarse weights w[0..S-2]
+            __syncwarp();
+            // renderer.py:245-247: max_pool1d(2,1,pad 1) -> avg_pool1d(2,1) -> +0.01 ; a_i, i = 0..S-2
+            // pdf over p_i = a_{i+1} + 1e-5, i = 0..S-4 ; cdf has S-2 entries (renderer.py:272-276)
+            float total = 0.f;
+            for (int i = 0; i < S - 3; ++i) {          // every lane computes the same serial sums (torch.cumsum order)
+                const int j = i + 1;                                         // index into a
+                const float m0 = fmaxf(w[j - 1], w[j]), m1 = fmaxf(w[j], w[j + 1]);   // 1 <= j <= S-3: no -inf padding reached
+                total += (0.5f * (m0 + m1) + 0.01f) + 1e-5f;
+            }
+            float run = 0.f;
+            if (lane == 0) cd[0] = 0.f;
+            for (int i = 0; i < S - 3; ++i) {
+                const int j = i + 1;
+                const float m0 = fmaxf(w[j - 1], w[j]), m1 = fmaxf(w[j], w[j + 1]);
+                run += __fdiv_rn((0.5f * (m0 + m1) + 0.01f) + 1e-5f, total);
+                if (lane == 0) cd[i + 1] = run;
+            }
+            __syncwarp();
+            const int ncdf = S - 2;
+            const int m_ray = ray_of<R>(a, tile, r);
+            for (int j = lane; j < Ni; j += 32) {
+                float dfine = 0.f;
+                if (m_ray < a.M) {
+                    const float u = a.u_fine[((size_t)n * a.M + m_ray) * Ni + j];
+                    int idx = 0;                                             // searchsorted(cdf, u, right=True)
+                    while (idx < ncdf && cd[idx] <= u) ++idx;
+                    const int lo = max(idx - 1, 0), hi = min(idx, S - 3);
+                    const float c_lo = cd[lo], c_hi = cd[hi];
+                    float den = c_hi - c_lo;
+                    if (den < 1e-5f) den = 1.0f;
+                    const float b_lo = 0.5f * (dd[lo] + dd[lo + 1]), b_hi = 0.5f * (dd[hi] + dd[hi + 1]);
+                    dfine = b_lo + __fdiv_rn(u - c_lo, den) * (b_hi - b_lo);
+                    dmin = fminf(dmin, dfine); dmax = fmaxf(dmax, dfine);
+                }
+                dd[S + j] = dfine;
+            }
+        }
+        __syncthreads();
+        run_pass(S, Ni);
+        // merge: stable rank of every sample among the ray's ST depths (== torch.sort order when depths are distinct)
+        for (int r = warp; r < R; r += kWarps) {
+            const float* dd = dep + r * ST; int* od = ord + r * ST;
+            for (int i = lane; i < ST; i += 32) {
+                const float di = dd[i];
+                int rank = 0;
+                for (int j = 0; j < ST; ++j) { const float dj = dd[j]; rank += (dj < di) || (dj == di && j < i); }
+                od[rank] = i;
+            }
+            __syncwarp();
+            march(r, ST, od, true, nullptr);
+        }
+    }
+
+    // call-wide min/max of the sample depths (ray_marcher.py:50)
+    dmin = warp_min(dmin); dmax = warp_max(dmax);
+    if (lane == 0 && dmin <= dmax) { atomicMin(&a.ws->d_min, f2ord(dmin)); atomicMax(&a.ws->d_max, f2ord(dmax)); }
+}
+
+// Stand-alone marcher: one warp per ray, lane = channel (C <= 32 per pass, loops for wider C).
+__global__ void ray_march_kernel(const float* __restrict__ colors, const float* __restrict__ sigmas,
+                                 const float* __restrict__ depths, int NM, int S, int C, int white_back,
+                                 float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ weights, RenderWs* ws) {
+    const int ray = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    float dmin = __int_as_float(0x7f800000), dmax = __int_as_float(0xff800000);
+    if (ray < NM) {
+        const float* dd = depths + (size_t)ray * S; const float* ss = sigmas + (size_t)ray * S;
+        const float* cc = colors + (size_t)ray * S * C;
+        for (int i = lane; i < S; i += 32) { dmin = fminf(dmin, dd[i]); dmax = fmaxf(dmax, dd[i]); }
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            const int c = c0 + lane; const bool on = c < C;
+            float T = 1.f, acc = 0.f, wsum = 0.f, dsum = 0.f;
+            for (int i = 0; i + 1 < S; ++i) {
+                const float delta = dd[i + 1] - dd[i];
+                const float smid = softplus_fast((ss[i] + ss[i + 1]) * 0.5f - 1.0f);
+                const float alpha = 1.0f - __expf(-(smid * delta));
+                const float w = alpha * T;
+                T *= (1.0f - alpha + 1e-10f);
+                if (on) acc = fmaf(w, (cc[(size_t)i * C + c] + cc[(size_t)(i + 1) * C + c]) * 0.5f, acc);
+                wsum += w; dsum = fmaf(w, (dd[i] + dd[i + 1]) * 0.5f, dsum);
+                if (c0 == 0 && lane == 0) weights[(size_t)ray * (S - 1) + i] = w;
+            }
+            if (white_back) acc = acc + 1.0f - wsum;
+            if (on) rgb[(size_t)ray * C + c] = acc * 2.0f - 1.0f;
+            if (c0 == 0 && lane == 0) depth[ray] = dsum / wsum;
+        }
+    }
+    dmin = warp_min(dmin); dmax = warp_max(dmax);
+    if (lane == 0 && dmin <= dmax) { atomicMin(&ws->d_min, f2ord(dmin)); atomicMax(&ws->d_max, f2ord(dmax)); }
+}
+
+static size_t render_smem_bytes(int R, int ST) {
+    return sizeof(MlpSmem) + (size_t)R * ST * kRow * 4 + 3 * (size_t)R * ST * 4 + (size_t)R * 8 * 4 + (size_t)R * ST * 4;
+}
+
+template <int R>
+static int launch_render(const RenderArgs& a, cudaStream_t st) {
+    const size_t smem = render_smem_bytes(R, a.S + a.S_imp);
+    R3DP_CUDA(cudaFuncSetAttribute(render_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(a.tiles_per_frame, a.N);
+    render_kernel<R><<<grid, kRenderThreads, smem, st>>>(a);
+    R3DP_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace r3dp
+
+using namespace r3dp;
+
+extern "C" int r3dp_gen_rays(const float* cam2world, const float* intrinsics, int N, int res, float* ray_o, float* ray_d,
+                             r3dp_stream_t stream) {
+    R3DP_REQUIRE(N > 0 && res > 0, "gen_rays: N and res must be positive (got %d, %d)", N, res);
+    R3DP_REQUIRE(cam2world && intrinsics && ray_o && ray_d, "gen_rays: null pointer");
+    const int total = N * res * res;
+    gen_rays_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(cam2world, intrinsics, N, res, ray_o, ray_d);
+    count_launches(1);
+    R3DP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" size_t r3dp_render_workspace_bytes(int N, int M) {
+    return sizeof(RenderWs) + (size_t)N * M * sizeof(float2);
+}
+
+static int check_mlp(const r3dp_mlp_t* mlp, int C) {
+    R3DP_REQUIRE(mlp && mlp->w1 && mlp->b1 && mlp->w2 && mlp->b2, "decoder: null parameter pointer");
+    R3DP_REQUIRE(mlp->in_features == kC && mlp->hidden == kHidden && mlp->out_dim == kOut - 1 && C == kC,
+                 "decoder: only the OSGDecoder shape 32->64->1+32 is built (got %d->%d->1+%d, C=%d)",
+                 mlp->in_features, mlp->hidden, mlp->out_dim, C);
+    return 0;
+}
+
+extern "C" int r3dp_render(const float* planes_cl, int N, int C, int H, int W, const float* ray_o, const float* ray_d,
+                           const float* camera, int M, int res, int S, int S_imp, float box_warp, int white_back,
+                           const float* u_coarse, const float* u_fine, const r3dp_mlp_t* mlp, float* rgb, float* depth,
+                           float* weights_sum, uint8_t* is_ray_valid, void* workspace, size_t workspace_bytes,
+                           r3dp_stream_t stream) {
+    if (check_mlp(mlp, C)) return 1;
+    R3DP_REQUIRE(planes_cl && u_coarse && rgb && depth && weights_sum && is_ray_valid && workspace, "render: null pointer");
+    R3DP_REQUIRE(N > 0 && M > 0 && H > 0 && W > 0, "render: bad shape N=%d M=%d H=%d W=%d", N, M, H, W);
+    R3DP_REQUIRE(S >= 4, "render: depth_resolution must be >= 4 (got %d)", S);
+    R3DP_REQUIRE(S_imp >= 0 && (S_imp == 0 || u_fine), "render: depth_resolution_importance=%d needs u_fine", S_imp);
+    R3DP_REQUIRE(box_warp > 0.f, "render: box_warp must be positive");
+    R3DP_REQUIRE((ray_o && ray_d) || (camera && res > 0 && res * res == M), "render: need rays, or camera with M == res*res");
+    R3DP_REQUIRE(workspace_bytes >= r3dp_render_workspace_bytes(N, M), "render: workspace too small");
+    const int ST = S + S_imp;
+    R3DP_REQUIRE(ST <= 384, "render: at most 384 samples per ray are supported (got %d)", ST);
+    cudaStream_t st = as_stream(stream);
+
+    RenderWs* ws = reinterpret_cast<RenderWs*>(workspace);
+    float2* limits = reinterpret_cast<float2*>(reinterpret_cast<char*>(workspace) + sizeof(RenderWs));
+    init_ws_kernel<<<1, 1, 0, st>>>(ws);
+    const int total = N * M;
+    ray_limits_kernel<<<(total + 255) / 256, 256, 0, st>>>(ray_o, ray_d, camera, res, N, M, box_warp, limits, is_ray_valid, ws);
+    R3DP_LAUNCH_CHECK();
+
+    RenderArgs a;
+    a.planes = planes_cl; a.N = N; a.H = H; a.W = W; a.ray_o = ray_o; a.ray_d = ray_d; a.camera = camera; a.M = M; a.res = res;
+    a.S = S; a.S_imp = S_imp; a.box_warp = box_warp; a.white_back = white_back; a.u_coarse = u_coarse; a.u_fine = u_fine;
+    a.mlp = *mlp; a.rgb = rgb; a.depth = depth; a.wsum = weights_sum; a.limits = limits; a.valid = is_ray_valid; a.ws = ws;
+    const int R = ST <= 48 ? 8 : ST <= 96 ? 4 : ST <= 192 ? 2 : 1;
+    const bool image = res > 0 && res * res == M && (res % R) == 0;
+    a.tile_cols = image ? res : 0;
+    a.tiles_per_frame = (M + R - 1) / R;
+    int rc = R == 8 ? launch_render<8>(a, st) : R == 4 ? launch_render<4>(a, st) : R == 2 ? launch_render<2>(a, st) : launch_render<1>(a, st);
+    if (rc) return rc;
+    count_launches(4);
+    depth_clamp_kernel<<<(total + 255) / 256, 256, 0, st>>>(depth, total, ws);
+    R3DP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int r3dp_ray_march(const float* colors, const float* sigmas, const float* depths, int N, int M, int S, int C,
+                              int white_back, float* rgb, float* depth, float* weights, void* workspace, r3dp_stream_t stream) {
+    R3DP_REQUIRE(colors && sigmas && depths && rgb && depth && weights && workspace, "ray_march: null pointer");
+    R3DP_REQUIRE(N > 0 && M > 0 && S >= 2 && C > 0, "ray_march: bad shape");
+    cudaStream_t st = as_stream(stream);
+    RenderWs* ws = reinterpret_cast<RenderWs*>(workspace);
+    init_ws_kernel<<<1, 1, 0, st>>>(ws);
+    const int NM = N * M;
+    ray_march_kernel<<<(NM + 7) / 8, 256, 0, st>>>(colors, sigmas, depths, NM, S, C, white_back, rgb, depth, weights, ws);
+    depth_clamp_kernel<<<(NM + 255) / 256, 256, 0, st>>>(depth, NM, ws);
+    count_launches(3);
+    R3DP_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,203 @@
+// Stand-alone tri-plane ops behind the reference's public sampler API:
+//   planes_to_channels_last   [N,3,C,H,W] -> [N,3,H,W,C]        (HBM-bound transposition)
+//   triplane_sample           sample_from_planes (renderer.py:65-75): the HBM-roofline gather, write-dominated
+//   run_model                 ImportanceRenderer.run_model (renderer.py:169-188): gather + OSG decoder
+#include "render_core.cuh"
+
+namespace r3dp {
+
+// ---- layout change ------------------------------------------------------------------------------------------------
+// One CTA moves a [32 ch][128 px] tile through shared memory: reads are 512 B contiguous per channel row (float4 per
+// lane), writes are 128 B contiguous per pixel (float4 per lane, 8 lanes per pixel).
+constexpr int kTilePx = 128;
+__global__ void __launch_bounds__(256) planes_to_cl_kernel(const float* __restrict__ src, float* __restrict__ dst, int HW) {
+    __shared__ float tile[kC][kTilePx + 1];
+    const int plane = blockIdx.y;                         // n*3 + p
+    const int px0 = blockIdx.x * kTilePx;
+    const float* s = src + (size_t)plane * kC * HW;
+    float* d = dst + (size_t)plane * HW * kC;
+    const int tid = threadIdx.x;
+    const bool full = (px0 + kTilePx <= HW) && ((HW & 3) == 0);
+    if (full) {
+#pragma unroll
+        for (int it = 0; it < (kC * kTilePx / 4) / 256; ++it) {       // 4 iterations
+            const int v = it * 256 + tid;                              // float4 index in tile
+            const int c = v / (kTilePx / 4), p4 = v % (kTilePx / 4);
+            const float4 f = ldg_nc_f4(s + (size_t)c * HW + px0 + p4 * 4);
+            tile[c][p4 * 4 + 0] = f.x; tile[c][p4 * 4 + 1] = f.y; tile[c][p4 * 4 + 2] = f.z; tile[c][p4 * 4 + 3] = f.w;
+        }
+    } else {
+        for (int v = tid; v < kC * kTilePx; v += 256) {
+            const int c = v / kTilePx, p = v % kTilePx;
+            tile[c][p] = (px0 + p < HW) ? s[(size_t)c * HW + px0 + p] : 0.f;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < (kC * kTilePx / 4) / 256; ++it) {
+        const int v = it * 256 + tid;
+        const int p = v / (kC / 4), c4 = v % (kC / 4);
+        if (px0 + p < HW) {
+            float4 f = make_float4(tile[c4 * 4 + 0][p], tile[c4 * 4 + 1][p], tile[c4 * 4 + 2][p], tile[c4 * 4 + 3][p]);
+            *reinterpret_cast<float4*>(d + (size_t)(px0 + p) * kC + c4 * 4) = f;
+        }
+    }
+}
+
+// ---- sample_from_planes ---------------------------------------------------------------------------------------------
+// Persistent grid-stride kernel: a warp handles 4 points per step (8 lanes x float4 = one 128 B texel line per tap),
+// 12 independent 16 B loads in flight per lane, outputs written with streaming stores (never re-read here).
+__global__ void __launch_bounds__(256) triplane_sample_kernel(const float* __restrict__ planes, int N, int H, int W,
+                                                              const float* __restrict__ coords, int P, float scale,
+                                                              float* __restrict__ out) {
+    const int lane = threadIdx.x & 31, sub = lane >> 3, cq = lane & 7;
+    const long long total4 = ((long long)N * P + 3) / 4;
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < total4; g += wstride) {
+        const long long pt = g * 4 + sub;
+        if (pt >= (long long)N * P) continue;
+        const int n = (int)(pt / P); const int s = (int)(pt - (long long)n * P);
+        const float* c = coords + pt * 3;
+        const float x = __ldg(c), y = __ldg(c + 1), z = __ldg(c + 2);
+        PlaneView pv; pv.base = planes + (size_t)n * 3 * H * W * kC; pv.H = H; pv.W = W; pv.scale = scale;
+        float4 f0, f1, f2;
+        gather3(pv, x, y, z, cq, f0, f1, f2);
+        float* o = out + (((size_t)n * 3) * P + s) * kC + cq * 4;
+        stg_cs_f4(o, f0);
+        stg_cs_f4(o + (size_t)P * kC, f1);
+        stg_cs_f4(o + 2 * (size_t)P * kC, f2);
+    }
+}
+
+// ---- run_model ----------------------------------------------------------------------------------------------------
+constexpr int kRmThreads = 192, kRmPoints = 384;
+__global__ void __launch_bounds__(kRmThreads, 2) run_model_kernel(const float* __restrict__ planes, int N, int H, int W,
+                                                                 const float* __restrict__ coords, int P, float scale,
+                                                                 const r3dp_mlp_t m, float* __restrict__ rgb,
+                                                                 float* __restrict__ sigma) {
+    extern __shared__ __align__(16) float smem[];
+    MlpSmem& mlp = *reinterpret_cast<MlpSmem*>(smem);
+    float* rows = smem + sizeof(MlpSmem) / 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane >> 3, cq = lane & 7;
+    const int n = blockIdx.y, p0 = blockIdx.x * kRmPoints;
+    const int cnt = min(kRmPoints, P - p0);
+    load_mlp_smem(mlp, m, tid, kRmThreads);
+    PlaneView pv; pv.base = planes + (size_t)n * 3 * H * W * kC; pv.H = H; pv.W = W; pv.scale = scale;
+    for (int q4 = warp * 4; q4 < cnt; q4 += (kRmThreads / 32) * 4) {
+        const int q = q4 + sub;
+        if (q < cnt) {
+            const float* c = coords + ((size_t)n * P + p0 + q) * 3;
+            float4 f0, f1, f2;
+            gather3(pv, __ldg(c), __ldg(c + 1), __ldg(c + 2), cq, f0, f1, f2);
+            float* row = rows + (size_t)q * kRow + cq * 4;
+            const float third = 1.0f / 3.0f;
+            row[0] = (f0.x + f1.x + f2.x) * third; row[1] = (f0.y + f1.y + f2.y) * third;
+            row[2] = (f0.z + f1.z + f2.z) * third; row[3] = (f0.w + f1.w + f2.w) * third;
+        }
+    }
+    __syncthreads();
+    const int half = (cnt + 1) >> 1;
+    for (int p = tid; p < half; p += kRmThreads) {
+        const bool has_b = p + half < cnt;
+        decode_pair(mlp, rows + (size_t)p * kRow, rows + (size_t)(has_b ? p + half : p) * kRow, has_b);
+    }
+    __syncthreads();
+    float* o = rgb + ((size_t)n * P + p0) * (kOut - 1);
+    for (int i = tid; i < cnt * (kOut - 1); i += kRmThreads) {
+        const int q = i >> 5, c = i & 31;
+        o[i] = rows[(size_t)q * kRow + 1 + c];
+    }
+    for (int q = tid; q < cnt; q += kRmThreads) sigma[(size_t)n * P + p0 + q] = rows[(size_t)q * kRow];
+}
+
+// ---- OSGDecoder.forward on caller-supplied features (triplane.py:133-146) -------------------------------------------
+// feat [N,K,P,C] with K = 3 (mean over planes, triplane.py:135-136) or K = 1 (already aggregated).
+__global__ void __launch_bounds__(kRmThreads, 2) decode_kernel(const float* __restrict__ feat, int K, int P, const r3dp_mlp_t m,
+                                                              float* __restrict__ rgb, float* __restrict__ sigma) {
+    extern __shared__ __align__(16) float smem[];
+    MlpSmem& mlp = *reinterpret_cast<MlpSmem*>(smem);
+    float* rows = smem + sizeof(MlpSmem) / 4;
+    const int tid = threadIdx.x;
+    const int n = blockIdx.y, p0 = blockIdx.x * kRmPoints;
+    const int cnt = min(kRmPoints, P - p0);
+    load_mlp_smem(mlp, m, tid, kRmThreads);
+    const float invk = 1.0f / (float)K;
+    for (int i = tid; i < cnt * kC; i += kRmThreads) {
+        const int q = i >> 5, c = i & 31;
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) acc += feat[(((size_t)n * K + k) * P + p0 + q) * kC + c];
+        rows[(size_t)q * kRow + c] = K == 1 ? acc : acc * invk;
+    }
+    __syncthreads();
+    const int half = (cnt + 1) >> 1;
+    for (int p = tid; p < half; p += kRmThreads) {
+        const bool has_b = p + half < cnt;
+        decode_pair(mlp, rows + (size_t)p * kRow, rows + (size_t)(has_b ? p + half : p) * kRow, has_b);
+    }
+    __syncthreads();
+    float* o = rgb + ((size_t)n * P + p0) * (kOut - 1);
+    for (int i = tid; i < cnt * (kOut - 1); i += kRmThreads) o[i] = rows[(size_t)(i >> 5) * kRow + 1 + (i & 31)];
+    for (int q = tid; q < cnt; q += kRmThreads) sigma[(size_t)n * P + p0 + q] = rows[(size_t)q * kRow];
+}
+
+}  // namespace r3dp
+
+using namespace r3dp;
+
+extern "C" int r3dp_planes_to_channels_last(const float* planes_nchw, int N, int C, int H, int W, float* planes_cl,
+                                            r3dp_stream_t stream) {
+    R3DP_REQUIRE(planes_nchw && planes_cl, "planes_to_channels_last: null pointer");
+    R3DP_REQUIRE(C == kC, "planes_to_channels_last: C must be %d (got %d)", kC, C);
+    R3DP_REQUIRE(N > 0 && H > 0 && W > 0, "planes_to_channels_last: bad shape");
+    const int HW = H * W;
+    dim3 grid((HW + kTilePx - 1) / kTilePx, N * 3);
+    planes_to_cl_kernel<<<grid, 256, 0, as_stream(stream)>>>(planes_nchw, planes_cl, HW);
+    count_launches(1);
+    R3DP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int r3dp_triplane_sample(const float* planes_cl, int N, int C, int H, int W, const float* coords, int P,
+                                    float box_warp, float* out, r3dp_stream_t stream) {
+    R3DP_REQUIRE(planes_cl && coords && out, "triplane_sample: null pointer");
+    R3DP_REQUIRE(C == kC, "triplane_sample: C must be %d (got %d)", kC, C);
+    R3DP_REQUIRE(N > 0 && P > 0 && H > 0 && W > 0 && box_warp > 0.f, "triplane_sample: bad shape");
+    const long long warps = ((long long)N * P + 3) / 4;
+    long long blocks = (warps + 7) / 8;
+    const long long cap = (long long)sm_count() * 8;                    // 8 resident CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    triplane_sample_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(planes_cl, N, H, W, coords, P, 2.0f / box_warp, out);
+    count_launches(1);
+    R3DP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int r3dp_run_model(const float* planes_cl, int N, int C, int H, int W, const float* coords, int P, float box_warp,
+                              const r3dp_mlp_t* mlp, float* rgb, float* sigma, r3dp_stream_t stream) {
+    R3DP_REQUIRE(planes_cl && coords && rgb && sigma && mlp, "run_model: null pointer");
+    R3DP_REQUIRE(mlp->in_features == kC && mlp->hidden == kHidden && mlp->out_dim == kOut - 1 && C == kC,
+                 "run_model: only the OSGDecoder shape 32->64->1+32 is built");
+    R3DP_REQUIRE(N > 0 && P > 0 && H > 0 && W > 0 && box_warp > 0.f, "run_model: bad shape");
+    const size_t smem = sizeof(MlpSmem) + (size_t)kRmPoints * kRow * 4;
+    R3DP_CUDA(cudaFuncSetAttribute(run_model_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((P + kRmPoints - 1) / kRmPoints, N);
+    run_model_kernel<<<grid, kRmThreads, smem, as_stream(stream)>>>(planes_cl, N, H, W, coords, P, 2.0f / box_warp, *mlp, rgb, sigma);
+    count_launches(1);
+    R3DP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int r3dp_decode(const float* feat, int N, int K, int P, int C, const r3dp_mlp_t* mlp, float* rgb, float* sigma,
+                           r3dp_stream_t stream) {
+    R3DP_REQUIRE(feat && rgb && sigma && mlp, "decode: null pointer");
+    R3DP_REQUIRE(mlp->in_features == kC && mlp->hidden == kHidden && mlp->out_dim == kOut - 1 && C == kC,
+                 "decode: only the OSGDecoder shape 32->64->1+32 is built");
+    R3DP_REQUIRE(N > 0 && P > 0 && (K == 1 || K == 3), "decode: bad shape (K must be 1 or 3, got %d)", K);
+    const size_t smem = sizeof(MlpSmem) + (size_t)kRmPoints * kRow * 4;
+    R3DP_CUDA(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((P + kRmPoints - 1) / kRmPoints, N);
+    decode_kernel<<<grid, kRmThreads, smem, as_stream(stream)>>>(feat, K, P, *mlp, rgb, sigma);
+    count_launches(1);
+    R3DP_LAUNCH_CHECK();
+    return 0;
+}

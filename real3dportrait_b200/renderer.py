@@ -1,0 +1,144 @@
+"""ImportanceRenderer — host mirror of modules/eg3ds/volumetric_rendering/renderer.py:30-297.
+
+`forward` keeps the reference signature and return tuple; the whole body (box limits, stratified depths, tri-plane
+gather, OSG decoder, ray march, importance resampling, merge) is ONE fused CUDA call (r3dp_render).  Jitter uniforms
+are drawn here with torch.rand in the reference's order and shapes ([N,M,S,1] then [N*M,S_imp]; renderer.py:226,281), so
+`torch.manual_seed` reproduces runs exactly as it does for the reference; tests may instead pass them explicitly through
+rendering_options['u_coarse'] / ['u_fine']."""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+from typing import Optional, Union
+
+import torch
+
+from . import _capi as capi
+from .decoder import OSGDecoder
+from .ray_marcher import MipRayMarcher2
+
+
+def generate_planes() -> torch.Tensor:
+    """The three plane axis frames of the reference (renderer.py:30-47)."""
+    return torch.tensor([[[1, 0, 0], [0, 1, 0], [0, 0, 1]],
+                         [[1, 0, 0], [0, 0, 1], [0, 1, 0]],
+                         [[0, 0, 1], [1, 0, 0], [0, 1, 0]]], dtype=torch.float32)
+
+
+class PlanesCL:
+    """Tri-planes already in the gather layout [N,3,H,W,C] (one texel = one 128-byte line)."""
+
+    def __init__(self, data: torch.Tensor):
+        assert data.ndim == 5 and data.is_cuda and data.dtype == torch.float32 and data.is_contiguous()
+        self.data = data
+
+    @property
+    def dims(self):
+        N, _, H, W, Cc = self.data.shape
+        return N, Cc, H, W
+
+
+def planes_to_channels_last(planes: torch.Tensor, out: Optional[torch.Tensor] = None) -> PlanesCL:
+    """[N,3,C,H,W] (reference layout, secc_img2plane.py:105-110) -> PlanesCL."""
+    planes = capi.f32(planes)
+    assert planes.ndim == 5 and planes.shape[1] == 3, planes.shape
+    N, _, Cc, H, W = planes.shape
+    if out is None:
+        out = torch.empty(N, 3, H, W, Cc, device=planes.device, dtype=torch.float32)
+    with capi.region('repack'):
+        capi.check(capi.lib().r3dp_planes_to_channels_last(capi.ptr(planes), N, Cc, H, W, capi.ptr(out), capi.stream()))
+    return PlanesCL(out)
+
+
+def _as_cl(planes: Union[torch.Tensor, PlanesCL]) -> PlanesCL:
+    return planes if isinstance(planes, PlanesCL) else planes_to_channels_last(planes)
+
+
+def sample_from_planes(plane_axes, plane_features, coordinates, mode='bilinear', padding_mode='zeros', box_warp=None):
+    """renderer.py:65-75: plane_features [N,3,C,H,W] (or PlanesCL), coordinates [N,P,3] -> [N,3,P,C]."""
+    assert padding_mode == 'zeros' and mode == 'bilinear'
+    if plane_axes is not None and not torch.equal(plane_axes.detach().cpu().float(), generate_planes()):
+        raise NotImplementedError('only the reference plane axes (generate_planes()) are built')
+    pcl = _as_cl(plane_features)
+    N, Cc, H, W = pcl.dims
+    coords = capi.f32(coordinates)
+    P = coords.shape[1]
+    out = torch.empty(N, 3, P, Cc, device=coords.device, dtype=torch.float32)
+    capi.check(capi.lib().r3dp_triplane_sample(capi.ptr(pcl.data), N, Cc, H, W, capi.ptr(coords), P, C.c_float(float(box_warp)),
+                                               capi.ptr(out), capi.stream()))
+    return out
+
+
+class ImportanceRenderer(torch.nn.Module):
+    def __init__(self, hp=None):
+        super().__init__()
+        if hp is None:
+            hp = {'enable_rescale_plane_regulation': False, 'triplane_feature_type': 'triplane'}
+        self.hparams = copy.copy(hp)
+        self.ray_marcher = MipRayMarcher2()
+        self.plane_axes = generate_planes()
+        self.triplane_feature_type = self.hparams.get('triplane_feature_type', 'triplane')
+        if self.triplane_feature_type != 'triplane':
+            raise NotImplementedError(f"triplane_feature_type={self.triplane_feature_type!r}: only 'triplane' is built (SURVEY.md §8f #4)")
+
+    def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options):
+        """planes [N,3,C,H,W] | PlanesCL, decoder: OSGDecoder, rays [N,M,3] ->
+        (rgb [N,M,C], depth [N,M,1], weights_sum [N,M,1], is_ray_valid [N,M,1] bool)   (renderer.py:118-167)."""
+        opt = rendering_options
+        if not (opt['ray_start'] == opt['ray_end'] == 'auto'):
+            # the reference itself raises NameError on this branch (is_ray_valid undefined, renderer.py:121,167)
+            raise NotImplementedError("only ray_start = ray_end = 'auto' is supported (as in every Real3D config)")
+        if opt.get('disparity_space_sampling', False):
+            raise NotImplementedError('disparity_space_sampling is not used by Real3D-Portrait (img2plane_baseline.py:109)')
+        assert opt.get('clamp_mode', 'softplus') == 'softplus', 'MipRayMarcher only supports `clamp_mode`=`softplus`!'
+        if opt.get('density_noise', 0) > 0 or (self.hparams.get('enable_rescale_plane_regulation', False) and self.training):
+            raise NotImplementedError('training-time density noise / plane rescaling are outside the inference path')
+        if not isinstance(decoder, OSGDecoder):
+            raise TypeError('the fused renderer needs an OSGDecoder (its four parameter tensors are read by the kernel)')
+        pcl = _as_cl(planes)
+        N, Cc, H, W = pcl.dims
+        ray_o, ray_d = capi.f32(ray_origins), capi.f32(ray_directions)
+        M = ray_o.shape[1]
+        S, S_imp = int(opt['depth_resolution']), int(opt.get('depth_resolution_importance', 0) or 0)
+        dev = ray_o.device
+        u_c = opt.get('u_coarse')
+        u_c = torch.rand(N, M, S, 1, device=dev) if u_c is None else capi.f32(u_c)
+        u_f = None
+        if S_imp > 0:
+            u_f = opt.get('u_fine')
+            u_f = torch.rand(N * M, S_imp, device=dev) if u_f is None else capi.f32(u_f)
+        res = int(round(M ** 0.5))
+        res = res if res * res == M else 0
+        rgb = torch.empty(N, M, Cc, device=dev)
+        depth = torch.empty(N, M, 1, device=dev)
+        wsum = torch.empty(N, M, 1, device=dev)
+        valid = torch.empty(N, M, 1, device=dev, dtype=torch.bool)
+        L = capi.lib()
+        ws_bytes = L.r3dp_render_workspace_bytes(N, M)
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        m = decoder.mlp_struct()
+        with capi.region('render'):
+            capi.check(L.r3dp_render(capi.ptr(pcl.data), N, Cc, H, W, capi.ptr(ray_o), capi.ptr(ray_d), None, M, res, S, S_imp,
+                                     float(opt['box_warp']), int(bool(opt.get('white_back', False))),
+                                     capi.ptr(u_c), capi.ptr(u_f), C.byref(m), capi.ptr(rgb), capi.ptr(depth), capi.ptr(wsum),
+                                     capi.ptr(valid, torch.bool), capi.ptr(ws, torch.uint8), ws_bytes, capi.stream()))
+        return rgb, depth, wsum, valid
+
+    def run_model(self, planes, decoder, sample_coordinates, sample_directions, options):
+        """renderer.py:169-188: planes, coords [N,P,3] -> {'rgb': [N,P,C], 'sigma': [N,P,1]}."""
+        if options.get('density_noise', 0) > 0:
+            raise NotImplementedError('density_noise is a training-time option')
+        pcl = _as_cl(planes)
+        N, Cc, H, W = pcl.dims
+        coords = capi.f32(sample_coordinates)
+        P = coords.shape[1]
+        if isinstance(decoder, OSGDecoder):
+            rgb = torch.empty(N, P, Cc, device=coords.device)
+            sigma = torch.empty(N, P, 1, device=coords.device)
+            m = decoder.mlp_struct()
+            capi.check(capi.lib().r3dp_run_model(capi.ptr(pcl.data), N, Cc, H, W, capi.ptr(coords), P,
+                                                 C.c_float(float(options['box_warp'])), C.byref(m), capi.ptr(rgb), capi.ptr(sigma),
+                                                 capi.stream()))
+            return {'rgb': rgb, 'sigma': sigma}
+        feats = sample_from_planes(None, pcl, coords, box_warp=options['box_warp'])
+        return decoder(feats, coords)

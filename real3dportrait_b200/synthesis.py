@@ -1,0 +1,72 @@
+"""RenderHead — the part of OSAvatarSECC_Img2plane.synthesis() that follows plane production
+(modules/real3d/secc_img2plane.py:93-137 with _forward_sr from img2plane_baseline.py:140-147): cameras + tri-planes ->
+rays -> fused render -> feature image -> super-resolution -> the reference's `ret` dict."""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from .decoder import OSGDecoder
+from .ray_sampler import RaySampler
+from .renderer import ImportanceRenderer
+from .superresolution import SuperresolutionHybrid8XDC
+
+DEFAULT_HPARAMS = {
+    'neural_rendering_resolution': 64, 'w_dim': 512, 'final_resolution': 512, 'triplane_hid_dim': 32,
+    'num_samples_coarse': 48, 'num_samples_fine': 0, 'box_warp': 1.0, 'base_channel': 32768, 'max_channel': 512,
+    'enable_rescale_plane_regulation': False, 'triplane_feature_type': 'triplane', 'mask_invalid_rays': False,
+}
+
+
+class RenderHead(torch.nn.Module):
+    """Child module names (`decoder`, `superresolution`, `renderer`, `ray_sampler`) match the reference model, so the
+    corresponding slices of a released checkpoint load unchanged."""
+
+    def __init__(self, hp: Optional[dict] = None, sr_mode: str = 'fp32'):
+        super().__init__()
+        self.hparams = dict(DEFAULT_HPARAMS, **(hp or {}))
+        hp = self.hparams
+        self.neural_rendering_resolution = hp['neural_rendering_resolution']
+        c = hp['triplane_hid_dim']
+        self.decoder = OSGDecoder(c, {'decoder_lr_mul': 1, 'decoder_output_dim': c})
+        self.superresolution = SuperresolutionHybrid8XDC(channels=c, img_resolution=hp['final_resolution'], sr_num_fp16_res=0,
+                                                         sr_antialias=True, sr_mode=sr_mode, channel_base=hp['base_channel'],
+                                                         channel_max=hp['max_channel'], fused_modconv_default='inference_only')
+        self.renderer = ImportanceRenderer(hp=hp)
+        self.ray_sampler = RaySampler()
+        self.rendering_kwargs = {
+            'image_resolution': hp['final_resolution'], 'disparity_space_sampling': False, 'clamp_mode': 'softplus',
+            'superresolution_noise_mode': 'none', 'sr_antialias': True, 'depth_resolution': hp['num_samples_coarse'],
+            'depth_resolution_importance': hp['num_samples_fine'], 'ray_start': 'auto', 'ray_end': 'auto',
+            'box_warp': hp.get('box_warp', 1.0), 'white_back': False,
+        }
+
+    @torch.no_grad()
+    def synthesis(self, planes, camera: torch.Tensor, ret: Optional[Dict] = None, **render_overrides) -> Dict[str, torch.Tensor]:
+        """planes [N,3,C,H,W], camera [N,25] -> ret dict with the reference's keys (secc_img2plane.py:134-136)."""
+        if ret is None:
+            ret = {}
+        cam2world = camera[:, :16].reshape(-1, 4, 4)
+        intrinsics = camera[:, 16:25].reshape(-1, 3, 3)
+        res = self.neural_rendering_resolution
+        ray_o, ray_d = self.ray_sampler(cam2world, intrinsics, res)
+        N = ray_o.shape[0]
+        opts = dict(self.rendering_kwargs, **render_overrides)
+        feat, depth, wsum, valid = self.renderer(planes, self.decoder, ray_o, ray_d, opts)
+        feature_image = feat.permute(0, 2, 1).reshape(N, feat.shape[-1], res, res).contiguous()
+        weights_image = wsum.permute(0, 2, 1).reshape(N, 1, res, res).contiguous()
+        depth_image = depth.permute(0, 2, 1).reshape(N, 1, res, res)
+        if self.hparams.get('mask_invalid_rays', False):
+            mask = valid.reshape(N, 1, res, res)
+            feature_image = torch.where(mask, feature_image, torch.full_like(feature_image, -1.0))
+            depth_image = torch.where(mask, depth_image, depth_image[mask].min())
+        rgb_image = feature_image[:, :3]
+        ret['weights_img'] = weights_image
+        ones_ws = torch.ones(N, 14, self.hparams['w_dim'], device=feature_image.device)
+        sr_image = self.superresolution(rgb_image, feature_image, ones_ws, noise_mode='none')
+        ret.update({'image_raw': rgb_image.clamp(-1, 1), 'image_depth': depth_image, 'image': sr_image.clamp(-1, 1),
+                    'image_feature': feature_image[:, 3:], 'plane': planes, 'is_ray_valid': valid})
+        return ret
+
+    forward = synthesis

@@ -1,0 +1,60 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, the host mirror keeps the reference's
+state_dict layout, and the product path refuses to run without CUDA (no silent fallback)."""
+import os
+
+import pytest
+import torch
+
+import real3dportrait_b200 as r3
+from real3dportrait_b200 import _capi, synthetic as syn, build as r3build
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = r3build.build()
+    assert os.path.exists(path)
+    L = _capi.lib()
+    declared = _capi.declared_symbols()
+    assert len(declared) >= 17
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(declared) == set(_capi._SIGNATURES), set(declared) ^ set(_capi._SIGNATURES)
+    assert L.r3dp_abi_version() == 1
+
+
+def test_state_dict_layout_matches_reference_checkpoints():
+    # key list == what the REFERENCE modules accepted with strict=True in tests/golden/make_golden.py
+    head = r3.RenderHead()
+    want = {'decoder.' + k for k in syn.make_decoder_params()} | {'superresolution.' + k for k in syn.make_sr_params()}
+    assert set(head.state_dict().keys()) == want
+    sd = {'decoder.' + k: v for k, v in syn.make_decoder_params().items()}
+    sd.update({'superresolution.' + k: v for k, v in syn.make_sr_params().items()})
+    head.load_state_dict(sd, strict=True)
+    assert sum(p.numel() for p in head.superresolution.parameters()) == 1649578 - 0  # 1 649 578 SR params
+    assert sum(p.numel() for p in head.decoder.parameters()) == 4257
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        r3.RaySampler()(torch.eye(4)[None], torch.eye(3)[None], 4)
+    planes = torch.zeros(1, 3, 32, 4, 4)
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        r3.planes_to_channels_last(planes)
+
+
+def test_unsupported_options_raise():
+    ren = r3.ImportanceRenderer()
+    dec = r3.OSGDecoder(32, {'decoder_lr_mul': 1, 'decoder_output_dim': 32})
+    opts = dict(syn.RENDERING_OPTIONS, ray_start=2.0, ray_end=3.0)
+    with pytest.raises(NotImplementedError):
+        ren(torch.zeros(1, 3, 32, 4, 4), dec, torch.zeros(1, 4, 3), torch.zeros(1, 4, 3), opts)
+    with pytest.raises(NotImplementedError):
+        r3.ImportanceRenderer(hp={'triplane_feature_type': 'trigrid_v2', 'enable_rescale_plane_regulation': False})
+
+
+def test_synthetic_cameras_hit_the_box():
+    from oracle import real3d_oracle as orc
+    cam = syn.make_cameras(8, seed=1)
+    c2w, K = syn.split_camera(cam)
+    o, d = orc.gen_rays(c2w, K, 64)
+    _, _, valid = orc.auto_limits(o, d, 1.0)
+    assert bool(valid.all())

@@ -63,6 +63,22 @@ class ClockSampler(threading.Thread):
                 'samples': len(self.rows)}
 
 
+def host_threads():
+    """Threads the CPU baseline may really use: min(cpu_count, affinity mask, cgroup cpu quota)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = max(1, min(n, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_frame_fn(n_frames):
     """The oracle (port of the reference's PyTorch CPU path: same library ops) on `n_frames` frames of the workload."""
     from oracle import real3d_oracle as orc
@@ -77,16 +93,27 @@ def cpu_frame_fn(n_frames):
     return run
 
 
-def time_cpu(n_frames, reps, warm=1):
-    torch.set_num_threads(os.cpu_count())
+def time_cpu(n_frames, reps, warm=1, budget_s=45.0):
+    """Median frames/s of the oracle on the host.  Tries the full thread count and (if that is > 32) 32 threads, because
+    torch's CPU convolutions often run SLOWER when heavily over-threaded; reports the best, with the count used."""
     fn = cpu_frame_fn(n_frames)
-    for _ in range(warm):
-        fn()
-    ts = []
-    for _ in range(reps):
-        t = time.perf_counter(); fn(); ts.append(time.perf_counter() - t)
-    ts.sort()
-    return n_frames / ts[len(ts) // 2], ts
+    best = None
+    cands = [host_threads()] + ([32] if host_threads() > 32 else [])
+    for nt in cands:
+        torch.set_num_threads(nt)
+        t_start = time.perf_counter()
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            t = time.perf_counter(); fn(); ts.append(time.perf_counter() - t)
+            if time.perf_counter() - t_start > budget_s / len(cands):
+                break
+        ts.sort()
+        fps = n_frames / ts[len(ts) // 2]
+        if best is None or fps > best[0]:
+            best = (fps, ts, nt)
+    return best
 
 
 def config_of(args, extra=None):
@@ -104,13 +131,13 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warm = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
-    fps, ts = time_cpu(1, steps, warm)
+    fps, ts, nthr = time_cpu(1, steps, warm)
     line = {'impl': 'reference', 'metric': 'rendered frames/sec @512^2 (64^2 NeRF, 48 samples/ray)', 'value': fps, 'unit': 'frames/s',
             'n_gpus': args.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * ts[len(ts) // 2], 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': config_of(args, {'note': 'each step = ONE frame of the batch on the host CPU (bounded sample)'}),
-            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'port',
-                             'sample': f'{steps} x 1 frame (render 64^2x48 + SR), torch CPU threads={os.cpu_count()}'},
+            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': nthr, 'kind': 'port',
+                             'sample': f'{len(ts)} x 1 frame (render 64^2x48 + SR), torch CPU threads={nthr} of {host_threads()} usable'},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
@@ -235,9 +262,10 @@ def main():
         'stage_ms_per_step': {k: v / args.steps for k, v in prof['stages'].items()},
     }
     if not args.no_cpu_baseline:
-        cpu_fps, ts = time_cpu(1, 5, 1)
-        line['cpu_baseline'] = {'value': cpu_fps, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'port',
-                                'sample': f'5 x 1 frame of the same workload (oracle, torch CPU, {os.cpu_count()} threads), median'}
+        cpu_fps, ts, nthr = time_cpu(1, 5, 1)
+        line['cpu_baseline'] = {'value': cpu_fps, 'unit': 'frames/s', 'cores': nthr, 'kind': 'port',
+                                'sample': f'{len(ts)} x 1 frame of the same workload (oracle = port of the reference PyTorch CPU path), '
+                                          f'{nthr} torch threads of {host_threads()} usable, median'}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -138,6 +138,30 @@ int r3dp_sr_layer_fp32(const float* x, const float* wf, const float* bias, int N
 int r3dp_sr_torgb_fp32(const float* x, const float* wf_rgb, const float* bias, const float* img_in, int N, int I,
                        int H, int W, float* img_out, r3dp_stream_t stream);
 
+/* --------------------------------------------------------------- super-resolution on tensor cores (tcgen05) ---
+ * Same layers as above as TMA-fed tcgen05 implicit GEMMs: fp16 operands, fp32 accumulation in TMEM, fp32 epilogue.
+ * Activations are NHWC fp16 with channels padded to a multiple of 64; weights are the per-sample folded weights
+ * (r3dp_sr_fold_weights) packed to fp16 [Nw][9][O][Ipad] with Nw == N (per-sample styles) or 1 (shared styles).
+ * Restrictions (met by SuperresolutionHybrid8XDC): W % 128 == 0, Cout % 128 == 0.
+ *
+ * r3dp_sr_tc_pack_weights  wf fp32 [Nw,O,I,3,3] -> packed fp16
+ * r3dp_sr_tc_input         x fp32 NCHW [N,C,h,w] -> bilinear (align_corners=False) to size x size -> NHWC fp16 [N,size,size,Cpad]
+ * r3dp_sr_tc_layer         SynthesisLayer (networks_stylegan2.py:322-342): up == 1 -> y [N,H,W,O]; up == 2 -> y [N,2H,2W,O]
+ *                          (transposed conv as 4 parity phases + FIR, conv2d_resample.py:116-133); scratch for up == 2:
+ *                          r3dp_sr_tc_scratch_bytes(N,O,H,W)
+ * r3dp_sr_tc_torgb         ToRGB + upsampled skip of a non-final block -> img fp32 NCHW [N,3,H,W]
+ * r3dp_sr_tc_last_layer    last conv (I -> 128) fused with ToRGB + skip: only the image is written (fp32 NCHW [N,3,H,W]);
+ *                          wrgb [Nw,3,128], brgb [3], img_prev [N,3,H/2,W/2]. */
+int r3dp_sr_tc_pack_weights(const float* wf, int Nw, int O, int I, void* packed_f16, r3dp_stream_t stream);
+int r3dp_sr_tc_input(const float* x, int N, int C, int h, int w, int size, void* y_f16, r3dp_stream_t stream);
+size_t r3dp_sr_tc_scratch_bytes(int N, int O, int H, int W);
+int r3dp_sr_tc_layer(const void* x_f16, const void* wp_f16, const float* bias, int N, int Nw, int I, int O, int H, int W,
+                     int up, void* y_f16, void* scratch, r3dp_stream_t stream);
+int r3dp_sr_tc_torgb(const void* x_f16, const float* wrgb, const float* brgb, const float* img_prev, int N, int Nw, int C,
+                     int H, int W, float* img_out, r3dp_stream_t stream);
+int r3dp_sr_tc_last_layer(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
+                          const float* img_prev, int N, int Nw, int I, int H, int W, float* img_out, r3dp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,80 @@
+"""Tensor-core execution of SuperresolutionHybrid8XDC.forward (superresolution.py:348-359): the same layers as the
+fp32 modules in superresolution.py, run as tcgen05 implicit GEMMs (csrc/sr_tc.cu) on NHWC fp16 activations with fp32
+accumulation.  Weights are folded (modulated + demodulated) in fp32 per sample, exactly as the reference does, and only
+then rounded to fp16.  Stated tolerance vs the fp32 reference: see tests/test_gpu_parity.py::test_sr_full_tc."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _capi as capi
+
+
+def available() -> bool:
+    return hasattr(capi.lib(), 'r3dp_sr_tc_layer')
+
+
+def _pack(layer, w_lat: torch.Tensor) -> torch.Tensor:
+    """SynthesisLayer -> packed fp16 weights [Nw,9,O,Ipad]."""
+    wf = layer.folded_weight(w_lat)                                  # [Nw,O,I,3,3] fp32
+    Nw, O, I = wf.shape[:3]
+    Ip = (I + 63) // 64 * 64
+    out = torch.empty(Nw, 9, O, Ip, device=wf.device, dtype=torch.float16)
+    capi.check(capi.lib().r3dp_sr_tc_pack_weights(capi.ptr(wf), Nw, O, I, capi.ptr(out, torch.float16), capi.stream()))
+    return out
+
+
+def layer(x16: torch.Tensor, lay, wp: torch.Tensor, up: int) -> torch.Tensor:
+    """x16 [N,H,W,Ipad] fp16 NHWC -> [N,H*up,W*up,O] fp16 NHWC."""
+    N, H, W, _ = x16.shape
+    O, Nw = lay.out_channels, wp.shape[0]
+    L = capi.lib()
+    y = torch.empty(N, H * up, W * up, O, device=x16.device, dtype=torch.float16)
+    scratch = None
+    if up == 2:
+        scratch = torch.empty(L.r3dp_sr_tc_scratch_bytes(N, O, H, W), device=x16.device, dtype=torch.uint8)
+    with capi.region('sr_conv'):
+        capi.check(L.r3dp_sr_tc_layer(capi.ptr(x16, torch.float16), capi.ptr(wp, torch.float16), capi.ptr(capi.f32(lay.bias)), N, Nw,
+                                      lay.in_channels, O, H, W, up, capi.ptr(y, torch.float16), capi.ptr(scratch, torch.uint8), capi.stream()))
+    return y
+
+
+def to_nhwc_f16(x: torch.Tensor, size: int) -> torch.Tensor:
+    """fp32 NCHW [N,C,h,w] -> (bilinear to size) -> NHWC fp16 [N,size,size,Cpad]."""
+    x = capi.f32(x)
+    N, Cc, h, w = x.shape
+    Cp = (Cc + 63) // 64 * 64
+    y = torch.empty(N, size, size, Cp, device=x.device, dtype=torch.float16)
+    capi.check(capi.lib().r3dp_sr_tc_input(capi.ptr(x), N, Cc, h, w, size, capi.ptr(y, torch.float16), capi.stream()))
+    return y
+
+
+def forward(sr, rgb: torch.Tensor, x: torch.Tensor, ws3: torch.Tensor, shared_styles: Optional[bool] = None) -> torch.Tensor:
+    """rgb [N,3,h,w], x [N,C,h,w] (fp32 NCHW, h <= 128), ws3 [N,3,512] -> [N,3,512,512] fp32."""
+    from .superresolution import SuperresolutionHybrid8XDC
+    L = capi.lib()
+    N = x.shape[0]
+    if shared_styles is None:
+        shared_styles = N == 1 or getattr(sr, 'assume_shared_styles', False)
+    wsel = ws3[:1] if shared_styles else ws3
+    Nw = wsel.shape[0]
+    b0, b1 = sr.block0, sr.block1
+    with capi.region('sr_prep'):
+        x0 = to_nhwc_f16(x, sr.input_resolution)
+        rgb0 = SuperresolutionHybrid8XDC._resize(rgb, sr.input_resolution) if rgb.shape[-1] != sr.input_resolution else capi.f32(rgb)
+        wp = [_pack(b0.conv0, wsel[:, 0]), _pack(b0.conv1, wsel[:, 1]), _pack(b1.conv0, wsel[:, 0]), _pack(b1.conv1, wsel[:, 1])]
+        wrgb0, wrgb1 = b0.torgb.folded_weight(wsel[:, 2]), b1.torgb.folded_weight(wsel[:, 2])
+    a0 = layer(x0, b0.conv0, wp[0], 2)
+    a1 = layer(a0, b0.conv1, wp[1], 1)
+    img1 = torch.empty(N, 3, 256, 256, device=x.device)
+    with capi.region('sr_torgb'):
+        capi.check(L.r3dp_sr_tc_torgb(capi.ptr(a1, torch.float16), capi.ptr(wrgb0), capi.ptr(capi.f32(b0.torgb.bias)), capi.ptr(rgb0), N, Nw,
+                                      256, 256, 256, capi.ptr(img1), capi.stream()))
+    a2 = layer(a1, b1.conv0, wp[2], 2)
+    out = torch.empty(N, 3, 512, 512, device=x.device)
+    with capi.region('sr_conv'):
+        capi.check(L.r3dp_sr_tc_last_layer(capi.ptr(a2, torch.float16), capi.ptr(wp[3], torch.float16), capi.ptr(capi.f32(b1.conv1.bias)),
+                                           capi.ptr(wrgb1), capi.ptr(capi.f32(b1.torgb.bias)), capi.ptr(img1), N, Nw, 128, 512, 512,
+                                           capi.ptr(out), capi.stream()))
+    return out

@@ -168,14 +168,14 @@ class SuperresolutionHybrid8XDC(torch.nn.Module):
         """rgb [N,3,h,w], x [N,channels,h,w], ws [N,>=1,512] -> [N,3,512,512]   (superresolution.py:348-359)."""
         block_kwargs = {k: v for k, v in block_kwargs.items() if k != 'sr_mode'}
         ws = ws[:, -1:, :].repeat(1, 3, 1)
-        if x.shape[-1] != self.input_resolution:
-            if x.shape[-1] > self.input_resolution:
-                raise NotImplementedError('down-scaling inputs (antialiased) is not on the Real3D path')
-            x = self._resize(x, self.input_resolution)
-            rgb = self._resize(rgb, self.input_resolution)
+        if x.shape[-1] > self.input_resolution:
+            raise NotImplementedError('down-scaling inputs (antialiased) is not on the Real3D path')
         if self.sr_mode == 'tc':
             from . import sr_tc
             return sr_tc.forward(self, rgb, x, ws)
+        if x.shape[-1] != self.input_resolution:
+            x = self._resize(x, self.input_resolution)
+            rgb = self._resize(rgb, self.input_resolution)
         x, rgb = self.block0(x, rgb, ws, **block_kwargs)
         x, rgb = self.block1(x, rgb, ws, **block_kwargs)
         return rgb

@@ -123,7 +123,8 @@ def test_sr_layers_vs_reference(golden):
     x, w = g['x'].to(DEV), g['w'].to(DEV)
     for name, up in (('up', 2), ('same', 1)):
         lay = r3.SynthesisLayer(8, 16, w_dim=512, resolution=12 * up, up=up)
-        lay.load_state_dict({k[len(name) + 1:]: v for k, v in g.items() if k.startswith(name + '.') and not k.endswith('.y')}, strict=True)
+        lay.load_state_dict({k[len(name) + 1:]: torch.as_tensor(v) for k, v in g.items() if k.startswith(name + '.') and not k.endswith('.y')},
+                            strict=True)
         y = lay.to(DEV)(x, w, noise_mode='none')
         assert _maxdiff(y, g[name + '.y']) < 1e-4
     trgb = r3.ToRGBLayer(8, 3, w_dim=512)
@@ -170,3 +171,71 @@ def test_render_head_vs_oracle_with_per_sample_styles():
     ref_sr = orc.superres(fimg[:, :3], fimg, ws, srp)
     got = head.superresolution(fimg[:, :3].contiguous().to(DEV), fimg.to(DEV), ws.to(DEV), noise_mode='none')
     assert _maxdiff(got, ref_sr) < 1e-3 * float(ref_sr.abs().max())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tensor-core SR path (tcgen05, fp16 operands / fp32 accumulate).  Stated tolerances:
+#   single layer vs fp32 math on the SAME fp16-rounded operands: 2e-3 * max|y|  (only the fp16 rounding of the output differs)
+#   full SR image vs the fp32 reference: max-abs < 2e-2 on images of range ~[-6, 6] and PSNR > 60 dB
+# ---------------------------------------------------------------------------------------------------------------------
+def _tc_layer_case(up, I, O, H, W, N=2, shared=False, seed=0):
+    from real3dportrait_b200 import sr_tc
+    g = torch.Generator().manual_seed(seed)
+    lay = r3.SynthesisLayer(I, O, w_dim=512, resolution=W * up, up=up)
+    with torch.no_grad():
+        lay.bias.copy_(0.1 * torch.randn(O, generator=g))
+        lay.affine.bias.copy_(1 + 0.1 * torch.randn(I, generator=g))
+    lay = lay.to(DEV)
+    x = torch.randn(N, I, H, W, generator=g)
+    w = torch.randn(1 if shared else N, 512, generator=g)
+    x16 = x.half()
+    wp = sr_tc._pack(lay, w.to(DEV))                                         # [Nw,9,O,Ip] fp16, folded in fp32 first
+    Ip = wp.shape[-1]
+    xin = torch.zeros(N, H, W, Ip, dtype=torch.float16)
+    xin[..., :I] = x16.permute(0, 2, 3, 1)
+    y = sr_tc.layer(xin.to(DEV), lay, wp, up)                                # [N,H*up,W*up,O] fp16
+    torch.cuda.synchronize()
+    # oracle on the same fp16-rounded operands, fp32 arithmetic
+    wf16 = wp.float().cpu()[..., :I].reshape(-1, 3, 3, O, I).permute(0, 3, 4, 1, 2).contiguous()   # [Nw,O,I,3,3]
+    if shared:
+        wf16 = wf16.expand(N, -1, -1, -1, -1)
+    ref = orc.lrelu_gain(orc.mod_conv(x16.float(), wf16, up), lay.bias.detach().cpu())
+    got = y.float().cpu().permute(0, 3, 1, 2)
+    return got, ref
+
+
+@pytest.mark.parametrize('up,I,O,H,W,shared', [(1, 64, 128, 6, 128, False), (1, 256, 256, 5, 256, True), (2, 32, 128, 5, 128, False),
+                                               (2, 256, 128, 4, 256, False)])
+def test_tc_layer_vs_oracle(up, I, O, H, W, shared):
+    got, ref = _tc_layer_case(up, I, O, H, W, shared=shared)
+    assert got.shape == ref.shape
+    err = _maxdiff(got, ref)
+    assert err < 2e-3 * float(ref.abs().max()), (err, float(ref.abs().max()))
+
+
+def test_sr_full_tc_vs_reference(golden):
+    """BASELINE config 3 at N=1 through the tensor-core path, against the reference's fp32 image."""
+    fimg = orc.feature_image(golden('render_full48')['rgb'], 64).to(DEV)
+    sr = r3.SuperresolutionHybrid8XDC(channels=32, img_resolution=512, sr_num_fp16_res=0, sr_antialias=True, sr_mode='tc')
+    sr.load_state_dict(syn.make_sr_params(seed=5), strict=True)
+    img = sr.to(DEV)(fimg[:, :3], fimg, torch.ones(1, 14, 512, device=DEV), noise_mode='none')
+    ref = golden('sr_full')['image']
+    err = _maxdiff(img, ref)
+    mse = float(((img.cpu() - ref) ** 2).mean())
+    psnr = 10 * torch.log10(torch.tensor(float(ref.max() - ref.min()) ** 2 / mse)).item()
+    print(f'tc SR: max-abs {err:.3e} on range [{float(ref.min()):.2f},{float(ref.max()):.2f}], PSNR {psnr:.1f} dB')
+    assert err < 2e-2 and psnr > 60.0, (err, psnr)
+
+
+def test_sr_tc_per_sample_styles_vs_fp32_path():
+    """N=2 with different w per sample: tensor-core path vs the exact-fp32 CUDA path of this library."""
+    g = torch.Generator().manual_seed(9)
+    fimg = (torch.rand(2, 32, 64, 64, generator=g) * 2 - 1).to(DEV)
+    ws = (1 + 0.3 * torch.randn(2, 14, 512, generator=g)).to(DEV)
+    outs = {}
+    for mode in ('fp32', 'tc'):
+        sr = r3.SuperresolutionHybrid8XDC(channels=32, img_resolution=512, sr_num_fp16_res=0, sr_antialias=True, sr_mode=mode)
+        sr.load_state_dict(syn.make_sr_params(seed=5), strict=True)
+        outs[mode] = sr.to(DEV)(fimg[:, :3].contiguous(), fimg, ws, noise_mode='none')
+    err, rng = _maxdiff(outs['tc'], outs['fp32']), float(outs['fp32'].abs().max())
+    assert err < 5e-3 * rng, (err, rng)

@@ -152,6 +152,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--sr-mode', default=None, choices=[None, 'fp32', 'tc'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying one CUDA graph per step')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == 'reference':
@@ -173,7 +174,7 @@ def main():
     _capi.check(L.r3dp_device_info(None, None, None))
 
     sr_mode = args.sr_mode or engine.default_sr_mode()
-    eng = engine.FrameEngine(batch=args.batch, sr_mode=sr_mode, device=dev, world=world, rank=rank, dist=dist)
+    eng = engine.FrameEngine(batch=args.batch, sr_mode=sr_mode, device=dev, world=world, rank=rank, dist=dist, use_graph=not args.no_graph)
     eng.load_params(syn.make_decoder_params(seed=4), syn.make_sr_params(seed=5))
     B, P = args.batch, max(args.pool, args.batch)
     # resident inputs: every rank owns its own shard of the clip (different seeds per rank)
@@ -204,6 +205,8 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = L.r3dp_launch_count() - launches0
+    if eng.graph is not None:                       # kernels replayed from the captured graph are not re-counted by the library
+        launches += eng.launches_per_step * args.steps
     clocks = sampler.summary()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if dist is not None:
@@ -218,10 +221,14 @@ def main():
     # ---- end-to-end through the public call with HOST buffers (pinned), H2D + D2H inside the timed region
     h_planes = planes[:B].cpu().pin_memory(); h_cams = cams[:B].cpu().pin_memory(); h_u = u_c[:B].cpu().pin_memory()
     h_out = torch.empty(B, 3, 512, 512, dtype=torch.float32).pin_memory()
+    sp, sc, su = eng.static_inputs()
     def e2e_step():
-        dp, dc, du = h_planes.to(dev, non_blocking=True), h_cams.to(dev, non_blocking=True), h_u.to(dev, non_blocking=True)
-        out = eng.step(dp, dc, du)
-        h_out.copy_(out[:B] if out.shape[0] >= B else out, non_blocking=True)
+        if sp is not None:                       # graph mode: H2D lands directly in the step's static input buffers
+            sp.copy_(h_planes, non_blocking=True); sc.copy_(h_cams, non_blocking=True); su.copy_(h_u, non_blocking=True)
+            out = eng.step(sp, sc, su)
+        else:
+            out = eng.step(h_planes.to(dev, non_blocking=True), h_cams.to(dev, non_blocking=True), h_u.to(dev, non_blocking=True))
+        h_out.copy_(out[rank * B:(rank + 1) * B] if out.shape[0] > B else out, non_blocking=True)
     for _ in range(3):
         e2e_step()
     barrier()
@@ -251,7 +258,7 @@ def main():
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32 render; SR ' + ('f16 operands / f32 accumulate (tcgen05)' if sr_mode == 'tc' else 'f32'),
         'data': 'synthetic',
-        'config': config_of(args, {'sr_mode': sr_mode, 'l2_policy': f'inputs larger than L2: {P} distinct resident frames/GPU '
+        'config': config_of(args, {'sr_mode': sr_mode, 'cuda_graph': not args.no_graph, 'l2_policy': f'inputs larger than L2: {P} distinct resident frames/GPU '
                                    f'({P * 25.2:.0f} MB) cycled', 'timing': 'CUDA events on the launch stream, barrier+sync both sides, max over ranks'}),
         'clocks': clocks, 'gpu_launches': int(launches),
         'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': ksteps},

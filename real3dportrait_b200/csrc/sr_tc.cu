@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace r3dp {
 namespace tc {
@@ -231,10 +232,14 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        rgb[0] = fmaf(f[j], s_wrgb[c0 + j], rgb[0]);
-                        rgb[1] = fmaf(f[j], s_wrgb[BN + c0 + j], rgb[1]);
-                        rgb[2] = fmaf(f[j], s_wrgb[2 * BN + c0 + j], rgb[2]);
+                    for (int c = 0; c < 3; ++c) {
+                        const float4* w4 = reinterpret_cast<const float4*>(s_wrgb + c * BN + c0);
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 w = w4[j4];
+                            rgb[c] = fmaf(f[4 * j4 + 0], w.x, rgb[c]); rgb[c] = fmaf(f[4 * j4 + 1], w.y, rgb[c]);
+                            rgb[c] = fmaf(f[4 * j4 + 2], w.z, rgb[c]); rgb[c] = fmaf(f[4 * j4 + 3], w.w, rgb[c]);
+                        }
                     }
                 }
             }
@@ -273,6 +278,284 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     }
 }
 
+// =====================================================================================================================
+// conv_tc2_kernel<R>: persistent implicit-GEMM conv, R output rows (R x 128 pixels) x 128 couts per tile.
+//
+// Why: the v1 kernel above re-reads A (activations) once per tap and B (weights) once per 128-pixel tile: 32 MAC per L2
+// byte, i.e. L2-bandwidth-bound at ~1/3 of the tensor peak (measured 436 TFLOP/s).  Here
+//   * an input ROW STRIP {64 ch, 130 px} is loaded once per (64-channel chunk) and serves all horizontal taps: the UMMA
+//     smem descriptor simply starts 128 B x shift later (same absolute-address 128-byte swizzle TMA wrote), and serves
+//     the R output rows that touch it vertically;
+//   * every weight tile {64 ch, 128 couts} of a tap is used by R MMA groups (one per output row) before it is released;
+//   => (R+2) x 16.6 KB + 9 x 16 KB per 9R MMA groups: 89 MAC/B at R=2, 153 MAC/B at R=4.
+// Two mbarrier rings (A strips, B taps) are filled by one TMA lane in exactly the order the MMA lane consumes them;
+// accumulators (R x 128 TMEM columns) are double-buffered when they fit (R <= 2) so the epilogue overlaps the next tile.
+// =====================================================================================================================
+constexpr int A2_ROWS = 130, A2_BYTES = A2_ROWS * 128, A2_SLOT = 17408;       // 17 x 1024: every slot keeps the swizzle alignment
+struct Taps2 {
+    int n, ngroups;                 // taps sorted by (dy, dx); group = taps sharing dy
+    int dyi[9], shift[9], widx[9];  // group index, horizontal shift (dx - dx_min, in pixels), weight tap index
+    int gstart[4];                  // first tap of each group (+ sentinel)
+    int dy_min;
+};
+struct Conv2Args {
+    Taps2 taps;
+    int k_chunks, tiles_x, row_groups, rows, n_blocks, n_images, total_tiles;
+    int w_shared, mode, base_off_mode;
+    __half* out; int out_H, out_W, out_C, oy_mul, oy_off, ox_mul, ox_off;
+    const float* bias; const float* wrgb; const float* brgb; const float* img_prev; float* img_out;
+};
+
+template <int R> struct Cfg2 {
+    static constexpr int NA = (R >= 4) ? 8 : (R == 2 ? 5 : 4);
+    static constexpr int NB = (R >= 4) ? 5 : 8;
+    static constexpr int NACC = (R * BN * 2 <= 512) ? 2 : 1;
+    static constexpr int TMEM_COLS = (R * BN * NACC <= 128) ? 128 : (R * BN * NACC <= 256 ? 256 : 512);
+    static constexpr int SMEM = NA * A2_SLOT + NB * B_BYTES + 1024 + 4096;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_shift(uint32_t saddr, int base_off) {
+    return umma_desc_sw128(saddr) | ((uint64_t)(base_off & 7) << 49);
+}
+
+template <int R>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB, const Conv2Args a) {
+    using C = Cfg2<R>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + C::NA * A2_SLOT;
+    uint8_t* tail = b_ring + C::NB * B_BYTES;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* a_empty = a_full + C::NA;
+    uint64_t* b_full = a_empty + C::NA;
+    uint64_t* b_empty = b_full + C::NB;
+    uint64_t* acc_full = b_empty + C::NB;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* s_bias = reinterpret_cast<float*>(tail + 512);                    // [n_blocks<=2][128]
+    float* s_wrgb = s_bias + 256;                                            // [3][128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int DY = a.taps.ngroups, NS = R + DY - 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < C::NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {
+        const int t = threadIdx.x - 64;
+        for (int e = t; e < a.n_blocks * BN && e < 256; e += 128) s_bias[e] = a.bias ? a.bias[e] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile index -> (image n, cout block, row group, x block); x fastest so neighbouring CTAs share strips in L2
+    auto decode = [&](int tile, int& n, int& nblk, int& row0, int& col0) {
+        const int xb = tile % a.tiles_x; int r = tile / a.tiles_x;
+        const int rg = r % a.row_groups; r /= a.row_groups;
+        nblk = r % a.n_blocks; n = r / a.n_blocks;
+        row0 = rg * R; col0 = xb * BM;
+    };
+
+    if (warp == 0) {
+        // ===== TMA producer (one lane): strips and taps in consumption order =====
+        if (lane == 0) {
+            uint32_t aq = 0, bq = 0;                                         // running strip / tap sequence numbers
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                int n, nblk, row0, col0; decode(tile, n, nblk, row0, col0);
+                const int wn = a.w_shared ? 0 : n;
+                for (int kc = 0; kc < a.k_chunks; ++kc) {
+                    for (int d = 0; d < DY; ++d) {
+                        const int s_lo = d == 0 ? 0 : R - 1 + d, s_hi = R - 1 + d;
+                        for (int s = s_lo; s <= s_hi; ++s, ++aq) {
+                            const int slot = aq % C::NA;
+                            mbar_wait(&a_empty[slot], ((aq / C::NA) & 1) ^ 1);
+                            mbar_expect_tx(&a_full[slot], A2_BYTES);
+                            tma_load_4d(a_ring + slot * A2_SLOT, &tmA, &a_full[slot], kc * BK, col0 - 1, row0 + a.taps.dy_min + s, n);
+                        }
+                        for (int t = a.taps.gstart[d]; t < a.taps.gstart[d + 1]; ++t, ++bq) {
+                            const int slot = bq % C::NB;
+                            mbar_wait(&b_empty[slot], ((bq / C::NB) & 1) ^ 1);
+                            mbar_expect_tx(&b_full[slot], B_BYTES);
+                            tma_load_4d(b_ring + slot * B_BYTES, &tmB, &b_full[slot], kc * BK, nblk * BN, a.taps.widx[t], wn);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        uint32_t aq = 0, bq = 0, it = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it % C::NACC;
+            mbar_wait(&acc_empty[buf], (((it / C::NACC) & 1) ^ 1));
+            tc_fence_after();
+            const uint32_t acc0 = tmem_base + buf * (R * BN);
+            for (int kc = 0; kc < a.k_chunks; ++kc) {
+                const uint32_t a_base = aq;                                   // sequence number of strip 0 of this chunk
+                for (int d = 0; d < DY; ++d) {
+                    const int s_lo = d == 0 ? 0 : R - 1 + d, s_hi = R - 1 + d;
+                    for (int s = s_lo; s <= s_hi; ++s, ++aq) mbar_wait(&a_full[aq % C::NA], (aq / C::NA) & 1);
+                    for (int t = a.taps.gstart[d]; t < a.taps.gstart[d + 1]; ++t, ++bq) {
+                        const int bslot = bq % C::NB;
+                        mbar_wait(&b_full[bslot], (bq / C::NB) & 1);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint64_t db = umma_desc_sw128(smem_u32(b_ring + bslot * B_BYTES));
+                            const int sh = a.taps.shift[t];
+#pragma unroll
+                            for (int j = 0; j < R; ++j) {
+                                const uint32_t sq = a_base + j + d;
+                                const uint32_t sa = smem_u32(a_ring + (sq % C::NA) * A2_SLOT) + 128 * sh;
+                                const uint64_t da = umma_desc_sw128_shift(sa, a.base_off_mode ? sh : 0);
+#pragma unroll
+                                for (int k = 0; k < BK / UMMA_K; ++k)
+                                    tc_mma_f16(acc0 + j * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kc | t | k) != 0);
+                            }
+                            tc_commit(&b_empty[bslot]);
+                        }
+                        __syncwarp();
+                    }
+                    // strips no later group needs: strip d after group d; everything left after the last group
+                    if (lane == 0) {
+                        if (d < DY - 1) tc_commit(&a_empty[(a_base + d) % C::NA]);
+                        else for (int s = DY - 1; s < NS; ++s) tc_commit(&a_empty[(a_base + s) % C::NA]);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) tc_commit(&acc_full[buf]);
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue =====
+        const int q = warp & 3, m = q * 32 + lane;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+            int n, nblk, row0, col0; decode(tile, n, nblk, row0, col0);
+            const int wn = a.w_shared ? 0 : n;
+            const int buf = it % C::NACC;
+            if (a.mode == kToRgbFinal) {
+                // all four epilogue warps must be done with the previous tile's s_wrgb before it is overwritten
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int e = threadIdx.x - 64; e < 3 * BN; e += 128) s_wrgb[e] = a.wrgb[(size_t)wn * 3 * BN + e];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            mbar_wait(&acc_full[buf], (it / C::NACC) & 1);
+            tc_fence_after();
+            const int gcol = col0 + m, X = gcol * a.ox_mul + a.ox_off;
+#pragma unroll 1
+            for (int j = 0; j < R; ++j) {
+                const int row = row0 + j;
+                const int Y = row * a.oy_mul + a.oy_off;
+                const bool in_img = (row < a.rows) && (Y < a.out_H) && (X < a.out_W);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (R * BN) + j * BN;
+                float rgb[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tc_ld32(taddr + c0, r);
+                    if (a.mode == kStoreRaw) {
+                        if (in_img) {
+                            uint4* dst = reinterpret_cast<uint4*>(a.out + (((size_t)n * a.out_H + Y) * a.out_W + X) * a.out_C + nblk * BN + c0);
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) {
+                                __half2 h0 = __floats2half2_rn(__uint_as_float(r[8 * v + 0]), __uint_as_float(r[8 * v + 1]));
+                                __half2 h1 = __floats2half2_rn(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3]));
+                                __half2 h2 = __floats2half2_rn(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5]));
+                                __half2 h3 = __floats2half2_rn(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7]));
+                                uint4 pk;
+                                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                                dst[v] = pk;
+                            }
+                        }
+                    } else {
+                        float f[32];
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) {
+                            float v = __uint_as_float(r[jj]) + s_bias[nblk * BN + c0 + jj];
+                            f[jj] = (v < 0.f ? v * 0.2f : v) * 1.4142135623730951f;
+                        }
+                        if (a.mode == kStoreAct) {
+                            if (in_img) {
+                                uint4* dst = reinterpret_cast<uint4*>(a.out + (((size_t)n * a.out_H + Y) * a.out_W + X) * a.out_C + nblk * BN + c0);
+#pragma unroll
+                                for (int v = 0; v < 4; ++v) {
+                                    __half2 h0 = __floats2half2_rn(f[8 * v + 0], f[8 * v + 1]), h1 = __floats2half2_rn(f[8 * v + 2], f[8 * v + 3]);
+                                    __half2 h2 = __floats2half2_rn(f[8 * v + 4], f[8 * v + 5]), h3 = __floats2half2_rn(f[8 * v + 6], f[8 * v + 7]);
+                                    uint4 pk;
+                                    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                                    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                                    dst[v] = pk;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const float4* w4 = reinterpret_cast<const float4*>(s_wrgb + c * BN + c0);
+#pragma unroll
+                                for (int j4 = 0; j4 < 8; ++j4) {
+                                    const float4 w = w4[j4];
+                                    rgb[c] = fmaf(f[4 * j4 + 0], w.x, rgb[c]); rgb[c] = fmaf(f[4 * j4 + 1], w.y, rgb[c]);
+                                    rgb[c] = fmaf(f[4 * j4 + 2], w.z, rgb[c]); rgb[c] = fmaf(f[4 * j4 + 3], w.w, rgb[c]);
+                                }
+                            }
+                        }
+                    }
+                }
+                if (a.mode == kToRgbFinal && in_img) {
+                    const int h = a.out_H / 2, w = a.out_W / 2;
+                    const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float acc = 0.f;
+                        if (a.img_prev) {
+                            const float* ip = a.img_prev + ((size_t)n * 3 + c) * h * w;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int zy = Y + u - 2;
+                                if (zy < 0 || (zy & 1) || (zy >> 1) >= h) continue;
+                                float rowv = 0.f;
+#pragma unroll
+                                for (int v = 0; v < 4; ++v) {
+                                    const int zx = X + v - 2;
+                                    if (zx < 0 || (zx & 1) || (zx >> 1) >= w) continue;
+                                    rowv = fmaf(k4[v], __ldg(ip + (size_t)(zy >> 1) * w + (zx >> 1)), rowv);
+                                }
+                                acc = fmaf(k4[u], rowv, acc);
+                            }
+                        }
+                        a.img_out[(((size_t)n * 3 + c) * a.out_H + Y) * a.out_W + X] = rgb[c] + a.brgb[c] + acc;
+                    }
+                }
+            }
+            // this warp is done reading the accumulator buffer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    }
+}
+
 // ---- helpers around the GEMMs ---------------------------------------------------------------------------------------
 // wf fp32 [Nw][O][I][3][3] -> packed fp16 [Nw][9][O][Ip]  (zero for i >= I)
 __global__ void pack_weights_kernel(const float* __restrict__ wf, int Nw, int O, int I, int Ip, __half* __restrict__ out) {
@@ -305,68 +588,134 @@ __global__ void resize_to_nhwc_f16_kernel(const float* __restrict__ x, int N, in
 }
 
 // last column X = 2W of the transposed-conv result (the only part of the (2H+1)x(2W+1) grid the 128-wide GEMM tiles do not
-// cover): yb[n][Y][2W][co] = sum_{ci, ky == Y (mod 2)} x[(Y-ky)/2][W-1][ci] * w[ky*3+2][co][ci].  One warp per (Y, co).
-__global__ void upconv_edge_kernel(const __half* __restrict__ x, const __half* __restrict__ wp, int H, int W, int Cp, int O,
-                                   int w_shared, __half* __restrict__ yb) {
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.y;
+// cover): yb[n][Y][2W][co] = sum_{ci, ky == Y (mod 2)} x[(Y-ky)/2][W-1][ci] * w[ky*3+2][co][ci].
+// CTA = 16 consecutive rows Y of one image: the <= 10 input pixels they touch are staged in smem, each warp walks the couts
+// with its three weight rows (kx = 2 column of the kernel) in registers.  Cp <= 256.
+constexpr int kEdgeRows = 16;
+__global__ void __launch_bounds__(256) upconv_edge_kernel(const __half* __restrict__ x, const __half* __restrict__ wp, int H, int W, int Cp, int O,
+                                                          int w_shared, __half* __restrict__ yb) {
+    __shared__ __align__(16) __half s_x[kEdgeRows / 2 + 2][256];
+    const int n = blockIdx.y, Y0 = blockIdx.x * kEdgeRows;
     const int BH = 2 * H + 1, BW = 2 * W + 1;
-    if (gw >= BH * O) return;
-    const int Y = gw / O, co = gw - Y * O;
     const int wn = w_shared ? 0 : n;
-    float acc = 0.f;
-    for (int ky = (Y & 1); ky < 3; ky += 2) {
-        const int iy = (Y - ky) >> 1;
-        if ((Y - ky) < 0 || iy >= H) continue;
-        const __half* xp = x + (((size_t)n * H + iy) * W + (W - 1)) * Cp;
-        const __half* wq = wp + (((size_t)wn * 9 + ky * 3 + 2) * O + co) * Cp;
-        for (int c = lane; c < Cp; c += 32) acc = fmaf(__half2float(xp[c]), __half2float(wq[c]), acc);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int iy0 = Y0 / 2 - 1;                                              // first input row any of these Y can touch
+    for (int e = threadIdx.x; e < (kEdgeRows / 2 + 2) * Cp; e += 256) {
+        const int r = e / Cp, c = e - r * Cp, iy = iy0 + r;
+        s_x[r][c] = (iy >= 0 && iy < H) ? x[(((size_t)n * H + iy) * W + (W - 1)) * Cp + c] : __float2half(0.f);
     }
+    __syncthreads();
+    const int c0 = lane * 8;
+    const bool on = c0 < Cp;
+    for (int co = warp; co < O; co += 8) {
+        float wv[3][8];
 #pragma unroll
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) yb[(((size_t)n * BH + Y) * BW + 2 * W) * O + co] = __float2half_rn(acc);
+        for (int ky = 0; ky < 3; ++ky) {
+            uint4 raw = make_uint4(0, 0, 0, 0);
+            if (on) raw = __ldg(reinterpret_cast<const uint4*>(wp + (((size_t)wn * 9 + ky * 3 + 2) * O + co) * Cp + c0));
+            const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); wv[ky][2 * j] = f.x; wv[ky][2 * j + 1] = f.y; }
+        }
+#pragma unroll 1
+        for (int yy = 0; yy < kEdgeRows; ++yy) {
+            const int Y = Y0 + yy;
+            if (Y >= BH) break;
+            float acc = 0.f;
+            for (int ky = (Y & 1); ky < 3; ky += 2) {
+                const int r = ((Y - ky) >> 1) - iy0;                          // (Y-ky) is even; rows outside the image hold zeros
+                if ((Y - ky) < 0) continue;
+                if (on) {
+                    const uint4 raw = *reinterpret_cast<const uint4*>(&s_x[r][c0]);
+                    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = __half22float2(h[j]);
+                        acc = fmaf(f.x, wv[ky][2 * j], acc); acc = fmaf(f.y, wv[ky][2 * j + 1], acc);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) yb[(((size_t)n * BH + Y) * BW + 2 * W) * O + co] = __float2half_rn(acc);
+        }
+    }
 }
 
 // FIR 4x4 (pad 1, gain 4) + bias + lrelu*sqrt2 on the transposed-conv result: yb [N][2H+1][2W+1][C] fp16 -> y [N][2H][2W][C] fp16.
-// One thread = one output pixel x 8 channels (16-byte vectors); neighbouring threads share taps through L1.
+// HBM-bound (read 1x + write 1x).  A thread owns two adjacent output columns x 8 channels and MARCHES DOWN a segment of rows:
+// per input row it loads the 5 pixels its two outputs touch (16-byte vectors; the overlap with its neighbours is served by
+// L1), reduces them horizontally, and keeps the last four horizontal results in registers for the vertical pass - so every
+// yb element leaves L2 once instead of once per output row it contributes to.
+constexpr int kFirSeg = 32;
+__device__ __forceinline__ void fir_load8(const __half* p, bool ok, float* f) {
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    if (ok) raw = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 v = __half22float2(h[j]); f[2 * j] = v.x; f[2 * j + 1] = v.y; }
+}
 __global__ void __launch_bounds__(256) fir_bias_lrelu_f16_kernel(const __half* __restrict__ yb, const float* __restrict__ bias, int N, int OH,
                                                                  int OW, int C, __half* __restrict__ y) {
-    const int cv = C / 8;
+    const int cv = C / 8, pairs = OW / 2, segs = (OH + kFirSeg - 1) / kFirSeg;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)N * OH * OW * cv) return;
-    const int c8 = (int)(idx % cv); const int ox = (int)((idx / cv) % OW); const int oy = (int)((idx / ((long long)cv * OW)) % OH);
-    const int n = (int)(idx / ((long long)cv * OW * OH));
+    if (idx >= (long long)N * segs * pairs * cv) return;
+    const int c8 = (int)(idx % cv); const int xp = (int)((idx / cv) % pairs); const int seg = (int)((idx / ((long long)cv * pairs)) % segs);
+    const int n = (int)(idx / ((long long)cv * pairs * segs));
     const int BH = OH + 1, BW = OW + 1;
+    const int ox0 = xp * 2, oy0 = seg * kFirSeg, oy1 = min(oy0 + kFirSeg, OH);
     const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};
-    float acc[8];
+    float b[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 8; ++j) b[j] = bias[c8 * 8 + j];
+    float win[4][16];                                                        // last four horizontally-filtered rows: [row][2 outputs x 8 ch]
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const int yy = oy + u - 1;
-        if ((unsigned)yy >= (unsigned)BH) continue;
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const int xx = ox + v - 1;
-            if ((unsigned)xx >= (unsigned)BW) continue;
-            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(yb + (((size_t)n * BH + yy) * BW + xx) * C + c8 * 8));
-            const __half2* h = reinterpret_cast<const __half2*>(&raw);
-            const float wgt = k4[u] * k4[v];
+        for (int j = 0; j < 16; ++j) win[r][j] = 0.f;
+    const __half* base = yb + (size_t)n * BH * BW * C + c8 * 8;
+    // input rows oy0-1 .. oy1+1 ; output row oy is complete once input row oy+2 has been pushed
+#pragma unroll 4
+    for (int yy = oy0 - 1; yy <= oy1 + 1; ++yy) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h[j]);
-                acc[2 * j] = fmaf(wgt, f.x, acc[2 * j]); acc[2 * j + 1] = fmaf(wgt, f.y, acc[2 * j + 1]);
+        for (int j = 0; j < 16; ++j) { win[0][j] = win[1][j]; win[1][j] = win[2][j]; win[2][j] = win[3][j]; win[3][j] = 0.f; }
+        if ((unsigned)yy < (unsigned)BH) {
+            const __half* rowp = base + (size_t)yy * BW * C;
+            float px[8];
+#pragma unroll
+            for (int v = 0; v < 5; ++v) {                                    // pixel ox0-1+v feeds output 0 with tap v and output 1 with tap v-1
+                const int xx = ox0 - 1 + v;
+                fir_load8(rowp + (size_t)xx * C, (unsigned)xx < (unsigned)BW, px);
+                if (v < 4) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) win[3][j] = fmaf(k4[v], px[j], win[3][j]);
+                }
+                if (v > 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) win[3][8 + j] = fmaf(k4[v - 1], px[j], win[3][8 + j]);
+                }
             }
         }
-    }
-    uint4 pk; __half2* ph = reinterpret_cast<__half2*>(&pk);
+        const int oy = yy - 2;
+        if (oy >= oy0 && oy < oy1) {
+            uint4 pk[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float a0 = acc[2 * j] + bias[c8 * 8 + 2 * j], a1 = acc[2 * j + 1] + bias[c8 * 8 + 2 * j + 1];
-        a0 = (a0 < 0.f ? a0 * 0.2f : a0) * 1.4142135623730951f; a1 = (a1 < 0.f ? a1 * 0.2f : a1) * 1.4142135623730951f;
-        ph[j] = __floats2half2_rn(a0, a1);
+            for (int o = 0; o < 2; ++o) {
+                __half2* ph = reinterpret_cast<__half2*>(&pk[o]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float a0 = b[2 * j], a1 = b[2 * j + 1];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { a0 = fmaf(k4[u], win[u][o * 8 + 2 * j], a0); a1 = fmaf(k4[u], win[u][o * 8 + 2 * j + 1], a1); }
+                    a0 = (a0 < 0.f ? a0 * 0.2f : a0) * 1.4142135623730951f; a1 = (a1 < 0.f ? a1 * 0.2f : a1) * 1.4142135623730951f;
+                    ph[j] = __floats2half2_rn(a0, a1);
+                }
+            }
+            __half* dst = y + (((size_t)n * OH + oy) * OW + ox0) * C + c8 * 8;
+            *reinterpret_cast<uint4*>(dst) = pk[0];
+            *reinterpret_cast<uint4*>(dst + C) = pk[1];
+        }
     }
-    *reinterpret_cast<uint4*>(y + (((size_t)n * OH + oy) * OW + ox) * C + c8 * 8) = pk;
 }
 
 // ToRGB for the first block: x NHWC fp16 [N][H][W][C] -> img_out NCHW fp32 = upsample2d(img_prev) + conv1x1 + bias.  One warp per
@@ -441,7 +790,11 @@ static EncodeTiledFn encode_fn() {
 }
 
 // fp16 tensor [d3][d2][d1][d0] (d0 innermost, dense), box {64, box1, 1, 1}, 128-byte swizzle, zero fill outside
+static int make_map_4d_box(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint32_t box1);
 static int make_map_4d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint32_t box1) {
+    return make_map_4d_box(m, ptr, d0, d1, d2, d3, box1);
+}
+static int make_map_4d_box(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint32_t box1) {
     EncodeTiledFn fn = encode_fn();
     R3DP_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[4] = {d0, d1, d2, d3};
@@ -455,7 +808,10 @@ static int make_map_4d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1
     return 0;
 }
 
+static int launch_conv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, const ConvArgs& a1, cudaStream_t st);
+static int tc_version();
 static int launch_conv(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, ConvArgs a, cudaStream_t st) {
+    if (tc_version() == 2) return launch_conv2(x, N, H, W, Cp, wp, Nw, O, a, st);
     CUtensorMap tmA, tmB;
     if (make_map_4d(&tmA, x, (uint64_t)Cp, (uint64_t)W, (uint64_t)H, (uint64_t)N, BM)) return 1;
     if (make_map_4d(&tmB, wp, (uint64_t)Cp, (uint64_t)O, 9, (uint64_t)Nw, BN)) return 1;
@@ -471,6 +827,84 @@ static int launch_conv(const void* x, int N, int H, int W, int Cp, const void* w
     R3DP_LAUNCH_CHECK();
     count_launches(1);
     return 0;
+}
+
+
+static int tc_version() {                      // R3DP_TC_KERNEL=1 selects the simple v1 kernel (debug / A-B comparison)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("R3DP_TC_KERNEL"); v = (e && e[0] == '1') ? 1 : 2; }
+    return v;
+}
+// Row-shifted strip views keep the descriptor's base_offset field 0: the 128-byte swizzle is a function of the ABSOLUTE
+// shared-memory address (as TMA wrote it).  Verified on B200: base_offset = shift gives wrong results, 0 is bit-exact with v1.
+static int tc_base_off_mode() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("R3DP_TC_BASEOFF"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v;
+}
+static int tc_rows() {                         // R3DP_TC_ROWS = 1 | 2 | 4 output rows per tile (default 2: double-buffered accumulators)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("R3DP_TC_ROWS"); v = e ? atoi(e) : 2; if (v != 1 && v != 2 && v != 4) v = 2; }
+    return v;
+}
+
+template <int R>
+static int launch_conv2_r(const CUtensorMap& tmA, const CUtensorMap& tmB, Conv2Args a, cudaStream_t st) {
+    using C = Cfg2<R>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        R3DP_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    a.row_groups = (a.rows + R - 1) / R;
+    a.total_tiles = a.tiles_x * a.row_groups * a.n_blocks * a.n_images;
+    const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
+    conv_tc2_kernel<R><<<grid, kThreads, C::SMEM, st>>>(tmA, tmB, a);
+    R3DP_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+// taps given as (dy, dx, widx) lists -> sorted/grouped Taps2
+static void fill_taps2(Taps2& t2, const Taps& t) {
+    int order[9], n = t.n;
+    for (int i = 0; i < n; ++i) order[i] = i;
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j) {
+            const int a = order[i], b = order[j];
+            if (t.dy[b] < t.dy[a] || (t.dy[b] == t.dy[a] && t.dx[b] < t.dx[a])) { order[i] = b; order[j] = a; }
+        }
+    int dy_min = 99, dx_min = 99;
+    for (int i = 0; i < n; ++i) { if (t.dy[i] < dy_min) dy_min = t.dy[i]; if (t.dx[i] < dx_min) dx_min = t.dx[i]; }
+    t2.n = n; t2.dy_min = dy_min; t2.ngroups = 0;
+    int last = -99;
+    for (int i = 0; i < n; ++i) {
+        const int o = order[i];
+        if (t.dy[o] != last) { t2.gstart[t2.ngroups++] = i; last = t.dy[o]; }
+        t2.dyi[i] = t.dy[o] - dy_min; t2.shift[i] = t.dx[o] + 1; t2.widx[i] = t.widx[o];      // strip box starts at x0 - 1
+    }
+    t2.gstart[t2.ngroups] = n;
+}
+
+static int launch_conv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, const ConvArgs& a1, cudaStream_t st) {
+    CUtensorMap tmA, tmB;
+    if (make_map_4d_box(&tmA, x, (uint64_t)Cp, (uint64_t)W, (uint64_t)H, (uint64_t)N, A2_ROWS)) return 1;
+    if (make_map_4d_box(&tmB, wp, (uint64_t)Cp, (uint64_t)O, 9, (uint64_t)Nw, BN)) return 1;
+    Conv2Args a = {};
+    fill_taps2(a.taps, a1.taps);
+    // contiguous dy groups are required by the strip schedule (true for 3x3 and for every transposed-conv phase)
+    a.k_chunks = Cp / BK; a.tiles_x = a1.tiles_x; a.rows = a1.rows; a.n_blocks = O / BN; a.n_images = N;
+    a.w_shared = (Nw == 1); a.mode = a1.mode; a.base_off_mode = tc_base_off_mode();
+    a.out = a1.out; a.out_H = a1.out_H; a.out_W = a1.out_W; a.out_C = a1.out_C;
+    a.oy_mul = a1.oy_mul; a.oy_off = a1.oy_off; a.ox_mul = a1.ox_mul; a.ox_off = a1.ox_off;
+    a.bias = a1.bias; a.wrgb = a1.wrgb; a.brgb = a1.brgb; a.img_prev = a1.img_prev; a.img_out = a1.img_out;
+    R3DP_REQUIRE(a.n_blocks <= 2, "conv_tc2: at most 256 output channels");
+    switch (tc_rows()) {
+        case 1: return launch_conv2_r<1>(tmA, tmB, a, st);
+        case 2: return launch_conv2_r<2>(tmA, tmB, a, st);
+        case 4: return launch_conv2_r<4>(tmA, tmB, a, st);
+        default: return launch_conv2_r<2>(tmA, tmB, a, st);
+    }
 }
 
 }  // namespace tc
@@ -538,13 +972,13 @@ extern "C" int r3dp_sr_tc_layer(const void* x_f16, const void* wp_f16, const flo
             if (launch_conv(x_f16, N, H, W, Ip, wp_f16, Nw, O, a, st)) return 1;
         }
     {
-        const int warps = (2 * H + 1) * O;
-        dim3 grid((warps * 32 + 255) / 256, N);
+        R3DP_REQUIRE(Ip <= 256, "sr_tc_layer: up=2 supports at most 256 input channels");
+        dim3 grid((2 * H + 1 + kEdgeRows - 1) / kEdgeRows, N);
         upconv_edge_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(x_f16), reinterpret_cast<const __half*>(wp_f16), H, W, Ip, O,
                                                  Nw == 1, yb);
     }
     {
-        const long long total = (long long)N * (2 * H) * (2 * W) * (O / 8);
+        const long long total = (long long)N * ((2 * H + kFirSeg - 1) / kFirSeg) * W * (O / 8);
         fir_bias_lrelu_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(yb, bias, N, 2 * H, 2 * W, O, reinterpret_cast<__half*>(y_f16));
     }
     R3DP_LAUNCH_CHECK();

@@ -20,35 +20,91 @@ def default_sr_mode() -> str:
 
 
 class FrameEngine:
-    def __init__(self, batch: int = 4, sr_mode: str = 'fp32', device=None, world: int = 1, rank: int = 0, dist=None, hp: Optional[dict] = None):
+    """batch: frames per step; static_styles: the SR styles are constant (Real3D passes ws == 1, img2plane_baseline.py:142) so
+    the folded fp16 weights are prepared once per parameter load; use_graph: replay the whole step (≈70 kernels) as ONE CUDA
+    graph — inputs are copied into static buffers first, the only per-step host work is the replay."""
+
+    def __init__(self, batch: int = 4, sr_mode: str = 'fp32', device=None, world: int = 1, rank: int = 0, dist=None, hp: Optional[dict] = None,
+                 static_styles: bool = True, use_graph: bool = True):
         self.batch, self.world, self.rank, self.dist = batch, world, rank, dist
         self.device = device if device is not None else torch.device('cuda', torch.cuda.current_device())
         self.head = RenderHead(hp=hp, sr_mode=sr_mode).to(self.device).eval()
+        self.static_styles, self.use_graph = static_styles, use_graph
         self.gathered = torch.empty(world * batch, 3, 512, 512, device=self.device) if world > 1 else None
+        self.graph = None
+        self.launches_per_step = 0
+        self.s_planes = self.s_cams = self.s_u = self.s_out = None
 
     def load_params(self, decoder_params: Dict[str, torch.Tensor], sr_params: Dict[str, torch.Tensor]) -> None:
         sd = {'decoder.' + k: v for k, v in decoder_params.items()}
         sd.update({'superresolution.' + k: v for k, v in sr_params.items()})
         self.head.load_state_dict(sd, strict=True)
+        self.graph = None
+        sr = self.head.superresolution
+        sr.static_prepared = None
+        if self.static_styles and sr.sr_mode == 'tc':
+            from . import sr_tc
+            ones = torch.ones(1, 3, self.head.hparams['w_dim'], device=self.device)
+            with torch.no_grad():
+                sr.static_prepared = sr_tc.Prepared(sr, ones)
+
+    @torch.no_grad()
+    def _body(self, planes, cameras, u_coarse) -> torch.Tensor:
+        return self.head.synthesis(planes, cameras, u_coarse=u_coarse)['image']
+
+    def _capture(self, planes, cameras, u_coarse) -> None:
+        self.s_planes, self.s_cams, self.s_u = planes.clone(), cameras.clone(), u_coarse.clone()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):                                       # warm-up outside capture: lazy inits (func attributes, driver entry points)
+                self._body(self.s_planes, self.s_cams, self.s_u)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        c0 = capi.lib().r3dp_launch_count()
+        with torch.cuda.graph(g):
+            self.s_out = self._body(self.s_planes, self.s_cams, self.s_u)
+        self.launches_per_step = int(capi.lib().r3dp_launch_count() - c0)      # libr3dp kernels inside one replay
+        self.graph = g
 
     @torch.no_grad()
     def step(self, planes: torch.Tensor, cameras: torch.Tensor, u_coarse: Optional[torch.Tensor] = None, u_fine=None) -> torch.Tensor:
-        """planes [B,3,32,256,256], cameras [B,25] -> frames [B,3,512,512] (world == 1) or the all-gathered
-        [world*B,3,512,512] (rank-major)."""
-        over = {}
-        if u_coarse is not None:
-            over['u_coarse'] = u_coarse
-        if u_fine is not None:
-            over['u_fine'] = u_fine
-        out = self.head.synthesis(planes, cameras, **over)['image']
+        """planes [B,3,32,256,256], cameras [B,25], u_coarse [B,4096,S,1] (drawn here if None) -> frames [B,3,512,512]
+        (world == 1) or the all-gathered [world*B,3,512,512] (rank-major).  The returned tensor is reused by the next step."""
+        if u_coarse is None:
+            S = self.head.rendering_kwargs['depth_resolution']
+            u_coarse = torch.rand(planes.shape[0], self.head.neural_rendering_resolution ** 2, S, 1, device=planes.device)
+        graphable = self.use_graph and capi.PROF is None and u_fine is None and planes.shape[0] == self.batch
+        if graphable:
+            if self.graph is None:
+                self._capture(planes, cameras, u_coarse)
+            if planes.data_ptr() != self.s_planes.data_ptr():
+                self.s_planes.copy_(planes, non_blocking=True)
+            if cameras.data_ptr() != self.s_cams.data_ptr():
+                self.s_cams.copy_(cameras, non_blocking=True)
+            if u_coarse.data_ptr() != self.s_u.data_ptr():
+                self.s_u.copy_(u_coarse, non_blocking=True)
+            self.graph.replay()
+            out = self.s_out
+        else:
+            over = {'u_coarse': u_coarse}
+            if u_fine is not None:
+                over['u_fine'] = u_fine
+            out = self.head.synthesis(planes, cameras, **over)['image']
         if self.world > 1:
             with capi.region('allgather'):
                 self.dist.all_gather_into_tensor(self.gathered, out.contiguous())
             return self.gathered
         return out
 
+    def static_inputs(self):
+        """(planes, cameras, u_coarse) static buffers of the captured graph: a producer may write its outputs straight into them
+        and call step() with these very tensors to skip the copy-in."""
+        return self.s_planes, self.s_cams, self.s_u
+
     def profile_steps(self, inputs: Callable[[int], tuple], first: int, steps: int) -> Dict:
-        """Re-run `steps` steps with CUDA events around every stage (on the launching stream)."""
+        """Re-run `steps` steps eagerly with CUDA events around every stage (on the launching stream)."""
         capi.PROF = capi.Profiler()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -58,5 +114,5 @@ class FrameEngine:
         torch.cuda.synchronize()
         stages = capi.PROF.totals()
         capi.PROF = None
-        kernel = 'sr_tc_conv (tcgen05 implicit GEMM)' if self.head.superresolution.sr_mode == 'tc' else 'conv_taps_kernel (fp32 CUDA-core direct conv)'
+        kernel = 'conv_tc2_kernel (tcgen05 implicit GEMM)' if self.head.superresolution.sr_mode == 'tc' else 'conv_taps_kernel (fp32 CUDA-core direct conv)'
         return {'stages': stages, 'sr_conv_ms': stages.get('sr_conv', float('nan')), 'total_ms': a.elapsed_time(b), 'sr_kernel': kernel}

@@ -50,31 +50,44 @@ def to_nhwc_f16(x: torch.Tensor, size: int) -> torch.Tensor:
     return y
 
 
-def forward(sr, rgb: torch.Tensor, x: torch.Tensor, ws3: torch.Tensor, shared_styles: Optional[bool] = None) -> torch.Tensor:
-    """rgb [N,3,h,w], x [N,C,h,w] (fp32 NCHW, h <= 128), ws3 [N,3,512] -> [N,3,512,512] fp32."""
+class Prepared:
+    """Folded + packed weights of the four conv layers and the two ToRGB layers for a given set of styles."""
+    __slots__ = ('wp', 'wrgb0', 'wrgb1', 'Nw')
+
+    def __init__(self, sr, wsel: torch.Tensor):
+        b0, b1 = sr.block0, sr.block1
+        self.Nw = wsel.shape[0]
+        self.wp = [_pack(b0.conv0, wsel[:, 0]), _pack(b0.conv1, wsel[:, 1]), _pack(b1.conv0, wsel[:, 0]), _pack(b1.conv1, wsel[:, 1])]
+        self.wrgb0, self.wrgb1 = b0.torgb.folded_weight(wsel[:, 2]), b1.torgb.folded_weight(wsel[:, 2])
+
+
+def forward(sr, rgb: torch.Tensor, x: torch.Tensor, ws3: torch.Tensor, shared_styles: Optional[bool] = None,
+            x_is_nhwc: bool = False) -> torch.Tensor:
+    """rgb [N,3,h,w], x [N,C,h,w] (fp32 NCHW, h <= 128), ws3 [N,3,512] -> [N,3,512,512] fp32.
+    If `sr.static_prepared` is set (caller guarantees constant styles, e.g. Real3D's ws == 1) the weight preparation
+    (styles -> fold -> demod -> fp16 pack) is skipped."""
     from .superresolution import SuperresolutionHybrid8XDC
     L = capi.lib()
     N = x.shape[0]
-    if shared_styles is None:
-        shared_styles = N == 1 or getattr(sr, 'assume_shared_styles', False)
-    wsel = ws3[:1] if shared_styles else ws3
-    Nw = wsel.shape[0]
-    b0, b1 = sr.block0, sr.block1
+    prep = getattr(sr, 'static_prepared', None)
     with capi.region('sr_prep'):
+        if prep is None:
+            if shared_styles is None:
+                shared_styles = N == 1 or getattr(sr, 'assume_shared_styles', False)
+            prep = Prepared(sr, ws3[:1] if shared_styles else ws3)
         x0 = to_nhwc_f16(x, sr.input_resolution)
         rgb0 = SuperresolutionHybrid8XDC._resize(rgb, sr.input_resolution) if rgb.shape[-1] != sr.input_resolution else capi.f32(rgb)
-        wp = [_pack(b0.conv0, wsel[:, 0]), _pack(b0.conv1, wsel[:, 1]), _pack(b1.conv0, wsel[:, 0]), _pack(b1.conv1, wsel[:, 1])]
-        wrgb0, wrgb1 = b0.torgb.folded_weight(wsel[:, 2]), b1.torgb.folded_weight(wsel[:, 2])
+    b0, b1, Nw, wp = sr.block0, sr.block1, prep.Nw, prep.wp
     a0 = layer(x0, b0.conv0, wp[0], 2)
     a1 = layer(a0, b0.conv1, wp[1], 1)
     img1 = torch.empty(N, 3, 256, 256, device=x.device)
     with capi.region('sr_torgb'):
-        capi.check(L.r3dp_sr_tc_torgb(capi.ptr(a1, torch.float16), capi.ptr(wrgb0), capi.ptr(capi.f32(b0.torgb.bias)), capi.ptr(rgb0), N, Nw,
+        capi.check(L.r3dp_sr_tc_torgb(capi.ptr(a1, torch.float16), capi.ptr(prep.wrgb0), capi.ptr(capi.f32(b0.torgb.bias)), capi.ptr(rgb0), N, Nw,
                                       256, 256, 256, capi.ptr(img1), capi.stream()))
     a2 = layer(a1, b1.conv0, wp[2], 2)
     out = torch.empty(N, 3, 512, 512, device=x.device)
     with capi.region('sr_conv'):
         capi.check(L.r3dp_sr_tc_last_layer(capi.ptr(a2, torch.float16), capi.ptr(wp[3], torch.float16), capi.ptr(capi.f32(b1.conv1.bias)),
-                                           capi.ptr(wrgb1), capi.ptr(capi.f32(b1.torgb.bias)), capi.ptr(img1), N, Nw, 128, 512, 512,
+                                           capi.ptr(prep.wrgb1), capi.ptr(capi.f32(b1.torgb.bias)), capi.ptr(img1), N, Nw, 128, 512, 512,
                                            capi.ptr(out), capi.stream()))
     return out

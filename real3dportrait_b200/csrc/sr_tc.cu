@@ -589,13 +589,13 @@ __global__ void resize_to_nhwc_f16_kernel(const float* __restrict__ x, int N, in
 
 // last column X = 2W of the transposed-conv result (the only part of the (2H+1)x(2W+1) grid the 128-wide GEMM tiles do not
 // cover): yb[n][Y][2W][co] = sum_{ci, ky == Y (mod 2)} x[(Y-ky)/2][W-1][ci] * w[ky*3+2][co][ci].
-// CTA = 16 consecutive rows Y of one image: the <= 10 input pixels they touch are staged in smem, each warp walks the couts
-// with its three weight rows (kx = 2 column of the kernel) in registers.  Cp <= 256.
-constexpr int kEdgeRows = 16;
+// CTA = 16 consecutive rows Y x 32 couts of one image: the <= 10 input pixels the rows touch are staged in smem, each warp
+// owns 4 couts with their three weight rows (the kx = 2 column of the kernel) in registers.  Cp <= 256.
+constexpr int kEdgeRows = 16, kEdgeCo = 32;
 __global__ void __launch_bounds__(256) upconv_edge_kernel(const __half* __restrict__ x, const __half* __restrict__ wp, int H, int W, int Cp, int O,
                                                           int w_shared, __half* __restrict__ yb) {
     __shared__ __align__(16) __half s_x[kEdgeRows / 2 + 2][256];
-    const int n = blockIdx.y, Y0 = blockIdx.x * kEdgeRows;
+    const int n = blockIdx.z, Y0 = blockIdx.x * kEdgeRows, co0 = blockIdx.y * kEdgeCo;
     const int BH = 2 * H + 1, BW = 2 * W + 1;
     const int wn = w_shared ? 0 : n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -607,7 +607,10 @@ __global__ void __launch_bounds__(256) upconv_edge_kernel(const __half* __restri
     __syncthreads();
     const int c0 = lane * 8;
     const bool on = c0 < Cp;
-    for (int co = warp; co < O; co += 8) {
+#pragma unroll 1
+    for (int cc = 0; cc < kEdgeCo / 8; ++cc) {
+        const int co = co0 + warp * (kEdgeCo / 8) + cc;
+        if (co >= O) break;
         float wv[3][8];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
@@ -617,103 +620,115 @@ __global__ void __launch_bounds__(256) upconv_edge_kernel(const __half* __restri
 #pragma unroll
             for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); wv[ky][2 * j] = f.x; wv[ky][2 * j + 1] = f.y; }
         }
-#pragma unroll 1
+#pragma unroll
         for (int yy = 0; yy < kEdgeRows; ++yy) {
             const int Y = Y0 + yy;
-            if (Y >= BH) break;
             float acc = 0.f;
-            for (int ky = (Y & 1); ky < 3; ky += 2) {
-                const int r = ((Y - ky) >> 1) - iy0;                          // (Y-ky) is even; rows outside the image hold zeros
-                if ((Y - ky) < 0) continue;
-                if (on) {
-                    const uint4 raw = *reinterpret_cast<const uint4*>(&s_x[r][c0]);
-                    const __half2* h = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 f = __half22float2(h[j]);
-                        acc = fmaf(f.x, wv[ky][2 * j], acc); acc = fmaf(f.y, wv[ky][2 * j + 1], acc);
-                    }
+            for (int ky = 0; ky < 3; ++ky) {
+                if (((yy ^ ky) & 1) || !on) continue;                        // Y0 is even: parity of Y == parity of yy
+                const int r = ((yy - ky) >> 1) + 1;                          // == (Y-ky)/2 - iy0 ; rows outside the image hold zeros
+                const uint4 raw = *reinterpret_cast<const uint4*>(&s_x[r][c0]);
+                const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h[j]);
+                    acc = fmaf(f.x, wv[ky][2 * j], acc); acc = fmaf(f.y, wv[ky][2 * j + 1], acc);
                 }
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) yb[(((size_t)n * BH + Y) * BW + 2 * W) * O + co] = __float2half_rn(acc);
+            if (lane == 0 && Y < BH) yb[(((size_t)n * BH + Y) * BW + 2 * W) * O + co] = __float2half_rn(acc);
         }
     }
 }
 
 // FIR 4x4 (pad 1, gain 4) + bias + lrelu*sqrt2 on the transposed-conv result: yb [N][2H+1][2W+1][C] fp16 -> y [N][2H][2W][C] fp16.
-// HBM-bound (read 1x + write 1x).  A thread owns two adjacent output columns x 8 channels and MARCHES DOWN a segment of rows:
-// per input row it loads the 5 pixels its two outputs touch (16-byte vectors; the overlap with its neighbours is served by
-// L1), reduces them horizontally, and keeps the last four horizontal results in registers for the vertical pass - so every
-// yb element leaves L2 once instead of once per output row it contributes to.
-constexpr int kFirSeg = 32;
-__device__ __forceinline__ void fir_load8(const __half* p, bool ok, float* f) {
-    uint4 raw = make_uint4(0, 0, 0, 0);
-    if (ok) raw = __ldg(reinterpret_cast<const uint4*>(p));
-    const __half2* h = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { const float2 v = __half22float2(h[j]); f[2 * j] = v.x; f[2 * j + 1] = v.y; }
-}
-__global__ void __launch_bounds__(256) fir_bias_lrelu_f16_kernel(const __half* __restrict__ yb, const float* __restrict__ bias, int N, int OH,
-                                                                 int OW, int C, __half* __restrict__ y) {
-    const int cv = C / 8, pairs = OW / 2, segs = (OH + kFirSeg - 1) / kFirSeg;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)N * segs * pairs * cv) return;
-    const int c8 = (int)(idx % cv); const int xp = (int)((idx / cv) % pairs); const int seg = (int)((idx / ((long long)cv * pairs)) % segs);
-    const int n = (int)(idx / ((long long)cv * pairs * segs));
-    const int BH = OH + 1, BW = OW + 1;
-    const int ox0 = xp * 2, oy0 = seg * kFirSeg, oy1 = min(oy0 + kFirSeg, OH);
+// HBM-bound stencil (read 1x + write 1x), done the Blackwell way: a persistent CTA streams {64 ch, 35 px, 11 rows} boxes of yb
+// into shared memory with ONE TMA instruction each (double-buffered on mbarriers; the box is zero-filled outside the image,
+// which IS the FIR's zero padding), then 256 threads (32 px x 8 channel-vectors) march down the tile: 4 swizzled LDS.128 per
+// input row -> horizontal taps -> 4-row register window -> vertical taps, bias, lrelu -> one 16-byte store per output row.
+constexpr int FIR_TW = 32, FIR_TH = 8, FIR_BW = FIR_TW + 3, FIR_BH = FIR_TH + 3;
+constexpr int FIR_BOX_BYTES = FIR_BW * FIR_BH * 128, FIR_SLOT = (FIR_BOX_BYTES + 1023) / 1024 * 1024;
+constexpr int FIR_SMEM = 2 * FIR_SLOT + 1024 + 64;
+__global__ void __launch_bounds__(256) fir_tma_kernel(const __grid_constant__ CUtensorMap tmY, const float* __restrict__ bias, int N, int OH,
+                                                      int OW, int C, __half* __restrict__ y) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * FIR_SLOT);
+    const int tid = threadIdx.x, px = tid >> 3, c8 = tid & 7;
+    const int tiles_x = OW / FIR_TW, tiles_y = (OH + FIR_TH - 1) / FIR_TH, cgs = C / 64;
+    const int total = N * cgs * tiles_y * tiles_x;
+    if (tid == 0) {
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int tile, int buf) {
+        const int tx = tile % tiles_x; int r = tile / tiles_x;
+        const int ty = r % tiles_y; r /= tiles_y;
+        const int cg = r % cgs, n = r / cgs;
+        mbar_expect_tx(&full[buf], FIR_BOX_BYTES);
+        tma_load_4d(smem + buf * FIR_SLOT, &tmY, &full[buf], cg * 64, tx * FIR_TW - 1, ty * FIR_TH - 1, n);
+    };
+    if (tid == 0) {
+        if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
+        if ((int)(blockIdx.x + gridDim.x) < total) issue(blockIdx.x + gridDim.x, 1);
+    }
     const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};
-    float b[8];
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int tx = tile % tiles_x; int r = tile / tiles_x;
+        const int ty = r % tiles_y; r /= tiles_y;
+        const int cg = r % cgs, n = r / cgs;
+        float b[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) b[j] = bias[c8 * 8 + j];
-    float win[4][16];                                                        // last four horizontally-filtered rows: [row][2 outputs x 8 ch]
+        for (int j = 0; j < 8; ++j) b[j] = bias[cg * 64 + c8 * 8 + j];
+        mbar_wait(&full[buf], (it >> 1) & 1);
+        const uint8_t* sb = smem + buf * FIR_SLOT;
+        float win[4][8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+        for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) win[r][j] = 0.f;
-    const __half* base = yb + (size_t)n * BH * BW * C + c8 * 8;
-    // input rows oy0-1 .. oy1+1 ; output row oy is complete once input row oy+2 has been pushed
-#pragma unroll 4
-    for (int yy = oy0 - 1; yy <= oy1 + 1; ++yy) {
+            for (int j = 0; j < 8; ++j) win[rr][j] = 0.f;
+        const int ox = tx * FIR_TW + px;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { win[0][j] = win[1][j]; win[1][j] = win[2][j]; win[2][j] = win[3][j]; win[3][j] = 0.f; }
-        if ((unsigned)yy < (unsigned)BH) {
-            const __half* rowp = base + (size_t)yy * BW * C;
-            float px[8];
+        for (int ry = 0; ry < FIR_BH; ++ry) {
 #pragma unroll
-            for (int v = 0; v < 5; ++v) {                                    // pixel ox0-1+v feeds output 0 with tap v and output 1 with tap v-1
-                const int xx = ox0 - 1 + v;
-                fir_load8(rowp + (size_t)xx * C, (unsigned)xx < (unsigned)BW, px);
-                if (v < 4) {
+            for (int j = 0; j < 8; ++j) { win[0][j] = win[1][j]; win[1][j] = win[2][j]; win[2][j] = win[3][j]; win[3][j] = 0.f; }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) win[3][j] = fmaf(k4[v], px[j], win[3][j]);
+            for (int v = 0; v < 4; ++v) {
+                const int row = ry * FIR_BW + px + v;                            // 128-byte row of the box; swizzle = chunk ^ (row & 7)
+                const uint4 raw = *reinterpret_cast<const uint4*>(sb + row * 128 + ((c8 ^ (row & 7)) << 4));
+                const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h[j]);
+                    win[3][2 * j] = fmaf(k4[v], f.x, win[3][2 * j]); win[3][2 * j + 1] = fmaf(k4[v], f.y, win[3][2 * j + 1]);
                 }
-                if (v > 0) {
+            }
+            if (ry >= 3) {
+                const int oy = ty * FIR_TH + ry - 3;
+                if (oy < OH) {
+                    uint4 pk; __half2* ph = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) win[3][8 + j] = fmaf(k4[v - 1], px[j], win[3][8 + j]);
+                    for (int j = 0; j < 4; ++j) {
+                        float a0 = b[2 * j], a1 = b[2 * j + 1];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { a0 = fmaf(k4[u], win[u][2 * j], a0); a1 = fmaf(k4[u], win[u][2 * j + 1], a1); }
+                        a0 = (a0 < 0.f ? a0 * 0.2f : a0) * 1.4142135623730951f; a1 = (a1 < 0.f ? a1 * 0.2f : a1) * 1.4142135623730951f;
+                        ph[j] = __floats2half2_rn(a0, a1);
+                    }
+                    *reinterpret_cast<uint4*>(y + (((size_t)n * OH + oy) * OW + ox) * C + cg * 64 + c8 * 8) = pk;
                 }
             }
         }
-        const int oy = yy - 2;
-        if (oy >= oy0 && oy < oy1) {
-            uint4 pk[2];
-#pragma unroll
-            for (int o = 0; o < 2; ++o) {
-                __half2* ph = reinterpret_cast<__half2*>(&pk[o]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float a0 = b[2 * j], a1 = b[2 * j + 1];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) { a0 = fmaf(k4[u], win[u][o * 8 + 2 * j], a0); a1 = fmaf(k4[u], win[u][o * 8 + 2 * j + 1], a1); }
-                    a0 = (a0 < 0.f ? a0 * 0.2f : a0) * 1.4142135623730951f; a1 = (a1 < 0.f ? a1 * 0.2f : a1) * 1.4142135623730951f;
-                    ph[j] = __floats2half2_rn(a0, a1);
-                }
-            }
-            __half* dst = y + (((size_t)n * OH + oy) * OW + ox0) * C + c8 * 8;
-            *reinterpret_cast<uint4*>(dst) = pk[0];
-            *reinterpret_cast<uint4*>(dst + C) = pk[1];
+        __syncthreads();                                                      // everyone is done reading this buffer
+        if (tid == 0) {
+            const int nxt = tile + 2 * gridDim.x;
+            if (nxt < total) issue(nxt, buf);
         }
     }
 }
@@ -805,6 +820,19 @@ static int make_map_4d_box(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     R3DP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (dims %llu x %llu x %llu x %llu)", (int)r,
                  (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)d3);
+    return 0;
+}
+
+static int make_map_fir(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3) {
+    EncodeTiledFn fn = encode_fn();
+    R3DP_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[4] = {d0, d1, d2, d3};
+    cuuint64_t strides[3] = {d0 * 2, d0 * d1 * 2, d0 * d1 * d2 * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)FIR_BW, (cuuint32_t)FIR_BH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    R3DP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (FIR) failed with CUresult %d", (int)r);
     return 0;
 }
 
@@ -973,13 +1001,22 @@ extern "C" int r3dp_sr_tc_layer(const void* x_f16, const void* wp_f16, const flo
         }
     {
         R3DP_REQUIRE(Ip <= 256, "sr_tc_layer: up=2 supports at most 256 input channels");
-        dim3 grid((2 * H + 1 + kEdgeRows - 1) / kEdgeRows, N);
+        dim3 grid((2 * H + 1 + kEdgeRows - 1) / kEdgeRows, (O + kEdgeCo - 1) / kEdgeCo, N);
         upconv_edge_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(x_f16), reinterpret_cast<const __half*>(wp_f16), H, W, Ip, O,
                                                  Nw == 1, yb);
     }
     {
-        const long long total = (long long)N * ((2 * H + kFirSeg - 1) / kFirSeg) * W * (O / 8);
-        fir_bias_lrelu_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(yb, bias, N, 2 * H, 2 * W, O, reinterpret_cast<__half*>(y_f16));
+        R3DP_REQUIRE((2 * W) % FIR_TW == 0 && O % 64 == 0, "sr_tc_layer: FIR needs 2W %% 32 == 0 and Cout %% 64 == 0");
+        CUtensorMap tmY;
+        if (make_map_fir(&tmY, yb, (uint64_t)O, (uint64_t)(2 * W + 1), (uint64_t)(2 * H + 1), (uint64_t)N)) return 1;
+        static bool attr_set = false;
+        if (!attr_set) {
+            R3DP_CUDA(cudaFuncSetAttribute(fir_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIR_SMEM));
+            attr_set = true;
+        }
+        const int total = N * (O / 64) * ((2 * H + FIR_TH - 1) / FIR_TH) * (2 * W / FIR_TW);
+        const int grid = total < 2 * sm_count() ? total : 2 * sm_count();
+        fir_tma_kernel<<<grid, 256, FIR_SMEM, st>>>(tmY, bias, N, 2 * H, 2 * W, O, reinterpret_cast<__half*>(y_f16));
     }
     R3DP_LAUNCH_CHECK();
     count_launches(2);

@@ -4,8 +4,20 @@
 //   3. depth_clamp_kernel  NaN->inf, clamp depth to the call-wide [min,max] sample depth (ray_marcher.py:49-50)
 // plus gen_rays (RaySampler.forward) and a stand-alone ray marcher.
 #include "render_core.cuh"
+#include <stdlib.h>
 
 namespace r3dp {
+
+
+// writes the scaled decoder weights into the constant bank's backing store (visible to every later launch)
+__global__ void mlp_to_const_kernel(const r3dp_mlp_t m, MlpConst* dst) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    const float g1 = 0.17677669529663687f, g2 = 0.125f;        // 1/sqrt(32), 1/sqrt(64)  (networks_stylegan2.py:113)
+    for (int i = tid; i < kHidden * kC; i += nt) dst->w1[i] = m.w1[i] * g1;
+    for (int i = tid; i < kHidden * kOut; i += nt) { const int j = i / kOut, o = i - j * kOut; dst->w2[i] = m.w2[o * kHidden + j] * g2; }
+    for (int i = tid; i < kHidden; i += nt) dst->b1[i] = m.b1[i];
+    for (int i = tid; i < kOut; i += nt) dst->b2[i] = m.b2[i];
+}
 
 struct RenderWs {          // lives at the start of the caller's workspace
     unsigned t0_min, t0_max;   // ordered-uint encoded floats over valid rays
@@ -101,12 +113,13 @@ __device__ __forceinline__ int ray_of(const RenderArgs& a, int tile, int r) {
     return tile * R + r;
 }
 
-template <int R>
-__global__ void __launch_bounds__(kRenderThreads, 2) render_kernel(const RenderArgs a) {
+// CONST = decoder weights from the constant bank (1 sample/thread, 4 CTAs/SM); else staged in smem (2 samples/thread, 2 CTAs/SM)
+template <int R, bool CONST>
+__global__ void __launch_bounds__(kRenderThreads, CONST ? 4 : 2) render_kernel(const RenderArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int ST = a.S + a.S_imp;                         // samples per ray after the optional importance pass
     MlpSmem& mlp = *reinterpret_cast<MlpSmem*>(smem);
-    float* rows = smem + sizeof(MlpSmem) / 4;              // [R*ST][kRow]   features -> (sigma, colours)
+    float* rows = smem + (CONST ? 0 : sizeof(MlpSmem) / 4); // [R*ST][kRow]   features -> (sigma, colours)
     float* dep = rows + R * ST * kRow;                     // [R*ST]          sample depths
     float* wts = dep + R * ST;                             // [R*ST]          coarse interval weights
     float* cdf = wts + R * ST;                             // [R*ST]          importance cdf
@@ -117,7 +130,7 @@ __global__ void __launch_bounds__(kRenderThreads, 2) render_kernel(const RenderA
     constexpr int kWarps = kRenderThreads / 32;
     const int n = blockIdx.y, tile = blockIdx.x;
 
-    load_mlp_smem(mlp, a.mlp, tid, kRenderThreads);
+    if (!CONST) load_mlp_smem(mlp, a.mlp, tid, kRenderThreads);
 
     // ---- rays + limits -------------------------------------------------------------------------------------
     if (tid < R) {
@@ -180,6 +193,14 @@ __global__ void __launch_bounds__(kRenderThreads, 2) render_kernel(const RenderA
             }
         }
         __syncthreads();
+        if (CONST) {
+            for (int q = tid; q < nsamp; q += kRenderThreads) {
+                const int r = q / kn, k = k0 + (q - r * kn);
+                decode_one_const(rows + (size_t)(r * ST + k) * kRow);
+            }
+            __syncthreads();
+            return;
+        }
         // decode: two samples per thread
         const int half = (nsamp + 1) >> 1;
         for (int p = tid; p < half; p += kRenderThreads) {
@@ -322,18 +343,34 @@ __global__ void ray_march_kernel(const float* __restrict__ colors, const float* 
     if (lane == 0 && dmin <= dmax) { atomicMin(&ws->d_min, f2ord(dmin)); atomicMax(&ws->d_max, f2ord(dmax)); }
 }
 
-static size_t render_smem_bytes(int R, int ST) {
-    return sizeof(MlpSmem) + (size_t)R * ST * kRow * 4 + 3 * (size_t)R * ST * 4 + (size_t)R * 8 * 4 + (size_t)R * ST * 4;
+static size_t render_smem_bytes(int R, int ST, bool cst) {
+    return (cst ? 0 : sizeof(MlpSmem)) + (size_t)R * ST * kRow * 4 + 3 * (size_t)R * ST * 4 + (size_t)R * 8 * 4 + (size_t)R * ST * 4;
 }
 
-template <int R>
-static int launch_render(const RenderArgs& a, cudaStream_t st) {
-    const size_t smem = render_smem_bytes(R, a.S + a.S_imp);
-    R3DP_CUDA(cudaFuncSetAttribute(render_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+static bool mlp_in_const() {                       // R3DP_MLP=smem selects the shared-memory decoder variant (A/B comparison)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("R3DP_MLP"); v = (e && e[0] == 's') ? 0 : 1; }
+    return v == 1;
+}
+
+template <int R, bool CONST>
+static int launch_render_v(const RenderArgs& a, cudaStream_t st) {
+    const size_t smem = render_smem_bytes(R, a.S + a.S_imp, CONST);
+    R3DP_CUDA(cudaFuncSetAttribute(render_kernel<R, CONST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (CONST) {
+        MlpConst* dst = nullptr;
+        R3DP_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&dst), c_mlp));
+        mlp_to_const_kernel<<<4, 256, 0, st>>>(a.mlp, dst);
+        count_launches(1);
+    }
     dim3 grid(a.tiles_per_frame, a.N);
-    render_kernel<R><<<grid, kRenderThreads, smem, st>>>(a);
+    render_kernel<R, CONST><<<grid, kRenderThreads, smem, st>>>(a);
     R3DP_LAUNCH_CHECK();
     return 0;
+}
+template <int R>
+static int launch_render(const RenderArgs& a, cudaStream_t st) {
+    return mlp_in_const() ? launch_render_v<R, true>(a, st) : launch_render_v<R, false>(a, st);
 }
 
 }  // namespace r3dp

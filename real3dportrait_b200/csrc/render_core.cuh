@@ -180,4 +180,39 @@ __device__ __forceinline__ void decode_pair(const MlpSmem& w, float* __restrict_
     }
 }
 
+// ---- OSG decoder, constant-bank variant ------------------------------------------------------------------------------
+// The 4 257 scaled weights live in __constant__ memory (render.cu fills them with a tiny kernel before every render call).
+// Fully unrolled, every FFMA takes its weight as a constant-bank operand: no weight loads at all, one sample per thread,
+// ~80 registers.  hidden unit j is consumed immediately (32 FMAs -> softplus -> 33 FMAs into the outputs).
+struct MlpConst {
+    float w1[kHidden * kC];      // [j][c]   W1 * 1/sqrt(32)
+    float b1[kHidden];
+    float w2[kHidden * kOut];    // [j][o]   (W2 * 1/sqrt(64))^T
+    float b2[kOut];
+};
+static __constant__ MlpConst c_mlp;      // one copy per translation unit; only render.cu uses it
+
+__device__ __forceinline__ void decode_one_const(float* __restrict__ row) {
+    float x[kC], y[kOut];
+#pragma unroll
+    for (int c = 0; c < kC; ++c) x[c] = row[c];
+#pragma unroll
+    for (int o = 0; o < kOut; ++o) y[o] = c_mlp.b2[o];
+#pragma unroll
+    for (int j = 0; j < kHidden; ++j) {
+        float h0 = c_mlp.b1[j], h1 = 0.f;                      // two accumulation chains for ILP
+#pragma unroll
+        for (int c = 0; c < kC; c += 2) {
+            h0 = fmaf(x[c], c_mlp.w1[j * kC + c], h0);
+            h1 = fmaf(x[c + 1], c_mlp.w1[j * kC + c + 1], h1);
+        }
+        const float sp = softplus_fast(h0 + h1);
+#pragma unroll
+        for (int o = 0; o < kOut; ++o) y[o] = fmaf(sp, c_mlp.w2[j * kOut + o], y[o]);
+    }
+    row[0] = y[0];
+#pragma unroll
+    for (int o = 1; o < kOut; ++o) row[o] = sigmoid_fast(y[o]) * 1.002f - 0.001f;
+}
+
 }  // namespace r3dp

@@ -98,6 +98,53 @@ class FrameEngine:
             return self.gathered
         return out
 
+    # ---- host-buffer entry point: H2D / compute / D2H of consecutive steps overlap on three streams -----------------------
+    def _host_pipeline(self):
+        if getattr(self, '_hp', None) is None:
+            dev = self.device
+            self._hp = {
+                'copy_in': torch.cuda.Stream(device=dev), 'copy_out': torch.cuda.Stream(device=dev), 'k': 0,
+                'in_ready': [torch.cuda.Event() for _ in range(2)], 'in_free': [torch.cuda.Event() for _ in range(2)],
+                'out_ready': [torch.cuda.Event() for _ in range(2)], 'out_free': [torch.cuda.Event() for _ in range(2)],
+                'stage': [None, None], 'out': [None, None],
+            }
+        return self._hp
+
+    @torch.no_grad()
+    def step_host(self, h_planes: torch.Tensor, h_cameras: torch.Tensor, h_u: torch.Tensor, h_out: torch.Tensor) -> None:
+        """Same step, from PINNED HOST tensors to a pinned host output (frames of THIS rank), fully asynchronous: the call
+        enqueues H2D (copy-in stream) -> step (current stream) -> D2H (copy-out stream) and returns; with two staging slots the
+        copy of step i+1 runs under the compute of step i.  Call `sync_host()` before reading `h_out`."""
+        hp = self._host_pipeline()
+        k = hp['k'] & 1
+        hp['k'] += 1
+        cur = torch.cuda.current_stream()
+        if hp['stage'][k] is None:
+            hp['stage'][k] = (torch.empty_like(h_planes, device=self.device), torch.empty_like(h_cameras, device=self.device),
+                              torch.empty_like(h_u, device=self.device))
+            hp['out'][k] = torch.empty(self.batch, 3, 512, 512, device=self.device)
+            hp['in_free'][k].record(cur); hp['out_free'][k].record(cur)
+        sp, sc, su = hp['stage'][k]
+        with torch.cuda.stream(hp['copy_in']):
+            hp['copy_in'].wait_event(hp['in_free'][k])                 # the step that last read this slot is done
+            sp.copy_(h_planes, non_blocking=True); sc.copy_(h_cameras, non_blocking=True); su.copy_(h_u, non_blocking=True)
+            hp['in_ready'][k].record(hp['copy_in'])
+        cur.wait_event(hp['in_ready'][k])
+        out = self.step(sp, sc, su)
+        hp['in_free'][k].record(cur)
+        cur.wait_event(hp['out_free'][k])
+        mine = out[self.rank * self.batch:(self.rank + 1) * self.batch] if out.shape[0] > self.batch else out
+        hp['out'][k].copy_(mine, non_blocking=True)
+        hp['out_ready'][k].record(cur)
+        with torch.cuda.stream(hp['copy_out']):
+            hp['copy_out'].wait_event(hp['out_ready'][k])
+            h_out.copy_(hp['out'][k], non_blocking=True)
+            hp['out_free'][k].record(hp['copy_out'])
+
+    def sync_host(self) -> None:
+        hp = self._host_pipeline()
+        hp['copy_in'].synchronize(); hp['copy_out'].synchronize(); torch.cuda.current_stream().synchronize()
+
     def static_inputs(self):
         """(planes, cameras, u_coarse) static buffers of the captured graph: a producer may write its outputs straight into them
         and call step() with these very tensors to skip the copy-in."""

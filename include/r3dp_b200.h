@@ -159,6 +159,13 @@ int r3dp_sr_tc_layer(const void* x_f16, const void* wp_f16, const float* bias, i
                      int up, void* y_f16, void* scratch, r3dp_stream_t stream);
 int r3dp_sr_tc_torgb(const void* x_f16, const float* wrgb, const float* brgb, const float* img_prev, int N, int Nw, int C,
                      int H, int W, float* img_out, r3dp_stream_t stream);
+/* conv3x3 (up == 1) + bias/lrelu -> y fp16 NHWC, fused with the block's ToRGB + upsampled skip -> img_out fp32 NCHW
+ * (block0.conv1 + block0.torgb of SynthesisBlock.forward, networks_stylegan2.py:455-469). */
+int r3dp_sr_tc_layer_torgb(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
+                           const float* img_prev, int N, int Nw, int I, int O, int H, int W, void* y_f16, float* img_out,
+                           r3dp_stream_t stream);
+/* r3dp_sr_tc_input for a channels-last fp32 source [N,h,w,C] (the renderer's [N,M,C] output viewed as an image). */
+int r3dp_sr_tc_input_nhwc(const float* x_nhwc, int N, int C, int h, int w, int size, void* y_f16, r3dp_stream_t stream);
 int r3dp_sr_tc_last_layer(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
                           const float* img_prev, int N, int Nw, int I, int H, int W, float* img_out, r3dp_stream_t stream);
 

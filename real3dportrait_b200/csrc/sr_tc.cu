@@ -281,29 +281,37 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 // =====================================================================================================================
 // conv_tc2_kernel<R>: persistent implicit-GEMM conv, R output rows (R x 128 pixels) x 128 couts per tile.
 //
-// Why: the v1 kernel above re-reads A (activations) once per tap and B (weights) once per 128-pixel tile: 32 MAC per L2
-// byte, i.e. L2-bandwidth-bound at ~1/3 of the tensor peak (measured 436 TFLOP/s).  Here
-//   * an input ROW STRIP {64 ch, 130 px} is loaded once per (64-channel chunk) and serves all horizontal taps: the UMMA
-//     smem descriptor simply starts 128 B x shift later (same absolute-address 128-byte swizzle TMA wrote), and serves
-//     the R output rows that touch it vertically;
-//   * every weight tile {64 ch, 128 couts} of a tap is used by R MMA groups (one per output row) before it is released;
-//   => (R+2) x 16.6 KB + 9 x 16 KB per 9R MMA groups: 89 MAC/B at R=2, 153 MAC/B at R=4.
-// Two mbarrier rings (A strips, B taps) are filled by one TMA lane in exactly the order the MMA lane consumes them;
-// accumulators (R x 128 TMEM columns) are double-buffered when they fit (R <= 2) so the epilogue overlaps the next tile.
+// Why: ncu on the v1 kernel showed 58 % tensor-pipe activity on the largest layer, L2 at 65 % / 92 % hits: not L2-bound, but
+// with 128x128 tiles the two smem operands cost 128 B/clk of shared-memory reads per MMA, the same port TMA fills.  v2 cuts the
+// fill traffic and the per-tile overheads:
+//   * an input ROW STRIP {64 ch, 130 px} is loaded once per 64-channel chunk and serves all horizontal taps (the UMMA smem
+//     descriptor starts 128 B x shift later; the 128-byte swizzle is a function of the ABSOLUTE smem address, so the descriptor's
+//     base_offset stays 0 - verified on B200) and the R output rows that touch it vertically;
+//   * every weight tile {64 ch, 128 couts} of a tap is used by R MMA groups before it is released;
+//   * persistent CTAs, accumulators double-buffered in TMEM (R x 128 columns x 2), so the epilogue of tile i overlaps tile i+1;
+//   * the four output-parity phases of a transposed conv are units of ONE launch;
+//   * a unit = (image, phase, row group, x block); the CTA loops over the cout blocks of its unit so that ToRGB partial sums of a
+//     256-channel layer stay in registers (block0's ToRGB is fused like the last layer's).
+// Two mbarrier rings (A strips, B taps) are filled by one TMA lane in exactly the order the MMA lane consumes them.
 // =====================================================================================================================
 constexpr int A2_ROWS = 130, A2_BYTES = A2_ROWS * 128, A2_SLOT = 17408;       // 17 x 1024: every slot keeps the swizzle alignment
 struct Taps2 {
     int n, ngroups;                 // taps sorted by (dy, dx); group = taps sharing dy
-    int dyi[9], shift[9], widx[9];  // group index, horizontal shift (dx - dx_min, in pixels), weight tap index
+    int dyi[9], shift[9], widx[9];  // group index, horizontal shift (dx + 1, in pixels: strips start at x0 - 1), weight tap index
     int gstart[4];                  // first tap of each group (+ sentinel)
     int dy_min;
 };
-struct Conv2Args {
+struct Phase2 {
     Taps2 taps;
-    int k_chunks, tiles_x, row_groups, rows, n_blocks, n_images, total_tiles;
-    int w_shared, mode, base_off_mode;
-    __half* out; int out_H, out_W, out_C, oy_mul, oy_off, ox_mul, ox_off;
-    const float* bias; const float* wrgb; const float* brgb; const float* img_prev; float* img_out;
+    int rows, oy_off, ox_off;       // valid grid rows of this phase; output pixel = (row*oy_mul + oy_off, col*ox_mul + ox_off)
+};
+enum Mode2 { kActRgb = 3 };         // kStoreAct + ToRGB/skip accumulated over the cout blocks (in addition to Mode)
+struct Conv2Args {
+    Phase2 ph[4];
+    int n_phases, k_chunks, tiles_x, row_groups, n_blocks, n_images, total_units;
+    int w_shared, mode;
+    __half* out; int out_H, out_W, out_C, oy_mul, ox_mul;
+    const float* bias; const float* wrgb; const float* brgb; const float* img_prev; float* img_out; int img_H, img_W;
 };
 
 template <int R> struct Cfg2 {
@@ -311,11 +319,40 @@ template <int R> struct Cfg2 {
     static constexpr int NB = (R >= 4) ? 5 : 8;
     static constexpr int NACC = (R * BN * 2 <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (R * BN * NACC <= 128) ? 128 : (R * BN * NACC <= 256 ? 256 : 512);
-    static constexpr int SMEM = NA * A2_SLOT + NB * B_BYTES + 1024 + 4096;
+    static constexpr int SMEM = NA * A2_SLOT + NB * B_BYTES + 1024 + 5120;
 };
 
-__device__ __forceinline__ uint64_t umma_desc_sw128_shift(uint32_t saddr, int base_off) {
-    return umma_desc_sw128(saddr) | ((uint64_t)(base_off & 7) << 49);
+// FIR-upsampled skip image (upsample2d, upfirdn2d.py:317-354) at output pixel (Y,X): zero-insert x2, pad (2,1,2,1), [1,3,3,1]^2/64 * 4
+__device__ __forceinline__ float upsampled_skip(const float* __restrict__ ip, int h, int w, int Y, int X) {
+    const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+    float acc = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int zy = Y + u - 2;
+        if (zy < 0 || (zy & 1) || (zy >> 1) >= h) continue;
+        float rowv = 0.f;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int zx = X + v - 2;
+            if (zx < 0 || (zx & 1) || (zx >> 1) >= w) continue;
+            rowv = fmaf(k4[v], __ldg(ip + (size_t)(zy >> 1) * w + (zx >> 1)), rowv);
+        }
+        acc = fmaf(k4[u], rowv, acc);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ void store_half32(__half* dst, const float* f) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        __half2 h0 = __floats2half2_rn(f[8 * v + 0], f[8 * v + 1]), h1 = __floats2half2_rn(f[8 * v + 2], f[8 * v + 3]);
+        __half2 h2 = __floats2half2_rn(f[8 * v + 4], f[8 * v + 5]), h3 = __floats2half2_rn(f[8 * v + 6], f[8 * v + 7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        d4[v] = pk;
+    }
 }
 
 template <int R>
@@ -334,11 +371,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc2_kernel(const __grid_cons
     uint64_t* acc_full = b_empty + C::NB;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    float* s_bias = reinterpret_cast<float*>(tail + 512);                    // [n_blocks<=2][128]
-    float* s_wrgb = s_bias + 256;                                            // [3][128]
+    float* s_bias = reinterpret_cast<float*>(tail + 512);                    // [256]
+    float* s_wrgb = s_bias + 256;                                            // [3][n_blocks*128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int DY = a.taps.ngroups, NS = R + DY - 1;
+    const int units_per_image = a.n_phases * a.row_groups * a.tiles_x;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
@@ -361,11 +398,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc2_kernel(const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // tile index -> (image n, cout block, row group, x block); x fastest so neighbouring CTAs share strips in L2
-    auto decode = [&](int tile, int& n, int& nblk, int& row0, int& col0) {
-        const int xb = tile % a.tiles_x; int r = tile / a.tiles_x;
-        const int rg = r % a.row_groups; r /= a.row_groups;
-        nblk = r % a.n_blocks; n = r / a.n_blocks;
+    // unit index -> (image n, phase, row group, x block); x fastest so neighbouring CTAs share strips in L2
+    auto decode = [&](int unit, int& n, int& ph, int& row0, int& col0) {
+        n = unit / units_per_image; int r = unit - n * units_per_image;
+        const int xb = r % a.tiles_x; r /= a.tiles_x;
+        const int rg = r % a.row_groups; ph = r / a.row_groups;
         row0 = rg * R; col0 = xb * BM;
     };
 
@@ -373,179 +410,155 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc2_kernel(const __grid_cons
         // ===== TMA producer (one lane): strips and taps in consumption order =====
         if (lane == 0) {
             uint32_t aq = 0, bq = 0;                                         // running strip / tap sequence numbers
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                int n, nblk, row0, col0; decode(tile, n, nblk, row0, col0);
+            for (int unit = blockIdx.x; unit < a.total_units; unit += gridDim.x) {
+                int n, ph, row0, col0; decode(unit, n, ph, row0, col0);
+                const Taps2& tp = a.ph[ph].taps;
+                const int DY = tp.ngroups;
                 const int wn = a.w_shared ? 0 : n;
-                for (int kc = 0; kc < a.k_chunks; ++kc) {
-                    for (int d = 0; d < DY; ++d) {
-                        const int s_lo = d == 0 ? 0 : R - 1 + d, s_hi = R - 1 + d;
-                        for (int s = s_lo; s <= s_hi; ++s, ++aq) {
-                            const int slot = aq % C::NA;
-                            mbar_wait(&a_empty[slot], ((aq / C::NA) & 1) ^ 1);
-                            mbar_expect_tx(&a_full[slot], A2_BYTES);
-                            tma_load_4d(a_ring + slot * A2_SLOT, &tmA, &a_full[slot], kc * BK, col0 - 1, row0 + a.taps.dy_min + s, n);
+                for (int nblk = 0; nblk < a.n_blocks; ++nblk)
+                    for (int kc = 0; kc < a.k_chunks; ++kc)
+                        for (int d = 0; d < DY; ++d) {
+                            const int s_lo = d == 0 ? 0 : R - 1 + d, s_hi = R - 1 + d;
+                            for (int s = s_lo; s <= s_hi; ++s, ++aq) {
+                                const int slot = aq % C::NA;
+                                mbar_wait(&a_empty[slot], ((aq / C::NA) & 1) ^ 1);
+                                mbar_expect_tx(&a_full[slot], A2_BYTES);
+                                tma_load_4d(a_ring + slot * A2_SLOT, &tmA, &a_full[slot], kc * BK, col0 - 1, row0 + tp.dy_min + s, n);
+                            }
+                            for (int t = tp.gstart[d]; t < tp.gstart[d + 1]; ++t, ++bq) {
+                                const int slot = bq % C::NB;
+                                mbar_wait(&b_empty[slot], ((bq / C::NB) & 1) ^ 1);
+                                mbar_expect_tx(&b_full[slot], B_BYTES);
+                                tma_load_4d(b_ring + slot * B_BYTES, &tmB, &b_full[slot], kc * BK, nblk * BN, tp.widx[t], wn);
+                            }
                         }
-                        for (int t = a.taps.gstart[d]; t < a.taps.gstart[d + 1]; ++t, ++bq) {
-                            const int slot = bq % C::NB;
-                            mbar_wait(&b_empty[slot], ((bq / C::NB) & 1) ^ 1);
-                            mbar_expect_tx(&b_full[slot], B_BYTES);
-                            tma_load_4d(b_ring + slot * B_BYTES, &tmB, &b_full[slot], kc * BK, nblk * BN, a.taps.widx[t], wn);
-                        }
-                    }
-                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         uint32_t aq = 0, bq = 0, it = 0;
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-            const int buf = it % C::NACC;
-            mbar_wait(&acc_empty[buf], (((it / C::NACC) & 1) ^ 1));
-            tc_fence_after();
-            const uint32_t acc0 = tmem_base + buf * (R * BN);
-            for (int kc = 0; kc < a.k_chunks; ++kc) {
-                const uint32_t a_base = aq;                                   // sequence number of strip 0 of this chunk
-                for (int d = 0; d < DY; ++d) {
-                    const int s_lo = d == 0 ? 0 : R - 1 + d, s_hi = R - 1 + d;
-                    for (int s = s_lo; s <= s_hi; ++s, ++aq) mbar_wait(&a_full[aq % C::NA], (aq / C::NA) & 1);
-                    for (int t = a.taps.gstart[d]; t < a.taps.gstart[d + 1]; ++t, ++bq) {
-                        const int bslot = bq % C::NB;
-                        mbar_wait(&b_full[bslot], (bq / C::NB) & 1);
-                        tc_fence_after();
-                        if (lane == 0) {
-                            const uint64_t db = umma_desc_sw128(smem_u32(b_ring + bslot * B_BYTES));
-                            const int sh = a.taps.shift[t];
+        for (int unit = blockIdx.x; unit < a.total_units; unit += gridDim.x) {
+            int n, ph, row0, col0; decode(unit, n, ph, row0, col0);
+            const Taps2& tp = a.ph[ph].taps;
+            const int DY = tp.ngroups, NS = R + DY - 1;
+            for (int nblk = 0; nblk < a.n_blocks; ++nblk, ++it) {
+                const int buf = it % C::NACC;
+                mbar_wait(&acc_empty[buf], (((it / C::NACC) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t acc0 = tmem_base + buf * (R * BN);
+                for (int kc = 0; kc < a.k_chunks; ++kc) {
+                    const uint32_t a_base = aq;                               // sequence number of strip 0 of this chunk
+                    for (int d = 0; d < DY; ++d) {
+                        const int s_lo = d == 0 ? 0 : R - 1 + d, s_hi = R - 1 + d;
+                        for (int s = s_lo; s <= s_hi; ++s, ++aq) mbar_wait(&a_full[aq % C::NA], (aq / C::NA) & 1);
+                        for (int t = tp.gstart[d]; t < tp.gstart[d + 1]; ++t, ++bq) {
+                            const int bslot = bq % C::NB;
+                            mbar_wait(&b_full[bslot], (bq / C::NB) & 1);
+                            tc_fence_after();
+                            if (lane == 0) {
+                                const uint64_t db = umma_desc_sw128(smem_u32(b_ring + bslot * B_BYTES));
+                                const int sh = tp.shift[t];
 #pragma unroll
-                            for (int j = 0; j < R; ++j) {
-                                const uint32_t sq = a_base + j + d;
-                                const uint32_t sa = smem_u32(a_ring + (sq % C::NA) * A2_SLOT) + 128 * sh;
-                                const uint64_t da = umma_desc_sw128_shift(sa, a.base_off_mode ? sh : 0);
+                                for (int j = 0; j < R; ++j) {
+                                    const uint32_t sq = a_base + j + d;
+                                    const uint64_t da = umma_desc_sw128(smem_u32(a_ring + (sq % C::NA) * A2_SLOT) + 128 * sh);
 #pragma unroll
-                                for (int k = 0; k < BK / UMMA_K; ++k)
-                                    tc_mma_f16(acc0 + j * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kc | t | k) != 0);
+                                    for (int k = 0; k < BK / UMMA_K; ++k)
+                                        tc_mma_f16(acc0 + j * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kc | t | k) != 0);
+                                }
+                                tc_commit(&b_empty[bslot]);
                             }
-                            tc_commit(&b_empty[bslot]);
+                            __syncwarp();
+                        }
+                        // strips no later group needs: strip d after group d; everything left after the last group
+                        if (lane == 0) {
+                            if (d < DY - 1) tc_commit(&a_empty[(a_base + d) % C::NA]);
+                            else for (int s = DY - 1; s < NS; ++s) tc_commit(&a_empty[(a_base + s) % C::NA]);
                         }
                         __syncwarp();
                     }
-                    // strips no later group needs: strip d after group d; everything left after the last group
-                    if (lane == 0) {
-                        if (d < DY - 1) tc_commit(&a_empty[(a_base + d) % C::NA]);
-                        else for (int s = DY - 1; s < NS; ++s) tc_commit(&a_empty[(a_base + s) % C::NA]);
-                    }
-                    __syncwarp();
                 }
+                if (lane == 0) tc_commit(&acc_full[buf]);
+                __syncwarp();
             }
-            if (lane == 0) tc_commit(&acc_full[buf]);
-            __syncwarp();
         }
     } else {
-        // ===== epilogue =====
+        // ===== epilogue: warps 2..5 own TMEM lanes [32*(warp%4), +32) =====
         const int q = warp & 3, m = q * 32 + lane;
+        const bool want_rgb = (a.mode == kToRgbFinal) || (a.mode == kActRgb);
+        const int CW = a.n_blocks * BN;                                      // channels ToRGB sums over
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-            int n, nblk, row0, col0; decode(tile, n, nblk, row0, col0);
+        int n_loaded = -1;
+        for (int unit = blockIdx.x; unit < a.total_units; unit += gridDim.x) {
+            int n, ph, row0, col0; decode(unit, n, ph, row0, col0);
+            const Phase2& P = a.ph[ph];
             const int wn = a.w_shared ? 0 : n;
-            const int buf = it % C::NACC;
-            if (a.mode == kToRgbFinal) {
-                // all four epilogue warps must be done with the previous tile's s_wrgb before it is overwritten
+            if (want_rgb && wn != n_loaded) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");               // all four epilogue warps are done with the old weights
+                for (int e = threadIdx.x - 64; e < 3 * CW; e += 128) s_wrgb[e] = a.wrgb[(size_t)wn * 3 * CW + e];
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int e = threadIdx.x - 64; e < 3 * BN; e += 128) s_wrgb[e] = a.wrgb[(size_t)wn * 3 * BN + e];
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                n_loaded = wn;
             }
-            mbar_wait(&acc_full[buf], (it / C::NACC) & 1);
-            tc_fence_after();
-            const int gcol = col0 + m, X = gcol * a.ox_mul + a.ox_off;
-#pragma unroll 1
-            for (int j = 0; j < R; ++j) {
-                const int row = row0 + j;
-                const int Y = row * a.oy_mul + a.oy_off;
-                const bool in_img = (row < a.rows) && (Y < a.out_H) && (X < a.out_W);
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (R * BN) + j * BN;
-                float rgb[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t r[32];
-                    tc_ld32(taddr + c0, r);
-                    if (a.mode == kStoreRaw) {
-                        if (in_img) {
-                            uint4* dst = reinterpret_cast<uint4*>(a.out + (((size_t)n * a.out_H + Y) * a.out_W + X) * a.out_C + nblk * BN + c0);
+            const int gcol = col0 + m, X = gcol * a.ox_mul + P.ox_off;
+            float rgb[R][3];
 #pragma unroll
-                            for (int v = 0; v < 4; ++v) {
-                                __half2 h0 = __floats2half2_rn(__uint_as_float(r[8 * v + 0]), __uint_as_float(r[8 * v + 1]));
-                                __half2 h1 = __floats2half2_rn(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3]));
-                                __half2 h2 = __floats2half2_rn(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5]));
-                                __half2 h3 = __floats2half2_rn(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7]));
-                                uint4 pk;
-                                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                                dst[v] = pk;
-                            }
-                        }
-                    } else {
+            for (int j = 0; j < R; ++j) { rgb[j][0] = 0.f; rgb[j][1] = 0.f; rgb[j][2] = 0.f; }
+            for (int nblk = 0; nblk < a.n_blocks; ++nblk, ++it) {
+                const int buf = it % C::NACC;
+                mbar_wait(&acc_full[buf], (it / C::NACC) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int row = row0 + j;
+                    const int Y = row * a.oy_mul + P.oy_off;
+                    const bool in_img = (row < P.rows) && (Y < a.out_H) && (X < a.out_W);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (R * BN) + j * BN;
+                    __half* dst = a.out + (((size_t)n * a.out_H + Y) * a.out_W + X) * a.out_C + nblk * BN;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        uint32_t r[32];
+                        tc_ld32(taddr + c0, r);
                         float f[32];
+                        if (a.mode == kStoreRaw) {
 #pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) {
-                            float v = __uint_as_float(r[jj]) + s_bias[nblk * BN + c0 + jj];
-                            f[jj] = (v < 0.f ? v * 0.2f : v) * 1.4142135623730951f;
-                        }
-                        if (a.mode == kStoreAct) {
-                            if (in_img) {
-                                uint4* dst = reinterpret_cast<uint4*>(a.out + (((size_t)n * a.out_H + Y) * a.out_W + X) * a.out_C + nblk * BN + c0);
-#pragma unroll
-                                for (int v = 0; v < 4; ++v) {
-                                    __half2 h0 = __floats2half2_rn(f[8 * v + 0], f[8 * v + 1]), h1 = __floats2half2_rn(f[8 * v + 2], f[8 * v + 3]);
-                                    __half2 h2 = __floats2half2_rn(f[8 * v + 4], f[8 * v + 5]), h3 = __floats2half2_rn(f[8 * v + 6], f[8 * v + 7]);
-                                    uint4 pk;
-                                    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                                    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                                    dst[v] = pk;
-                                }
-                            }
+                            for (int jj = 0; jj < 32; ++jj) f[jj] = __uint_as_float(r[jj]);
                         } else {
 #pragma unroll
+                            for (int jj = 0; jj < 32; ++jj) {
+                                const float v = __uint_as_float(r[jj]) + s_bias[nblk * BN + c0 + jj];
+                                f[jj] = (v < 0.f ? v * 0.2f : v) * 1.4142135623730951f;      // bias_act lrelu, gain sqrt(2)
+                            }
+                        }
+                        if (a.mode != kToRgbFinal && in_img) store_half32(dst + c0, f);
+                        if (want_rgb) {
+#pragma unroll
                             for (int c = 0; c < 3; ++c) {
-                                const float4* w4 = reinterpret_cast<const float4*>(s_wrgb + c * BN + c0);
+                                const float4* w4 = reinterpret_cast<const float4*>(s_wrgb + c * CW + nblk * BN + c0);
+                                float acc = rgb[j][c];
 #pragma unroll
                                 for (int j4 = 0; j4 < 8; ++j4) {
                                     const float4 w = w4[j4];
-                                    rgb[c] = fmaf(f[4 * j4 + 0], w.x, rgb[c]); rgb[c] = fmaf(f[4 * j4 + 1], w.y, rgb[c]);
-                                    rgb[c] = fmaf(f[4 * j4 + 2], w.z, rgb[c]); rgb[c] = fmaf(f[4 * j4 + 3], w.w, rgb[c]);
+                                    acc = fmaf(f[4 * j4 + 0], w.x, acc); acc = fmaf(f[4 * j4 + 1], w.y, acc);
+                                    acc = fmaf(f[4 * j4 + 2], w.z, acc); acc = fmaf(f[4 * j4 + 3], w.w, acc);
                                 }
+                                rgb[j][c] = acc;
                             }
                         }
                     }
-                }
-                if (a.mode == kToRgbFinal && in_img) {
-                    const int h = a.out_H / 2, w = a.out_W / 2;
-                    const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+                    if (want_rgb && nblk == a.n_blocks - 1 && in_img) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        float acc = 0.f;
-                        if (a.img_prev) {
-                            const float* ip = a.img_prev + ((size_t)n * 3 + c) * h * w;
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int zy = Y + u - 2;
-                                if (zy < 0 || (zy & 1) || (zy >> 1) >= h) continue;
-                                float rowv = 0.f;
-#pragma unroll
-                                for (int v = 0; v < 4; ++v) {
-                                    const int zx = X + v - 2;
-                                    if (zx < 0 || (zx & 1) || (zx >> 1) >= w) continue;
-                                    rowv = fmaf(k4[v], __ldg(ip + (size_t)(zy >> 1) * w + (zx >> 1)), rowv);
-                                }
-                                acc = fmaf(k4[u], rowv, acc);
-                            }
+                        for (int c = 0; c < 3; ++c) {
+                            const float skip = a.img_prev ? upsampled_skip(a.img_prev + ((size_t)n * 3 + c) * (a.img_H / 2) * (a.img_W / 2),
+                                                                           a.img_H / 2, a.img_W / 2, Y, X) : 0.f;
+                            a.img_out[(((size_t)n * 3 + c) * a.img_H + Y) * a.img_W + X] = rgb[j][c] + a.brgb[c] + skip;
                         }
-                        a.img_out[(((size_t)n * 3 + c) * a.out_H + Y) * a.out_W + X] = rgb[c] + a.brgb[c] + acc;
                     }
                 }
+                // this warp is done reading the accumulator buffer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
             }
-            // this warp is done reading the accumulator buffer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
         }
     }
     tc_fence_before();
@@ -837,6 +850,7 @@ static int make_map_fir(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d
 }
 
 static int launch_conv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, const ConvArgs& a1, cudaStream_t st);
+static int launch_upconv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, __half* yb, const float* bias, cudaStream_t st);
 static int tc_version();
 static int launch_conv(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, ConvArgs a, cudaStream_t st) {
     if (tc_version() == 2) return launch_conv2(x, N, H, W, Cp, wp, Nw, O, a, st);
@@ -863,13 +877,6 @@ static int tc_version() {                      // R3DP_TC_KERNEL=1 selects the s
     if (v < 0) { const char* e = getenv("R3DP_TC_KERNEL"); v = (e && e[0] == '1') ? 1 : 2; }
     return v;
 }
-// Row-shifted strip views keep the descriptor's base_offset field 0: the 128-byte swizzle is a function of the ABSOLUTE
-// shared-memory address (as TMA wrote it).  Verified on B200: base_offset = shift gives wrong results, 0 is bit-exact with v1.
-static int tc_base_off_mode() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("R3DP_TC_BASEOFF"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v;
-}
 static int tc_rows() {                         // R3DP_TC_ROWS = 1 | 2 | 4 output rows per tile (default 2: double-buffered accumulators)
     static int v = -1;
     if (v < 0) { const char* e = getenv("R3DP_TC_ROWS"); v = e ? atoi(e) : 2; if (v != 1 && v != 2 && v != 4) v = 2; }
@@ -877,23 +884,23 @@ static int tc_rows() {                         // R3DP_TC_ROWS = 1 | 2 | 4 outpu
 }
 
 template <int R>
-static int launch_conv2_r(const CUtensorMap& tmA, const CUtensorMap& tmB, Conv2Args a, cudaStream_t st) {
+static int launch_conv2_r(const CUtensorMap& tmA, const CUtensorMap& tmB, Conv2Args a, int max_rows, cudaStream_t st) {
     using C = Cfg2<R>;
     static bool attr_set = false;
     if (!attr_set) {
         R3DP_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    a.row_groups = (a.rows + R - 1) / R;
-    a.total_tiles = a.tiles_x * a.row_groups * a.n_blocks * a.n_images;
-    const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
+    a.row_groups = (max_rows + R - 1) / R;
+    a.total_units = a.n_images * a.n_phases * a.row_groups * a.tiles_x;
+    const int grid = a.total_units < sm_count() ? a.total_units : sm_count();
     conv_tc2_kernel<R><<<grid, kThreads, C::SMEM, st>>>(tmA, tmB, a);
     R3DP_LAUNCH_CHECK();
     count_launches(1);
     return 0;
 }
 
-// taps given as (dy, dx, widx) lists -> sorted/grouped Taps2
+// taps given as (dy, dx, widx) lists -> sorted/grouped Taps2 (dy groups are contiguous for 3x3 and every transposed-conv phase)
 static void fill_taps2(Taps2& t2, const Taps& t) {
     int order[9], n = t.n;
     for (int i = 0; i < n; ++i) order[i] = i;
@@ -902,8 +909,8 @@ static void fill_taps2(Taps2& t2, const Taps& t) {
             const int a = order[i], b = order[j];
             if (t.dy[b] < t.dy[a] || (t.dy[b] == t.dy[a] && t.dx[b] < t.dx[a])) { order[i] = b; order[j] = a; }
         }
-    int dy_min = 99, dx_min = 99;
-    for (int i = 0; i < n; ++i) { if (t.dy[i] < dy_min) dy_min = t.dy[i]; if (t.dx[i] < dx_min) dx_min = t.dx[i]; }
+    int dy_min = 99;
+    for (int i = 0; i < n; ++i) if (t.dy[i] < dy_min) dy_min = t.dy[i];
     t2.n = n; t2.dy_min = dy_min; t2.ngroups = 0;
     int last = -99;
     for (int i = 0; i < n; ++i) {
@@ -914,25 +921,45 @@ static void fill_taps2(Taps2& t2, const Taps& t) {
     t2.gstart[t2.ngroups] = n;
 }
 
-static int launch_conv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, const ConvArgs& a1, cudaStream_t st) {
+static int run_conv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, Conv2Args& a, int max_rows, cudaStream_t st) {
     CUtensorMap tmA, tmB;
     if (make_map_4d_box(&tmA, x, (uint64_t)Cp, (uint64_t)W, (uint64_t)H, (uint64_t)N, A2_ROWS)) return 1;
     if (make_map_4d_box(&tmB, wp, (uint64_t)Cp, (uint64_t)O, 9, (uint64_t)Nw, BN)) return 1;
-    Conv2Args a = {};
-    fill_taps2(a.taps, a1.taps);
-    // contiguous dy groups are required by the strip schedule (true for 3x3 and for every transposed-conv phase)
-    a.k_chunks = Cp / BK; a.tiles_x = a1.tiles_x; a.rows = a1.rows; a.n_blocks = O / BN; a.n_images = N;
-    a.w_shared = (Nw == 1); a.mode = a1.mode; a.base_off_mode = tc_base_off_mode();
-    a.out = a1.out; a.out_H = a1.out_H; a.out_W = a1.out_W; a.out_C = a1.out_C;
-    a.oy_mul = a1.oy_mul; a.oy_off = a1.oy_off; a.ox_mul = a1.ox_mul; a.ox_off = a1.ox_off;
-    a.bias = a1.bias; a.wrgb = a1.wrgb; a.brgb = a1.brgb; a.img_prev = a1.img_prev; a.img_out = a1.img_out;
-    R3DP_REQUIRE(a.n_blocks <= 2, "conv_tc2: at most 256 output channels");
+    a.k_chunks = Cp / BK; a.tiles_x = W / BM; a.n_blocks = O / BN; a.n_images = N; a.w_shared = (Nw == 1);
+    R3DP_REQUIRE(a.n_blocks >= 1 && a.n_blocks <= 2, "conv_tc2: 128 or 256 output channels");
     switch (tc_rows()) {
-        case 1: return launch_conv2_r<1>(tmA, tmB, a, st);
-        case 2: return launch_conv2_r<2>(tmA, tmB, a, st);
-        case 4: return launch_conv2_r<4>(tmA, tmB, a, st);
-        default: return launch_conv2_r<2>(tmA, tmB, a, st);
+        case 1: return launch_conv2_r<1>(tmA, tmB, a, max_rows, st);
+        case 4: return launch_conv2_r<4>(tmA, tmB, a, max_rows, st);
+        default: return launch_conv2_r<2>(tmA, tmB, a, max_rows, st);
     }
+}
+
+// v1-style single-phase description -> v2 launch
+static int launch_conv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, const ConvArgs& a1, cudaStream_t st) {
+    Conv2Args a = {};
+    a.n_phases = 1;
+    fill_taps2(a.ph[0].taps, a1.taps);
+    a.ph[0].rows = a1.rows; a.ph[0].oy_off = a1.oy_off; a.ph[0].ox_off = a1.ox_off;
+    a.mode = a1.mode; a.out = a1.out; a.out_H = a1.out_H; a.out_W = a1.out_W; a.out_C = a1.out_C; a.oy_mul = a1.oy_mul; a.ox_mul = a1.ox_mul;
+    a.bias = a1.bias; a.wrgb = a1.wrgb; a.brgb = a1.brgb; a.img_prev = a1.img_prev; a.img_out = a1.img_out; a.img_H = a1.out_H; a.img_W = a1.out_W;
+    return run_conv2(x, N, H, W, Cp, wp, Nw, O, a, a1.rows, st);
+}
+
+// all four output-parity phases of the stride-2 transposed conv in ONE persistent launch (raw fp16 result on the (2H+1)x(2W+1) grid)
+static int launch_upconv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, __half* yb, const float* bias, cudaStream_t st) {
+    Conv2Args a = {};
+    a.n_phases = 4;
+    for (int pa = 0; pa < 2; ++pa)
+        for (int pb = 0; pb < 2; ++pb) {
+            Taps t = {};
+            for (int ky = pa; ky < 3; ky += 2)
+                for (int kx = pb; kx < 3; kx += 2) { const int i = t.n++; t.dy[i] = -(ky >> 1); t.dx[i] = -(kx >> 1); t.widx[i] = ky * 3 + kx; }
+            Phase2& P = a.ph[pa * 2 + pb];
+            fill_taps2(P.taps, t);
+            P.rows = pa ? H : H + 1; P.oy_off = pa; P.ox_off = pb;
+        }
+    a.mode = kStoreRaw; a.out = yb; a.out_H = 2 * H + 1; a.out_W = 2 * W + 1; a.out_C = O; a.oy_mul = a.ox_mul = 2; a.bias = bias;
+    return run_conv2(x, N, H, W, Cp, wp, Nw, O, a, H + 1, st);
 }
 
 }  // namespace tc
@@ -986,19 +1013,23 @@ extern "C" int r3dp_sr_tc_layer(const void* x_f16, const void* wp_f16, const flo
     }
     R3DP_REQUIRE(scratch, "sr_tc_layer: up=2 needs scratch");
     __half* yb = reinterpret_cast<__half*>(scratch);
-    a.mode = kStoreRaw; a.out = yb; a.out_H = 2 * H + 1; a.out_W = 2 * W + 1; a.out_C = O; a.oy_mul = a.ox_mul = 2;
-    a.tiles_x = W / BM;
-    for (int pa = 0; pa < 2; ++pa)
-        for (int pb = 0; pb < 2; ++pb) {
-            a.oy_off = pa; a.ox_off = pb; a.rows = pa ? H : H + 1;
-            a.taps.n = 0;
-            for (int ky = pa; ky < 3; ky += 2)
-                for (int kx = pb; kx < 3; kx += 2) {
-                    const int t = a.taps.n++;
-                    a.taps.dy[t] = -(ky >> 1); a.taps.dx[t] = -(kx >> 1); a.taps.widx[t] = ky * 3 + kx;
-                }
-            if (launch_conv(x_f16, N, H, W, Ip, wp_f16, Nw, O, a, st)) return 1;
-        }
+    if (tc_version() == 2) {
+        if (launch_upconv2(x_f16, N, H, W, Ip, wp_f16, Nw, O, yb, bias, st)) return 1;
+    } else {
+        a.mode = kStoreRaw; a.out = yb; a.out_H = 2 * H + 1; a.out_W = 2 * W + 1; a.out_C = O; a.oy_mul = a.ox_mul = 2;
+        a.tiles_x = W / BM;
+        for (int pa = 0; pa < 2; ++pa)
+            for (int pb = 0; pb < 2; ++pb) {
+                a.oy_off = pa; a.ox_off = pb; a.rows = pa ? H : H + 1;
+                a.taps.n = 0;
+                for (int ky = pa; ky < 3; ky += 2)
+                    for (int kx = pb; kx < 3; kx += 2) {
+                        const int t = a.taps.n++;
+                        a.taps.dy[t] = -(ky >> 1); a.taps.dx[t] = -(kx >> 1); a.taps.widx[t] = ky * 3 + kx;
+                    }
+                if (launch_conv(x_f16, N, H, W, Ip, wp_f16, Nw, O, a, st)) return 1;
+            }
+    }
     {
         R3DP_REQUIRE(Ip <= 256, "sr_tc_layer: up=2 supports at most 256 input channels");
         dim3 grid((2 * H + 1 + kEdgeRows - 1) / kEdgeRows, (O + kEdgeCo - 1) / kEdgeCo, N);
@@ -1046,6 +1077,74 @@ extern "C" int r3dp_sr_tc_torgb(const void* x_f16, const float* wrgb, const floa
     dim3 grid((H * W + 255) / 256, N);
     torgb_f16_kernel<<<grid, 256, 3 * C * sizeof(float), as_stream(stream)>>>(reinterpret_cast<const __half*>(x_f16), wrgb, brgb, img_prev, H, W, C,
                                                                               Nw == 1, img_out);
+    R3DP_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+// SynthesisLayer (up == 1) fused with the block's ToRGB + skip (networks_stylegan2.py:463-469): y [N,H,W,O] fp16 AND
+// img_out [N,3,H,W] fp32 = upsample2d(img_prev [N,3,H/2,W/2]) + conv1x1(y, wrgb [Nw,3,O]) + brgb.  O = 128 or 256.
+extern "C" int r3dp_sr_tc_layer_torgb(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
+                                      const float* img_prev, int N, int Nw, int I, int O, int H, int W, void* y_f16, float* img_out,
+                                      r3dp_stream_t stream) {
+    R3DP_REQUIRE(x_f16 && wp_f16 && bias && wrgb && brgb && y_f16 && img_out, "sr_tc_layer_torgb: null pointer");
+    R3DP_REQUIRE(N > 0 && (Nw == N || Nw == 1) && W % BM == 0 && O % BN == 0 && O <= 256 && H % 2 == 0, "sr_tc_layer_torgb: bad shape");
+    const int Ip = (I + 63) / 64 * 64;
+    Conv2Args a = {};
+    Taps t = {};
+    t.n = 9;
+    for (int i = 0; i < 9; ++i) { t.dy[i] = i / 3 - 1; t.dx[i] = i % 3 - 1; t.widx[i] = i; }
+    a.n_phases = 1;
+    fill_taps2(a.ph[0].taps, t);
+    a.ph[0].rows = H; a.ph[0].oy_off = 0; a.ph[0].ox_off = 0;
+    a.mode = kActRgb; a.out = reinterpret_cast<__half*>(y_f16); a.out_H = H; a.out_W = W; a.out_C = O; a.oy_mul = a.ox_mul = 1;
+    a.bias = bias; a.wrgb = wrgb; a.brgb = brgb; a.img_prev = img_prev; a.img_out = img_out; a.img_H = H; a.img_W = W;
+    return run_conv2(x_f16, N, H, W, Ip, wp_f16, Nw, O, a, H, as_stream(stream));
+}
+
+// bilinear up-resize of a CHANNELS-LAST fp32 image [N,h,w,C] (e.g. the renderer's [N,M,32] output viewed as an image) to
+// NHWC fp16 [N,size,size,Cpad]: one thread = one output pixel x 8 channels.
+__global__ void resize_nhwc_to_f16_kernel(const float* __restrict__ x, int N, int C, int h, int w, int size, int Cp, __half* __restrict__ y) {
+    const int cv = Cp / 8;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)N * size * size * cv) return;
+    const int c8 = (int)(idx % cv); const int ox = (int)((idx / cv) % size); const int oy = (int)((idx / ((long long)cv * size)) % size);
+    const int n = (int)(idx / ((long long)cv * size * size));
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c8 * 8 < C) {
+        const float sy = fmaxf(((float)oy + 0.5f) * ((float)h / (float)size) - 0.5f, 0.f);
+        const float sx = fmaxf(((float)ox + 0.5f) * ((float)w / (float)size) - 0.5f, 0.f);
+        const int y0 = min((int)sy, h - 1), x0 = min((int)sx, w - 1), y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+        const float ty = sy - (float)y0, tx = sx - (float)x0;
+        const float* b = x + (size_t)n * h * w * C + c8 * 8;
+        const float4* p00 = reinterpret_cast<const float4*>(b + ((size_t)y0 * w + x0) * C);
+        const float4* p10 = reinterpret_cast<const float4*>(b + ((size_t)y1 * w + x0) * C);
+        const float4* p01 = reinterpret_cast<const float4*>(b + ((size_t)y0 * w + x1) * C);
+        const float4* p11 = reinterpret_cast<const float4*>(b + ((size_t)y1 * w + x1) * C);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float4 a00 = __ldg(p00 + q), a10 = __ldg(p10 + q), a01 = __ldg(p01 + q), a11 = __ldg(p11 + q);
+            const float e00[4] = {a00.x, a00.y, a00.z, a00.w}, e10[4] = {a10.x, a10.y, a10.z, a10.w};
+            const float e01[4] = {a01.x, a01.y, a01.z, a01.w}, e11[4] = {a11.x, a11.y, a11.z, a11.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float r0 = e00[j] * (1.f - ty) + e10[j] * ty, r1 = e01[j] * (1.f - ty) + e11[j] * ty;
+                v[q * 4 + j] = r0 * (1.f - tx) + r1 * tx;
+            }
+        }
+    }
+    uint4 pk; __half2* ph = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ph[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(y + idx * 8) = pk;
+}
+
+extern "C" int r3dp_sr_tc_input_nhwc(const float* x_nhwc, int N, int C, int h, int w, int size, void* y_f16, r3dp_stream_t stream) {
+    R3DP_REQUIRE(x_nhwc && y_f16, "sr_tc_input_nhwc: null pointer");
+    R3DP_REQUIRE(N > 0 && C > 0 && C % 8 == 0 && h > 0 && w > 0 && size >= h && size >= w, "sr_tc_input_nhwc: bad shape (C %% 8 == 0, up-scaling only)");
+    const int Cp = (C + 63) / 64 * 64;
+    const long long total = (long long)N * size * size * (Cp / 8);
+    resize_nhwc_to_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x_nhwc, N, C, h, w, size, Cp, reinterpret_cast<__half*>(y_f16));
     R3DP_LAUNCH_CHECK();
     count_launches(1);
     return 0;

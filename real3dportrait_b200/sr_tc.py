@@ -62,8 +62,9 @@ class Prepared:
 
 
 def forward(sr, rgb: torch.Tensor, x: torch.Tensor, ws3: torch.Tensor, shared_styles: Optional[bool] = None,
-            x_is_nhwc: bool = False) -> torch.Tensor:
+            x_nhwc: Optional[torch.Tensor] = None) -> torch.Tensor:
     """rgb [N,3,h,w], x [N,C,h,w] (fp32 NCHW, h <= 128), ws3 [N,3,512] -> [N,3,512,512] fp32.
+    x_nhwc: the same features channels-last [N,h,w,C] (the renderer's native output) - skips a layout round trip.
     If `sr.static_prepared` is set (caller guarantees constant styles, e.g. Real3D's ws == 1) the weight preparation
     (styles -> fold -> demod -> fp16 pack) is skipped."""
     from .superresolution import SuperresolutionHybrid8XDC
@@ -75,18 +76,25 @@ def forward(sr, rgb: torch.Tensor, x: torch.Tensor, ws3: torch.Tensor, shared_st
             if shared_styles is None:
                 shared_styles = N == 1 or getattr(sr, 'assume_shared_styles', False)
             prep = Prepared(sr, ws3[:1] if shared_styles else ws3)
-        x0 = to_nhwc_f16(x, sr.input_resolution)
+        if x_nhwc is not None:
+            xn = capi.f32(x_nhwc)
+            _, h, w, Cc = xn.shape
+            x0 = torch.empty(N, sr.input_resolution, sr.input_resolution, (Cc + 63) // 64 * 64, device=xn.device, dtype=torch.float16)
+            capi.check(L.r3dp_sr_tc_input_nhwc(capi.ptr(xn), N, Cc, h, w, sr.input_resolution, capi.ptr(x0, torch.float16), capi.stream()))
+        else:
+            x0 = to_nhwc_f16(x, sr.input_resolution)
         rgb0 = SuperresolutionHybrid8XDC._resize(rgb, sr.input_resolution) if rgb.shape[-1] != sr.input_resolution else capi.f32(rgb)
     b0, b1, Nw, wp = sr.block0, sr.block1, prep.Nw, prep.wp
     a0 = layer(x0, b0.conv0, wp[0], 2)
-    a1 = layer(a0, b0.conv1, wp[1], 1)
+    a1 = torch.empty(N, 256, 256, 256, device=x.device, dtype=torch.float16)
     img1 = torch.empty(N, 3, 256, 256, device=x.device)
-    with capi.region('sr_torgb'):
-        capi.check(L.r3dp_sr_tc_torgb(capi.ptr(a1, torch.float16), capi.ptr(prep.wrgb0), capi.ptr(capi.f32(b0.torgb.bias)), capi.ptr(rgb0), N, Nw,
-                                      256, 256, 256, capi.ptr(img1), capi.stream()))
+    with capi.region('sr_conv'):                               # block0.conv1 + block0.torgb (+ upsampled skip) in one kernel
+        capi.check(L.r3dp_sr_tc_layer_torgb(capi.ptr(a0, torch.float16), capi.ptr(wp[1], torch.float16), capi.ptr(capi.f32(b0.conv1.bias)),
+                                            capi.ptr(prep.wrgb0), capi.ptr(capi.f32(b0.torgb.bias)), capi.ptr(rgb0), N, Nw, 256, 256, 256, 256,
+                                            capi.ptr(a1, torch.float16), capi.ptr(img1), capi.stream()))
     a2 = layer(a1, b1.conv0, wp[2], 2)
     out = torch.empty(N, 3, 512, 512, device=x.device)
-    with capi.region('sr_conv'):
+    with capi.region('sr_conv'):                               # block1.conv1 + block1.torgb: the 128-channel activation is never written
         capi.check(L.r3dp_sr_tc_last_layer(capi.ptr(a2, torch.float16), capi.ptr(wp[3], torch.float16), capi.ptr(capi.f32(b1.conv1.bias)),
                                            capi.ptr(prep.wrgb1), capi.ptr(capi.f32(b1.torgb.bias)), capi.ptr(img1), N, Nw, 128, 512, 512,
                                            capi.ptr(out), capi.stream()))

@@ -166,13 +166,14 @@ class SuperresolutionHybrid8XDC(torch.nn.Module):
 
     def forward(self, rgb, x, ws, **block_kwargs):
         """rgb [N,3,h,w], x [N,channels,h,w], ws [N,>=1,512] -> [N,3,512,512]   (superresolution.py:348-359)."""
+        x_nhwc = block_kwargs.pop('x_nhwc', None)          # optional: the same features channels-last (tensor-core path only)
         block_kwargs = {k: v for k, v in block_kwargs.items() if k != 'sr_mode'}
         ws = ws[:, -1:, :].repeat(1, 3, 1)
         if x.shape[-1] > self.input_resolution:
             raise NotImplementedError('down-scaling inputs (antialiased) is not on the Real3D path')
         if self.sr_mode == 'tc':
             from . import sr_tc
-            return sr_tc.forward(self, rgb, x, ws)
+            return sr_tc.forward(self, rgb, x, ws, x_nhwc=x_nhwc)
         if x.shape[-1] != self.input_resolution:
             x = self._resize(x, self.input_resolution)
             rgb = self._resize(rgb, self.input_resolution)

@@ -64,7 +64,8 @@ class RenderHead(torch.nn.Module):
         rgb_image = feature_image[:, :3]
         ret['weights_img'] = weights_image
         ones_ws = torch.ones(N, 14, self.hparams['w_dim'], device=feature_image.device)
-        sr_image = self.superresolution(rgb_image, feature_image, ones_ws, noise_mode='none')
+        extra = {'x_nhwc': feat.view(N, res, res, feat.shape[-1])} if self.superresolution.sr_mode == 'tc' else {}
+        sr_image = self.superresolution(rgb_image, feature_image, ones_ws, noise_mode='none', **extra)
         ret.update({'image_raw': rgb_image.clamp(-1, 1), 'image_depth': depth_image, 'image': sr_image.clamp(-1, 1),
                     'image_feature': feature_image[:, 3:], 'plane': planes, 'is_ray_valid': valid})
         return ret

@@ -569,6 +569,265 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc2_kernel(const __grid_cons
     }
 }
 
+// =====================================================================================================================
+// conv_tc3_kernel<R>: the v2 kernel on CTA PAIRS (thread-block cluster of 2 = one TPC, tcgen05 cta_group::2).
+// ncu on v1/v2: with 128x128 single-CTA tiles every MMA pulls 4 KB (A) + 4 KB (B) from shared memory per 64 clk = 128 B/clk, the
+// whole smem port, which TMA also needs for the fills -> tensor pipe stuck at ~58 %.  A pair computes M = 256 pixels (each CTA's
+// own 128-pixel strips) x N = 128 couts per instruction and each CTA keeps only HALF of the weight tile (64 couts): 6 KB per 64 clk
+// per SM.  Protocol: both CTAs run the same producer/epilogue loops on neighbouring units; all "full" barriers live in the leader
+// (rank 0) and receive the TMA bytes of both CTAs (cp.async.bulk.tensor.cta_group::2, peer bit cleared in the barrier address);
+// the leader's MMA lane issues tcgen05.mma.cta_group::2 and releases ring slots / publishes accumulators in BOTH CTAs with
+// multicast tcgen05.commit; the epilogue warps of both CTAs arrive on the leader's accumulator-empty barrier.
+// =====================================================================================================================
+constexpr int B3_BYTES = (BN / 2) * BK * 2;                                  // 64 couts x 64 ch fp16 = 8 KB per CTA
+constexpr uint32_t kIdesc3 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);    // M = 256 across the pair
+template <int R> struct Cfg3 {
+    static constexpr int NA = 8, NB = 8;
+    static constexpr int NACC = (R * BN * 2 <= 512) ? 2 : 1;
+    static constexpr int TMEM_COLS = (R * BN * NACC <= 128) ? 128 : (R * BN * NACC <= 256 ? 256 : 512);
+    static constexpr int SMEM = NA * A2_SLOT + NB * B3_BYTES + 1024 + 5120;
+};
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int R>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB, const Conv2Args a) {
+    using C = Cfg3<R>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + C::NA * A2_SLOT;
+    uint8_t* tail = b_ring + C::NB * B3_BYTES;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* a_empty = a_full + C::NA;
+    uint64_t* b_full = a_empty + C::NA;
+    uint64_t* b_empty = b_full + C::NB;
+    uint64_t* acc_full = b_empty + C::NB;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* s_bias = reinterpret_cast<float*>(tail + 512);                    // [256]
+    float* s_wrgb = s_bias + 256;                                            // [3][n_blocks*128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t cta_rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    const bool leader = cta_rank == 0;
+    const int units_per_image = a.n_phases * a.row_groups * a.tiles_x;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < C::NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {
+        const int t = threadIdx.x - 64;
+        for (int e = t; e < a.n_blocks * BN && e < 256; e += 128) s_bias[e] = a.bias ? a.bias[e] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // unit index -> (image n, phase, row group, x block); x fastest so neighbouring CTAs share strips in L2
+    auto decode = [&](int unit, int& n, int& ph, int& row0, int& col0) {
+        n = unit / units_per_image; int r = unit - n * units_per_image;
+        const int xb = r % a.tiles_x; r /= a.tiles_x;
+        const int rg = r % a.row_groups; ph = r / a.row_groups;
+        row0 = rg * R; col0 = xb * BM;
+    };
+
+    if (warp == 0) {
+        // ===== TMA producer (one lane): strips and taps in consumption order =====
+        if (lane == 0) {
+            uint32_t aq = 0, bq = 0;                                         // running strip / tap sequence numbers
+            for (int unit = (blockIdx.x & ~1) + (int)cta_rank; unit < a.total_units; unit += gridDim.x) {
+                int n, ph, row0, col0; decode(unit, n, ph, row0, col0);
+                const Taps2& tp = a.ph[ph].taps;
+                const int DY = tp.ngroups;
+                const int wn = a.w_shared ? 0 : n;
+                for (int nblk = 0; nblk < a.n_blocks; ++nblk)
+                    for (int kc = 0; kc < a.k_chunks; ++kc)
+                        for (int d = 0; d < DY; ++d) {
+                            const int s_lo = d == 0 ? 0 : R - 1 + d, s_hi = R - 1 + d;
+                            for (int s = s_lo; s <= s_hi; ++s, ++aq) {
+                                const int slot = aq % C::NA;
+                                mbar_wait(&a_empty[slot], ((aq / C::NA) & 1) ^ 1);
+                                if (leader) mbar_expect_tx(&a_full[slot], 2 * A2_BYTES);
+                                tma_load_4d_2sm(a_ring + slot * A2_SLOT, &tmA, &a_full[slot], kc * BK, col0 - 1, row0 + tp.dy_min + s, n);
+                            }
+                            for (int t = tp.gstart[d]; t < tp.gstart[d + 1]; ++t, ++bq) {
+                                const int slot = bq % C::NB;
+                                mbar_wait(&b_empty[slot], ((bq / C::NB) & 1) ^ 1);
+                                if (leader) mbar_expect_tx(&b_full[slot], 2 * B3_BYTES);
+                                tma_load_4d_2sm(b_ring + slot * B3_BYTES, &tmB, &b_full[slot], kc * BK, nblk * BN + (int)cta_rank * (BN / 2), tp.widx[t], wn);
+                            }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the leader CTA issues for the pair (M = 256: rows 0-127 from CTA0's strips, 128-255 from CTA1's) =====
+        if (leader) {
+        uint32_t aq = 0, bq = 0, it = 0;
+        for (int unit = (blockIdx.x & ~1) + (int)cta_rank; unit < a.total_units; unit += gridDim.x) {
+            int n, ph, row0, col0; decode(unit, n, ph, row0, col0);
+            const Taps2& tp = a.ph[ph].taps;
+            const int DY = tp.ngroups, NS = R + DY - 1;
+            for (int nblk = 0; nblk < a.n_blocks; ++nblk, ++it) {
+                const int buf = it % C::NACC;
+                mbar_wait(&acc_empty[buf], (((it / C::NACC) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t acc0 = tmem_base + buf * (R * BN);
+                for (int kc = 0; kc < a.k_chunks; ++kc) {
+                    const uint32_t a_base = aq;                               // sequence number of strip 0 of this chunk
+                    for (int d = 0; d < DY; ++d) {
+                        const int s_lo = d == 0 ? 0 : R - 1 + d, s_hi = R - 1 + d;
+                        for (int s = s_lo; s <= s_hi; ++s, ++aq) mbar_wait(&a_full[aq % C::NA], (aq / C::NA) & 1);
+                        for (int t = tp.gstart[d]; t < tp.gstart[d + 1]; ++t, ++bq) {
+                            const int bslot = bq % C::NB;
+                            mbar_wait(&b_full[bslot], (bq / C::NB) & 1);
+                            tc_fence_after();
+                            if (lane == 0) {
+                                const uint64_t db = umma_desc_sw128(smem_u32(b_ring + bslot * B3_BYTES));
+                                const int sh = tp.shift[t];
+#pragma unroll
+                                for (int j = 0; j < R; ++j) {
+                                    const uint32_t sq = a_base + j + d;
+                                    const uint64_t da = umma_desc_sw128(smem_u32(a_ring + (sq % C::NA) * A2_SLOT) + 128 * sh);
+#pragma unroll
+                                    for (int k = 0; k < BK / UMMA_K; ++k)
+                                        tc_mma_f16_2sm(acc0 + j * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc3, (kc | t | k) != 0);
+                                }
+                                tc_commit_2sm(&b_empty[bslot]);
+                            }
+                            __syncwarp();
+                        }
+                        // strips no later group needs: strip d after group d; everything left after the last group
+                        if (lane == 0) {
+                            if (d < DY - 1) tc_commit_2sm(&a_empty[(a_base + d) % C::NA]);
+                            else for (int s = DY - 1; s < NS; ++s) tc_commit_2sm(&a_empty[(a_base + s) % C::NA]);
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (lane == 0) tc_commit_2sm(&acc_full[buf]);
+                __syncwarp();
+            }
+        }
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lanes [32*(warp%4), +32) =====
+        const int q = warp & 3, m = q * 32 + lane;
+        const bool want_rgb = (a.mode == kToRgbFinal) || (a.mode == kActRgb);
+        const int CW = a.n_blocks * BN;                                      // channels ToRGB sums over
+        uint32_t it = 0;
+        int n_loaded = -1;
+        for (int unit = (blockIdx.x & ~1) + (int)cta_rank; unit < a.total_units; unit += gridDim.x) {
+            int n, ph, row0, col0; decode(unit, n, ph, row0, col0);
+            const Phase2& P = a.ph[ph];
+            const int wn = a.w_shared ? 0 : n;
+            if (want_rgb && wn != n_loaded) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");               // all four epilogue warps are done with the old weights
+                for (int e = threadIdx.x - 64; e < 3 * CW; e += 128) s_wrgb[e] = a.wrgb[(size_t)wn * 3 * CW + e];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                n_loaded = wn;
+            }
+            const int gcol = col0 + m, X = gcol * a.ox_mul + P.ox_off;
+            float rgb[R][3];
+#pragma unroll
+            for (int j = 0; j < R; ++j) { rgb[j][0] = 0.f; rgb[j][1] = 0.f; rgb[j][2] = 0.f; }
+            for (int nblk = 0; nblk < a.n_blocks; ++nblk, ++it) {
+                const int buf = it % C::NACC;
+                mbar_wait(&acc_full[buf], (it / C::NACC) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int row = row0 + j;
+                    const int Y = row * a.oy_mul + P.oy_off;
+                    const bool in_img = (row < P.rows) && (Y < a.out_H) && (X < a.out_W);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (R * BN) + j * BN;
+                    __half* dst = a.out + (((size_t)n * a.out_H + Y) * a.out_W + X) * a.out_C + nblk * BN;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        uint32_t r[32];
+                        tc_ld32(taddr + c0, r);
+                        float f[32];
+                        if (a.mode == kStoreRaw) {
+#pragma unroll
+                            for (int jj = 0; jj < 32; ++jj) f[jj] = __uint_as_float(r[jj]);
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 32; ++jj) {
+                                const float v = __uint_as_float(r[jj]) + s_bias[nblk * BN + c0 + jj];
+                                f[jj] = (v < 0.f ? v * 0.2f : v) * 1.4142135623730951f;      // bias_act lrelu, gain sqrt(2)
+                            }
+                        }
+                        if (a.mode != kToRgbFinal && in_img) store_half32(dst + c0, f);
+                        if (want_rgb) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const float4* w4 = reinterpret_cast<const float4*>(s_wrgb + c * CW + nblk * BN + c0);
+                                float acc = rgb[j][c];
+#pragma unroll
+                                for (int j4 = 0; j4 < 8; ++j4) {
+                                    const float4 w = w4[j4];
+                                    acc = fmaf(f[4 * j4 + 0], w.x, acc); acc = fmaf(f[4 * j4 + 1], w.y, acc);
+                                    acc = fmaf(f[4 * j4 + 2], w.z, acc); acc = fmaf(f[4 * j4 + 3], w.w, acc);
+                                }
+                                rgb[j][c] = acc;
+                            }
+                        }
+                    }
+                    if (want_rgb && nblk == a.n_blocks - 1 && in_img) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float skip = a.img_prev ? upsampled_skip(a.img_prev + ((size_t)n * 3 + c) * (a.img_H / 2) * (a.img_W / 2),
+                                                                           a.img_H / 2, a.img_W / 2, Y, X) : 0.f;
+                            a.img_out[(((size_t)n * 3 + c) * a.img_H + Y) * a.img_W + X] = rgb[j][c] + a.brgb[c] + skip;
+                        }
+                    }
+                }
+                // this warp is done reading the accumulator buffer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf]) & 0xFEFFFFFFu) : "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                     // the peer's smem/TMEM must stay alive until every MMA that reads it has retired
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    }
+}
+
 // ---- helpers around the GEMMs ---------------------------------------------------------------------------------------
 // wf fp32 [Nw][O][I][3][3] -> packed fp16 [Nw][9][O][Ip]  (zero for i >= I)
 __global__ void pack_weights_kernel(const float* __restrict__ wf, int Nw, int O, int I, int Ip, __half* __restrict__ out) {
@@ -853,7 +1112,7 @@ static int launch_conv2(const void* x, int N, int H, int W, int Cp, const void* 
 static int launch_upconv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, __half* yb, const float* bias, cudaStream_t st);
 static int tc_version();
 static int launch_conv(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, ConvArgs a, cudaStream_t st) {
-    if (tc_version() == 2) return launch_conv2(x, N, H, W, Cp, wp, Nw, O, a, st);
+    if (tc_version() >= 2) return launch_conv2(x, N, H, W, Cp, wp, Nw, O, a, st);
     CUtensorMap tmA, tmB;
     if (make_map_4d(&tmA, x, (uint64_t)Cp, (uint64_t)W, (uint64_t)H, (uint64_t)N, BM)) return 1;
     if (make_map_4d(&tmB, wp, (uint64_t)Cp, (uint64_t)O, 9, (uint64_t)Nw, BN)) return 1;
@@ -872,15 +1131,40 @@ static int launch_conv(const void* x, int N, int H, int W, int Cp, const void* w
 }
 
 
-static int tc_version() {                      // R3DP_TC_KERNEL=1 selects the simple v1 kernel (debug / A-B comparison)
+static int tc_version() {                      // R3DP_TC_KERNEL=1: simple v1 kernel; 2: single-CTA persistent v2; 3 (default): CTA pairs
     static int v = -1;
-    if (v < 0) { const char* e = getenv("R3DP_TC_KERNEL"); v = (e && e[0] == '1') ? 1 : 2; }
+    if (v < 0) { const char* e = getenv("R3DP_TC_KERNEL"); v = (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 3); }
     return v;
 }
+static bool tc_pairs() { return tc_version() == 3; }
 static int tc_rows() {                         // R3DP_TC_ROWS = 1 | 2 | 4 output rows per tile (default 2: double-buffered accumulators)
     static int v = -1;
     if (v < 0) { const char* e = getenv("R3DP_TC_ROWS"); v = e ? atoi(e) : 2; if (v != 1 && v != 2 && v != 4) v = 2; }
     return v;
+}
+
+template <int R>
+static int launch_conv3_r(const CUtensorMap& tmA, const CUtensorMap& tmB, Conv2Args a, int max_rows, cudaStream_t st) {
+    using C = Cfg3<R>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        R3DP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    a.row_groups = (max_rows + R - 1) / R;
+    if ((a.row_groups * a.tiles_x) & 1) a.row_groups += 1;       // the two CTAs of a pair must work on units of the same (image, phase)
+    a.total_units = a.n_images * a.n_phases * a.row_groups * a.tiles_x;
+    int grid = a.total_units < sm_count() ? a.total_units : sm_count();
+    grid &= ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    R3DP_CUDA(cudaLaunchKernelEx(&cfg, conv_tc3_kernel<R>, tmA, tmB, a));
+    count_launches(1);
+    return 0;
 }
 
 template <int R>
@@ -924,9 +1208,10 @@ static void fill_taps2(Taps2& t2, const Taps& t) {
 static int run_conv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, Conv2Args& a, int max_rows, cudaStream_t st) {
     CUtensorMap tmA, tmB;
     if (make_map_4d_box(&tmA, x, (uint64_t)Cp, (uint64_t)W, (uint64_t)H, (uint64_t)N, A2_ROWS)) return 1;
-    if (make_map_4d_box(&tmB, wp, (uint64_t)Cp, (uint64_t)O, 9, (uint64_t)Nw, BN)) return 1;
+    if (make_map_4d_box(&tmB, wp, (uint64_t)Cp, (uint64_t)O, 9, (uint64_t)Nw, tc_pairs() ? BN / 2 : BN)) return 1;
     a.k_chunks = Cp / BK; a.tiles_x = W / BM; a.n_blocks = O / BN; a.n_images = N; a.w_shared = (Nw == 1);
     R3DP_REQUIRE(a.n_blocks >= 1 && a.n_blocks <= 2, "conv_tc2: 128 or 256 output channels");
+    if (tc_pairs()) return tc_rows() == 1 ? launch_conv3_r<1>(tmA, tmB, a, max_rows, st) : launch_conv3_r<2>(tmA, tmB, a, max_rows, st);
     switch (tc_rows()) {
         case 1: return launch_conv2_r<1>(tmA, tmB, a, max_rows, st);
         case 4: return launch_conv2_r<4>(tmA, tmB, a, max_rows, st);
@@ -1013,7 +1298,7 @@ extern "C" int r3dp_sr_tc_layer(const void* x_f16, const void* wp_f16, const flo
     }
     R3DP_REQUIRE(scratch, "sr_tc_layer: up=2 needs scratch");
     __half* yb = reinterpret_cast<__half*>(scratch);
-    if (tc_version() == 2) {
+    if (tc_version() >= 2) {
         if (launch_upconv2(x_f16, N, H, W, Ip, wp_f16, Nw, O, yb, bias, st)) return 1;
     } else {
         a.mode = kStoreRaw; a.out = yb; a.out_H = 2 * H + 1; a.out_W = 2 * W + 1; a.out_C = O; a.oy_mul = a.ox_mul = 2;

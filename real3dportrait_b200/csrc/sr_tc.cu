@@ -50,6 +50,13 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// one lane of the (fully active) warp; everything feeding a tcgen05 instruction is computed warp-uniformly OUTSIDE the elected branch so
+// the operands live in uniform registers (an `if (lane == 0)` region makes ptxas wrap every UTCHMMA in an ELECT/R2UR waterfall loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -455,30 +462,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc2_kernel(const __grid_cons
                             const int bslot = bq % C::NB;
                             mbar_wait(&b_full[bslot], (bq / C::NB) & 1);
                             tc_fence_after();
-                            if (lane == 0) {
+                            {
                                 const uint64_t db = umma_desc_sw128(smem_u32(b_ring + bslot * B_BYTES));
                                 const int sh = tp.shift[t];
+                                const uint32_t first = (uint32_t)(kc | t);
 #pragma unroll
                                 for (int j = 0; j < R; ++j) {
                                     const uint32_t sq = a_base + j + d;
                                     const uint64_t da = umma_desc_sw128(smem_u32(a_ring + (sq % C::NA) * A2_SLOT) + 128 * sh);
+                                    if (elect_one()) {
 #pragma unroll
-                                    for (int k = 0; k < BK / UMMA_K; ++k)
-                                        tc_mma_f16(acc0 + j * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kc | t | k) != 0);
+                                        for (int k = 0; k < BK / UMMA_K; ++k)
+                                            tc_mma_f16(acc0 + j * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, first | (uint32_t)k);
+                                    }
                                 }
-                                tc_commit(&b_empty[bslot]);
+                                if (elect_one()) tc_commit(&b_empty[bslot]);
                             }
                             __syncwarp();
                         }
                         // strips no later group needs: strip d after group d; everything left after the last group
-                        if (lane == 0) {
-                            if (d < DY - 1) tc_commit(&a_empty[(a_base + d) % C::NA]);
-                            else for (int s = DY - 1; s < NS; ++s) tc_commit(&a_empty[(a_base + s) % C::NA]);
+                        if (d < DY - 1) {
+                            if (elect_one()) tc_commit(&a_empty[(a_base + d) % C::NA]);
+                        } else {
+                            for (int s = DY - 1; s < NS; ++s) { if (elect_one()) tc_commit(&a_empty[(a_base + s) % C::NA]); }
                         }
                         __syncwarp();
                     }
                 }
-                if (lane == 0) tc_commit(&acc_full[buf]);
+                if (elect_one()) tc_commit(&acc_full[buf]);
                 __syncwarp();
             }
         }
@@ -579,13 +590,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc2_kernel(const __grid_cons
 // the leader's MMA lane issues tcgen05.mma.cta_group::2 and releases ring slots / publishes accumulators in BOTH CTAs with
 // multicast tcgen05.commit; the epilogue warps of both CTAs arrive on the leader's accumulator-empty barrier.
 // =====================================================================================================================
+constexpr int kThreads3 = 64 + 256;                                          // TMA warp, MMA warp, 8 epilogue warps
 constexpr int B3_BYTES = (BN / 2) * BK * 2;                                  // 64 couts x 64 ch fp16 = 8 KB per CTA
 constexpr uint32_t kIdesc3 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);    // M = 256 across the pair
 template <int R> struct Cfg3 {
     static constexpr int NA = 8, NB = 8;
     static constexpr int NACC = (R * BN * 2 <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (R * BN * NACC <= 128) ? 128 : (R * BN * NACC <= 256 ? 256 : 512);
-    static constexpr int SMEM = NA * A2_SLOT + NB * B3_BYTES + 1024 + 5120;
+    static constexpr int SMEM = NA * A2_SLOT + NB * B3_BYTES + 1024 + 8192;
 };
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -608,7 +620,7 @@ __device__ __forceinline__ void tc_mma_f16_2sm(uint32_t tmem_d, uint64_t desc_a,
 }
 
 template <int R>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB, const Conv2Args a) {
     using C = Cfg3<R>;
     extern __shared__ uint8_t smem_raw[];
@@ -625,6 +637,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc3_kernel(const __grid_cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* s_bias = reinterpret_cast<float*>(tail + 512);                    // [256]
     float* s_wrgb = s_bias + 256;                                            // [3][n_blocks*128]
+    float* s_part = s_wrgb + 768;                                            // [R][128][3] ToRGB partial sums of the second column group
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t cta_rank;
@@ -635,7 +648,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc3_kernel(const __grid_cons
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < C::NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -646,7 +659,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc3_kernel(const __grid_cons
     }
     if (warp >= 2) {
         const int t = threadIdx.x - 64;
-        for (int e = t; e < a.n_blocks * BN && e < 256; e += 128) s_bias[e] = a.bias ? a.bias[e] : 0.f;
+        for (int e = t; e < a.n_blocks * BN && e < 256; e += 256) s_bias[e] = a.bias ? a.bias[e] : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -712,37 +725,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc3_kernel(const __grid_cons
                             const int bslot = bq % C::NB;
                             mbar_wait(&b_full[bslot], (bq / C::NB) & 1);
                             tc_fence_after();
-                            if (lane == 0) {
+                            {
                                 const uint64_t db = umma_desc_sw128(smem_u32(b_ring + bslot * B3_BYTES));
                                 const int sh = tp.shift[t];
+                                const uint32_t first = (uint32_t)(kc | t);
 #pragma unroll
                                 for (int j = 0; j < R; ++j) {
                                     const uint32_t sq = a_base + j + d;
                                     const uint64_t da = umma_desc_sw128(smem_u32(a_ring + (sq % C::NA) * A2_SLOT) + 128 * sh);
+                                    if (elect_one()) {
 #pragma unroll
-                                    for (int k = 0; k < BK / UMMA_K; ++k)
-                                        tc_mma_f16_2sm(acc0 + j * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc3, (kc | t | k) != 0);
+                                        for (int k = 0; k < BK / UMMA_K; ++k)
+                                            tc_mma_f16_2sm(acc0 + j * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc3, first | (uint32_t)k);
+                                    }
                                 }
-                                tc_commit_2sm(&b_empty[bslot]);
+                                if (elect_one()) tc_commit_2sm(&b_empty[bslot]);
                             }
                             __syncwarp();
                         }
                         // strips no later group needs: strip d after group d; everything left after the last group
-                        if (lane == 0) {
-                            if (d < DY - 1) tc_commit_2sm(&a_empty[(a_base + d) % C::NA]);
-                            else for (int s = DY - 1; s < NS; ++s) tc_commit_2sm(&a_empty[(a_base + s) % C::NA]);
+                        if (d < DY - 1) {
+                            if (elect_one()) tc_commit_2sm(&a_empty[(a_base + d) % C::NA]);
+                        } else {
+                            for (int s = DY - 1; s < NS; ++s) { if (elect_one()) tc_commit_2sm(&a_empty[(a_base + s) % C::NA]); }
                         }
                         __syncwarp();
                     }
                 }
-                if (lane == 0) tc_commit_2sm(&acc_full[buf]);
+                if (elect_one()) tc_commit_2sm(&acc_full[buf]);
                 __syncwarp();
             }
         }
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lanes [32*(warp%4), +32) =====
+        // ===== epilogue: warps 2..9; warp w reads TMEM lanes [32*(w%4), +32); warps 2-5 take columns 0-63 of each accumulator, 6-9 columns 64-127 =====
         const int q = warp & 3, m = q * 32 + lane;
+        const int cg = (warp - 2) >> 2;                                       // column group
         const bool want_rgb = (a.mode == kToRgbFinal) || (a.mode == kActRgb);
         const int CW = a.n_blocks * BN;                                      // channels ToRGB sums over
         uint32_t it = 0;
@@ -752,9 +770,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc3_kernel(const __grid_cons
             const Phase2& P = a.ph[ph];
             const int wn = a.w_shared ? 0 : n;
             if (want_rgb && wn != n_loaded) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");               // all four epilogue warps are done with the old weights
-                for (int e = threadIdx.x - 64; e < 3 * CW; e += 128) s_wrgb[e] = a.wrgb[(size_t)wn * 3 * CW + e];
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");               // all eight epilogue warps are done with the old weights
+                for (int e = threadIdx.x - 64; e < 3 * CW; e += 256) s_wrgb[e] = a.wrgb[(size_t)wn * 3 * CW + e];
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 n_loaded = wn;
             }
             const int gcol = col0 + m, X = gcol * a.ox_mul + P.ox_off;
@@ -773,7 +791,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc3_kernel(const __grid_cons
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (R * BN) + j * BN;
                     __half* dst = a.out + (((size_t)n * a.out_H + Y) * a.out_W + X) * a.out_C + nblk * BN;
 #pragma unroll 1
-                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                    for (int c0 = cg * (BN / 2); c0 < (cg + 1) * (BN / 2); c0 += 32) {
                         uint32_t r[32];
                         tc_ld32(taddr + c0, r);
                         float f[32];
@@ -803,7 +821,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc3_kernel(const __grid_cons
                             }
                         }
                     }
-                    if (want_rgb && nblk == a.n_blocks - 1 && in_img) {
+                    if (want_rgb && nblk == a.n_blocks - 1) {
+                        // the two column groups hold partial ToRGB sums of the same pixel: group 1 hands its sums to group 0 through smem
+                        if (cg == 1) { s_part[(j * BM + m) * 3 + 0] = rgb[j][0]; s_part[(j * BM + m) * 3 + 1] = rgb[j][1]; s_part[(j * BM + m) * 3 + 2] = rgb[j][2]; }
+                        asm volatile("bar.sync 2, 256;" ::: "memory");
+                        if (cg == 0) { rgb[j][0] += s_part[(j * BM + m) * 3 + 0]; rgb[j][1] += s_part[(j * BM + m) * 3 + 1]; rgb[j][2] += s_part[(j * BM + m) * 3 + 2]; }
+                        asm volatile("bar.sync 3, 256;" ::: "memory");
+                    }
+                    if (want_rgb && nblk == a.n_blocks - 1 && in_img && cg == 0) {
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
                             const float skip = a.img_prev ? upsampled_skip(a.img_prev + ((size_t)n * 3 + c) * (a.img_H / 2) * (a.img_W / 2),
@@ -1157,7 +1182,7 @@ static int launch_conv3_r(const CUtensorMap& tmA, const CUtensorMap& tmB, Conv2A
     int grid = a.total_units < sm_count() ? a.total_units : sm_count();
     grid &= ~1;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads3); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;

@@ -173,23 +173,49 @@ __global__ void __launch_bounds__(kRenderThreads, CONST ? 4 : 2) render_kernel(c
     // One "pass" = gather + decode for samples k in [k0, k0+kn) of every ray.
     auto run_pass = [&](int k0, int kn) {
         const int nsamp = R * kn;
-        // gather: each warp takes 4 samples per iteration, 8 lanes x float4 per sample
+        // (1) one thread per sample: position -> three tap descriptors (texel offset + 4 bilinear weights with the zero padding
+        //     folded in) written into the sample's own row; done ONCE per sample instead of once per lane of the gather group
+        for (int q = tid; q < nsamp; q += kRenderThreads) {
+            const int r = q / kn, k = k0 + (q - r * kn);
+            const float* rf = rayf + r * 8;
+            const float d = dep[r * ST + k];
+            const float x = __fadd_rn(rf[0], __fmul_rn(d, rf[3]));
+            const float y = __fadd_rn(rf[1], __fmul_rn(d, rf[4]));
+            const float z = __fadd_rn(rf[2], __fmul_rn(d, rf[5]));
+            const float gx = pv.scale * x, gy = pv.scale * y, gz = pv.scale * z;
+            float* row = rows + (size_t)(r * ST + k) * kRow;
+            tap_desc(gx, gy, pv.H, pv.W, 0, row);                      // plane 0 <- (x, y)   (renderer.py:30-63)
+            tap_desc(gx, gz, pv.H, pv.W, 1, row + 5);                  // plane 1 <- (x, z)
+            tap_desc(gz, gx, pv.H, pv.W, 2, row + 10);                 // plane 2 <- (z, x)
+        }
+        __syncthreads();
+        // (2) gather: each warp takes 4 samples per iteration, 8 lanes x float4 per sample; the row's descriptor is read by all 8
+        //     lanes and then overwritten by the 32 mean features
         const int sub = lane >> 3, cq = lane & 7;
         for (int q4 = warp * 4; q4 < nsamp; q4 += kWarps * 4) {
             const int q = q4 + sub;
             if (q < nsamp) {
                 const int r = q / kn, k = k0 + (q - r * kn);
-                const float* rf = rayf + r * 8;
-                const float d = dep[r * ST + k];
-                const float x = __fadd_rn(rf[0], __fmul_rn(d, rf[3]));
-                const float y = __fadd_rn(rf[1], __fmul_rn(d, rf[4]));
-                const float z = __fadd_rn(rf[2], __fmul_rn(d, rf[5]));
-                float4 f0, f1, f2;
-                gather3(pv, x, y, z, cq, f0, f1, f2);
-                float* row = rows + (size_t)(r * ST + k) * kRow + cq * 4;
+                float* row = rows + (size_t)(r * ST + k) * kRow;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                float dsc[15];
+#pragma unroll
+                for (int e = 0; e < 15; ++e) dsc[e] = row[e];
+                const int rowstep = pv.W * kC;
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const float* b = pv.base + __float_as_int(dsc[5 * p]) + cq * 4;
+                    const float4 t00 = ldg_nc_f4(b), t10 = ldg_nc_f4(b + kC), t01 = ldg_nc_f4(b + rowstep), t11 = ldg_nc_f4(b + rowstep + kC);
+                    const float w00 = dsc[5 * p + 1], w10 = dsc[5 * p + 2], w01 = dsc[5 * p + 3], w11 = dsc[5 * p + 4];
+                    acc.x += t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
+                    acc.y += t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
+                    acc.z += t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
+                    acc.w += t00.w * w00 + t10.w * w10 + t01.w * w01 + t11.w * w11;
+                }
+                __syncwarp(__activemask());
                 const float third = 1.0f / 3.0f;
-                row[0] = (f0.x + f1.x + f2.x) * third; row[1] = (f0.y + f1.y + f2.y) * third;
-                row[2] = (f0.z + f1.z + f2.z) * third; row[3] = (f0.w + f1.w + f2.w) * third;
+                row[cq * 4 + 0] = acc.x * third; row[cq * 4 + 1] = acc.y * third;
+                row[cq * 4 + 2] = acc.z * third; row[cq * 4 + 3] = acc.w * third;
             }
         }
         __syncthreads();
@@ -213,46 +239,70 @@ __global__ void __launch_bounds__(kRenderThreads, CONST ? 4 : 2) render_kernel(c
         __syncthreads();
     };
 
-    // Ray march over `cnt` samples of ray r taken in the order idx[0..cnt) (ray_marcher.py:26-57); lane = colour channel.
-    auto march = [&](int r, int cnt, const int* idx, bool write_out, float* wout) {
+    // Ray march (ray_marcher.py:26-57) over `cnt` samples of ray r taken in the order idx[0..cnt), one warp per ray:
+    //   (1) lane l owns a contiguous chunk of intervals: alpha_k from the midpoint density, local transmittance products;
+    //   (2) exclusive warp scan of the chunk products -> T_k, w_k = alpha_k T_k; sums of w and w*mid-depth by warp reduction;
+    //   (3) lane = colour channel: rgb = sum_k v_k c_k with v_k = (w_{k-1} + w_k)/2  (== sum_k w_k (c_k + c_{k+1})/2).
+    // `wbuf` (>= cnt floats) receives w_k (k < cnt-1); `vbuf` is scratch for v_k.
+    auto march = [&](int r, int cnt, const int* idx, bool write_out, float* wbuf, float* vbuf) {
         const float* rr = rows + (size_t)r * ST * kRow;
         const float* dd = dep + r * ST;
-        float T = 1.0f, acc = 0.f, wsum = 0.f, dsum = 0.f;
-        int ia = idx ? idx[0] : 0;
-        float da = dd[ia], sa = rr[ia * kRow], ca = rr[ia * kRow + 1 + lane];
-        for (int i = 0; i + 1 < cnt; ++i) {
-            const int ib = idx ? idx[i + 1] : i + 1;
-            const float db = dd[ib], sb = rr[ib * kRow], cb = rr[ib * kRow + 1 + lane];
-            const float delta = db - da;
-            const float smid = softplus_fast((sa + sb) * 0.5f - 1.0f);          // ray_marcher.py:33
+        const int nint = cnt - 1;
+        const int chunk = (nint + 31) >> 5;                                   // intervals per lane (2 for 47, 3 for 95)
+        const int kb = lane * chunk, ke = min(kb + chunk, nint);
+        float prod = 1.0f;
+        for (int k = kb; k < ke; ++k) {
+            const int ia = idx ? idx[k] : k, ib = idx ? idx[k + 1] : k + 1;
+            const float delta = dd[ib] - dd[ia];
+            const float smid = softplus_fast((rr[ia * kRow] + rr[ib * kRow]) * 0.5f - 1.0f);     // ray_marcher.py:33
             const float alpha = 1.0f - __expf(-(smid * delta));
+            wbuf[k] = alpha;                                                  // alpha for now, weight below
+            prod *= (1.0f - alpha + 1e-10f);
+        }
+        float incl = prod;                                                    // inclusive scan of the chunk products
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl *= t; }
+        float T = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) T = 1.0f;
+        float wsum = 0.f, dsum = 0.f;
+        for (int k = kb; k < ke; ++k) {
+            const int ia = idx ? idx[k] : k, ib = idx ? idx[k + 1] : k + 1;
+            const float alpha = wbuf[k];
             const float w = alpha * T;
             T *= (1.0f - alpha + 1e-10f);
-            acc = fmaf(w, (ca + cb) * 0.5f, acc);
-            wsum += w; dsum = fmaf(w, (da + db) * 0.5f, dsum);
-            if (wout && lane == 0) wout[i] = w;
-            da = db; sa = sb; ca = cb;
+            wbuf[k] = w;
+            wsum += w; dsum = fmaf(w, (dd[ia] + dd[ib]) * 0.5f, dsum);
         }
-        if (write_out) {
-            const int m = ray_of<R>(a, tile, r);
-            if (m < a.M) {
-                const size_t o = (size_t)n * a.M + m;
-                if (a.white_back) acc = acc + 1.0f - wsum;
-                a.rgb[o * (kOut - 1) + lane] = acc * 2.0f - 1.0f;
-                if (lane == 0) { a.wsum[o] = wsum; a.depth[o] = dsum / wsum; }   // 0/0 -> NaN, fixed by depth_clamp_kernel
-            }
+        __syncwarp();
+        if (!write_out) return;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { wsum += __shfl_xor_sync(0xffffffffu, wsum, o); dsum += __shfl_xor_sync(0xffffffffu, dsum, o); }
+        for (int k = lane; k < cnt; k += 32) vbuf[k] = 0.5f * ((k > 0 ? wbuf[k - 1] : 0.f) + (k < nint ? wbuf[k] : 0.f));
+        __syncwarp();
+        float acc = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
+            const int ia = idx ? idx[k] : k;
+            acc = fmaf(vbuf[k], rr[ia * kRow + 1 + lane], acc);
+        }
+        const int m = ray_of<R>(a, tile, r);
+        if (m < a.M) {
+            const size_t o = (size_t)n * a.M + m;
+            if (a.white_back) acc = acc + 1.0f - wsum;
+            a.rgb[o * (kOut - 1) + lane] = acc * 2.0f - 1.0f;
+            if (lane == 0) { a.wsum[o] = wsum; a.depth[o] = dsum / wsum; }       // 0/0 -> NaN, fixed by depth_clamp_kernel
         }
     };
 
     run_pass(0, a.S);
 
     if (a.S_imp == 0) {
-        for (int r = warp; r < R; r += kWarps) march(r, a.S, nullptr, true, nullptr);
+        for (int r = warp; r < R; r += kWarps) march(r, a.S, nullptr, true, wts + r * ST, cdf + r * ST);
     } else {
         const int S = a.S, Ni = a.S_imp;
         for (int r = warp; r < R; r += kWarps) {
             float* w = wts + r * ST; float* cd = cdf + r * ST; float* dd = dep + r * ST;
-            march(r, S, nullptr, false, w);                                   // coarse weights w[0..S-2]
+            march(r, S, nullptr, false, w, cd);                               // coarse weights w[0..S-2]
             __syncwarp();
             // renderer.py:245-247: max_pool1d(2,1,pad 1) -> avg_pool1d(2,1) -> +0.01 ; a_i, i = 0..S-2
             // pdf over p_i = a_{i+1} + 1e-5, i = 0..S-4 ; cdf has S-2 entries (renderer.py:272-276)
@@ -302,7 +352,7 @@ __global__ void __launch_bounds__(kRenderThreads, CONST ? 4 : 2) render_kernel(c
                 od[rank] = i;
             }
             __syncwarp();
-            march(r, ST, od, true, nullptr);
+            march(r, ST, od, true, wts + r * ST, cdf + r * ST);
         }
     }
 
@@ -407,7 +457,7 @@ extern "C" int r3dp_render(const float* planes_cl, int N, int C, int H, int W, c
                            r3dp_stream_t stream) {
     if (check_mlp(mlp, C)) return 1;
     R3DP_REQUIRE(planes_cl && u_coarse && rgb && depth && weights_sum && is_ray_valid && workspace, "render: null pointer");
-    R3DP_REQUIRE(N > 0 && M > 0 && H > 0 && W > 0, "render: bad shape N=%d M=%d H=%d W=%d", N, M, H, W);
+    R3DP_REQUIRE(N > 0 && M > 0 && H >= 2 && W >= 2, "render: bad shape N=%d M=%d H=%d W=%d (planes must be at least 2x2)", N, M, H, W);
     R3DP_REQUIRE(S >= 4, "render: depth_resolution must be >= 4 (got %d)", S);
     R3DP_REQUIRE(S_imp >= 0 && (S_imp == 0 || u_fine), "render: depth_resolution_importance=%d needs u_fine", S_imp);
     R3DP_REQUIRE(box_warp > 0.f, "render: box_warp must be positive");

@@ -118,6 +118,33 @@ __device__ __forceinline__ float4 bilinear_cl(const float* __restrict__ plane, i
     return r;
 }
 
+// Descriptor of one bilinear tap quad for the fused renderer: out[0] = float-punned offset (in floats, from the frame's plane base)
+// of a 2x2 texel block that lies fully inside the plane, out[1..4] = weights of its (x,y), (x+1,y), (x,y+1), (x+1,y+1) texels.
+// grid_sample's zero padding is folded into the weights: a tap outside the plane gets weight 0 and the block is shifted inside,
+// so the gather needs no bounds checks (requires H, W >= 2).  The products are the same ones grid_sample forms.
+__device__ __forceinline__ void axis_taps(float p, int size, int& base, float& wa, float& wb) {
+    const float f0 = floorf(p);
+    const float w1 = p - f0, w0 = (f0 + 1.0f) - p;
+    const int i0 = (int)fminf(fmaxf(f0, -2.0f), (float)size + 1.0f);
+    base = min(max(i0, 0), size - 2);
+    const bool finite = (p == p);
+    wa = 0.f; wb = 0.f;
+    if (finite) {
+        if (i0 == base) { wa = w0; wb = w1; }                 // both taps inside
+        else if (i0 == -1) { wa = w1; }                       // left tap outside: the right tap is texel 0 = base
+        else if (i0 == size - 1) { wb = w0; }                 // right tap outside: the left tap is texel size-1 = base+1
+    }
+}
+__device__ __forceinline__ void tap_desc(float gu, float gv, int H, int W, int plane, float* out) {
+    const float px = ((gu + 1.0f) * (float)W - 1.0f) * 0.5f;      // align_corners=False
+    const float py = ((gv + 1.0f) * (float)H - 1.0f) * 0.5f;
+    int bx, by; float wxa, wxb, wya, wyb;
+    axis_taps(px, W, bx, wxa, wxb);
+    axis_taps(py, H, by, wya, wyb);
+    out[0] = __int_as_float(((plane * H + by) * W + bx) * kC);
+    out[1] = wxa * wya; out[2] = wxb * wya; out[3] = wxa * wyb; out[4] = wxb * wyb;
+}
+
 // plane 0 <- (x,y), plane 1 <- (x,z), plane 2 <- (z,x)   (generate_planes + project_onto_planes, renderer.py:30-63)
 __device__ __forceinline__ void gather3(const PlaneView& pv, float x, float y, float z, int cq, float4& f0, float4& f1, float4& f2) {
     const float gx = pv.scale * x, gy = pv.scale * y, gz = pv.scale * z;

@@ -886,57 +886,56 @@ __global__ void resize_to_nhwc_f16_kernel(const float* __restrict__ x, int N, in
 
 // last column X = 2W of the transposed-conv result (the only part of the (2H+1)x(2W+1) grid the 128-wide GEMM tiles do not
 // cover): yb[n][Y][2W][co] = sum_{ci, ky == Y (mod 2)} x[(Y-ky)/2][W-1][ci] * w[ky*3+2][co][ci].
-// CTA = 16 consecutive rows Y x 32 couts of one image: the <= 10 input pixels the rows touch are staged in smem, each warp
-// owns 4 couts with their three weight rows (the kx = 2 column of the kernel) in registers.  Cp <= 256.
+// CTA = 32 couts x 16 rows of one image.  The kx = 2 column of the kernel for these couts ([3][32][Cp] fp16) and the <= 10 input
+// pixels are staged in smem; thread (co, row pair) then runs plain dot products - no cross-lane reductions.  Cp <= 256.
 constexpr int kEdgeRows = 16, kEdgeCo = 32;
 __global__ void __launch_bounds__(256) upconv_edge_kernel(const __half* __restrict__ x, const __half* __restrict__ wp, int H, int W, int Cp, int O,
                                                           int w_shared, __half* __restrict__ yb) {
-    __shared__ __align__(16) __half s_x[kEdgeRows / 2 + 2][256];
+    extern __shared__ __align__(16) uint8_t edge_smem[];
+    __half* s_x = reinterpret_cast<__half*>(edge_smem);                      // [10][Cp]
+    __half* s_w = s_x + (kEdgeRows / 2 + 2) * Cp;                            // [3][32][Cp + 8]   (+8 halfs: rows land in different banks)
+    const int WS = Cp + 8;
     const int n = blockIdx.z, Y0 = blockIdx.x * kEdgeRows, co0 = blockIdx.y * kEdgeCo;
     const int BH = 2 * H + 1, BW = 2 * W + 1;
     const int wn = w_shared ? 0 : n;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int iy0 = Y0 / 2 - 1;                                              // first input row any of these Y can touch
-    for (int e = threadIdx.x; e < (kEdgeRows / 2 + 2) * Cp; e += 256) {
-        const int r = e / Cp, c = e - r * Cp, iy = iy0 + r;
-        s_x[r][c] = (iy >= 0 && iy < H) ? x[(((size_t)n * H + iy) * W + (W - 1)) * Cp + c] : __float2half(0.f);
+    const int vec = Cp / 8;
+    for (int e = threadIdx.x; e < (kEdgeRows / 2 + 2) * vec; e += 256) {
+        const int r = e / vec, c8 = e - r * vec, iy = iy0 + r;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (iy >= 0 && iy < H) v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)n * H + iy) * W + (W - 1)) * Cp) + c8);
+        *reinterpret_cast<uint4*>(s_x + r * Cp + c8 * 8) = v;
+    }
+    for (int e = threadIdx.x; e < 3 * kEdgeCo * vec; e += 256) {
+        const int c8 = e % vec, co = (e / vec) % kEdgeCo, ky = e / (vec * kEdgeCo);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (co0 + co < O) v = __ldg(reinterpret_cast<const uint4*>(wp + (((size_t)wn * 9 + ky * 3 + 2) * O + co0 + co) * Cp) + c8);
+        *reinterpret_cast<uint4*>(s_w + (ky * kEdgeCo + co) * WS + c8 * 8) = v;
     }
     __syncthreads();
-    const int c0 = lane * 8;
-    const bool on = c0 < Cp;
-#pragma unroll 1
-    for (int cc = 0; cc < kEdgeCo / 8; ++cc) {
-        const int co = co0 + warp * (kEdgeCo / 8) + cc;
-        if (co >= O) break;
-        float wv[3][8];
+    const int co = threadIdx.x & 31, yp = threadIdx.x >> 5;                  // 8 warps x 2 rows each; lanes = couts
+    if (co0 + co >= O) return;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            uint4 raw = make_uint4(0, 0, 0, 0);
-            if (on) raw = __ldg(reinterpret_cast<const uint4*>(wp + (((size_t)wn * 9 + ky * 3 + 2) * O + co) * Cp + c0));
-            const __half2* h = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); wv[ky][2 * j] = f.x; wv[ky][2 * j + 1] = f.y; }
-        }
-#pragma unroll
-        for (int yy = 0; yy < kEdgeRows; ++yy) {
-            const int Y = Y0 + yy;
-            float acc = 0.f;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                if (((yy ^ ky) & 1) || !on) continue;                        // Y0 is even: parity of Y == parity of yy
-                const int r = ((yy - ky) >> 1) + 1;                          // == (Y-ky)/2 - iy0 ; rows outside the image hold zeros
-                const uint4 raw = *reinterpret_cast<const uint4*>(&s_x[r][c0]);
-                const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    for (int half = 0; half < 2; ++half) {
+        const int yy = yp * 2 + half, Y = Y0 + yy;
+        if (Y >= BH) continue;
+        float acc = 0.f;
+        for (int ky = (yy & 1); ky < 3; ky += 2) {                           // Y0 is even: parity of Y == parity of yy
+            const int r = ((yy - ky) >> 1) + 1;                              // == (Y-ky)/2 - iy0 ; rows outside the image hold zeros
+            const uint4* xr = reinterpret_cast<const uint4*>(s_x + r * Cp);
+            const uint4* wr = reinterpret_cast<const uint4*>(s_w + (ky * kEdgeCo + co) * WS);
+            for (int c8 = 0; c8 < vec; ++c8) {
+                const uint4 xv = xr[c8], wv = wr[c8];
+                const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+                const __half2* wh = reinterpret_cast<const __half2*>(&wv);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float2 f = __half22float2(h[j]);
-                    acc = fmaf(f.x, wv[ky][2 * j], acc); acc = fmaf(f.y, wv[ky][2 * j + 1], acc);
+                    const float2 a = __half22float2(xh[j]), b = __half22float2(wh[j]);
+                    acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
                 }
             }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0 && Y < BH) yb[(((size_t)n * BH + Y) * BW + 2 * W) * O + co] = __float2half_rn(acc);
         }
+        yb[(((size_t)n * BH + Y) * BW + 2 * W) * O + co0 + co] = __float2half_rn(acc);
     }
 }
 
@@ -1343,7 +1342,10 @@ extern "C" int r3dp_sr_tc_layer(const void* x_f16, const void* wp_f16, const flo
     {
         R3DP_REQUIRE(Ip <= 256, "sr_tc_layer: up=2 supports at most 256 input channels");
         dim3 grid((2 * H + 1 + kEdgeRows - 1) / kEdgeRows, (O + kEdgeCo - 1) / kEdgeCo, N);
-        upconv_edge_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(x_f16), reinterpret_cast<const __half*>(wp_f16), H, W, Ip, O,
+        const size_t esmem = ((size_t)(kEdgeRows / 2 + 2) * Ip + 3 * (size_t)kEdgeCo * (Ip + 8)) * sizeof(__half);
+        static bool eattr = false;
+        if (!eattr) { R3DP_CUDA(cudaFuncSetAttribute(upconv_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); eattr = true; }
+        upconv_edge_kernel<<<grid, 256, esmem, st>>>(reinterpret_cast<const __half*>(x_f16), reinterpret_cast<const __half*>(wp_f16), H, W, Ip, O,
                                                  Nw == 1, yb);
     }
     {

@@ -49,6 +49,8 @@ _SIGNATURES = {
     'r3dp_sr_tc_scratch_bytes': (_Z, [_I, _I, _I, _I]),
     'r3dp_sr_tc_layer': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'r3dp_sr_tc_torgb': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    'r3dp_sr_tc_pack_weights_up_composed': (_I, [_P, _I, _I, _I, _P, _P]),
+    'r3dp_sr_tc_layer_up_composed': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     'r3dp_sr_tc_layer_torgb': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'r3dp_sr_tc_input_nhwc': (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     'r3dp_sr_tc_last_layer': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),

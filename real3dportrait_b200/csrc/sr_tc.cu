@@ -1229,10 +1229,10 @@ static void fill_taps2(Taps2& t2, const Taps& t) {
     t2.gstart[t2.ngroups] = n;
 }
 
-static int run_conv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, Conv2Args& a, int max_rows, cudaStream_t st) {
+static int run_conv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, Conv2Args& a, int max_rows, cudaStream_t st, int n_taps = 9) {
     CUtensorMap tmA, tmB;
     if (make_map_4d_box(&tmA, x, (uint64_t)Cp, (uint64_t)W, (uint64_t)H, (uint64_t)N, A2_ROWS)) return 1;
-    if (make_map_4d_box(&tmB, wp, (uint64_t)Cp, (uint64_t)O, 9, (uint64_t)Nw, tc_pairs() ? BN / 2 : BN)) return 1;
+    if (make_map_4d_box(&tmB, wp, (uint64_t)Cp, (uint64_t)O, (uint64_t)n_taps, (uint64_t)Nw, tc_pairs() ? BN / 2 : BN)) return 1;
     a.k_chunks = Cp / BK; a.tiles_x = W / BM; a.n_blocks = O / BN; a.n_images = N; a.w_shared = (Nw == 1);
     R3DP_REQUIRE(a.n_blocks >= 1 && a.n_blocks <= 2, "conv_tc2: 128 or 256 output channels");
     if (tc_pairs()) return tc_rows() == 1 ? launch_conv3_r<1>(tmA, tmB, a, max_rows, st) : launch_conv3_r<2>(tmA, tmB, a, max_rows, st);
@@ -1460,4 +1460,66 @@ extern "C" int r3dp_sr_tc_input_nhwc(const float* x_nhwc, int N, int C, int h, i
     R3DP_LAUNCH_CHECK();
     count_launches(1);
     return 0;
+}
+
+// ---- composed up-convolution for small Cin -------------------------------------------------------------------------------
+// FIR(conv_transpose(x, w)) == four 3x3 correlations on the low-resolution input, one per output parity (p,q), with weights
+//   G[p][q][dy][dx] = sum_{ky,kx} A[p][dy][ky] * A[q][dx][kx] * w[ky][kx],   A[p][dy][ky] = sum_u g[u] * [p + u - 1 - ky == 2 dy],
+// g = [1,3,3,1]/4 (FIR * gain 4), dy,dx in {-1,0,1}  (derivation in DESIGN.md).  This costs 4x the MACs of the two-step form but
+// needs no (2H+1)x(2W+1) intermediate, no FIR pass and no edge column: a win when Cin is small (block0.conv0: 32 -> 256).
+// wf fp32 [Nw][O][I][3][3] -> packed fp16 [Nw][36][O][Ip], tap index = (p*2+q)*9 + (dy+1)*3 + (dx+1).
+__global__ void compose_up_weights_kernel(const float* __restrict__ wf, int Nw, int O, int I, int Ip, __half* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)Nw * 36 * O * Ip;
+    if (idx >= total) return;
+    const int i = (int)(idx % Ip); const int o = (int)((idx / Ip) % O); const int t = (int)((idx / ((long long)Ip * O)) % 36);
+    const int nw = (int)(idx / ((long long)Ip * O * 36));
+    float acc = 0.f;
+    if (i < I) {
+        const int ph = t / 9, tap = t % 9, p = ph >> 1, q = ph & 1, dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const float g[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+        const float* w = wf + (((size_t)nw * O + o) * I + i) * 9;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int u = 2 * dy + 1 + ky - p;                      // p + u - 1 - ky == 2 dy
+            if (u < 0 || u > 3) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int v = 2 * dx + 1 + kx - q;
+                if (v < 0 || v > 3) continue;
+                acc = fmaf(g[u] * g[v], w[ky * 3 + kx], acc);
+            }
+        }
+    }
+    out[idx] = __float2half_rn(acc);
+}
+
+extern "C" int r3dp_sr_tc_pack_weights_up_composed(const float* wf, int Nw, int O, int I, void* packed_f16, r3dp_stream_t stream) {
+    R3DP_REQUIRE(wf && packed_f16, "sr_tc_pack_weights_up_composed: null pointer");
+    R3DP_REQUIRE(Nw > 0 && O > 0 && I > 0, "sr_tc_pack_weights_up_composed: bad shape");
+    const int Ip = (I + 63) / 64 * 64;
+    const long long total = (long long)Nw * 36 * O * Ip;
+    compose_up_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(wf, Nw, O, I, Ip, reinterpret_cast<__half*>(packed_f16));
+    R3DP_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+// SynthesisLayer with up == 2 through the composed weights: x [N][H][W][Ip] fp16 -> y [N][2H][2W][O] fp16 (bias + lrelu fused).
+extern "C" int r3dp_sr_tc_layer_up_composed(const void* x_f16, const void* wpc_f16, const float* bias, int N, int Nw, int I, int O, int H,
+                                            int W, void* y_f16, r3dp_stream_t stream) {
+    R3DP_REQUIRE(x_f16 && wpc_f16 && bias && y_f16, "sr_tc_layer_up_composed: null pointer");
+    R3DP_REQUIRE(N > 0 && (Nw == N || Nw == 1) && W % BM == 0 && O % BN == 0 && O <= 256, "sr_tc_layer_up_composed: bad shape");
+    R3DP_REQUIRE(tc_version() >= 2, "sr_tc_layer_up_composed needs the persistent conv kernels");
+    const int Ip = (I + 63) / 64 * 64;
+    Conv2Args a = {};
+    a.n_phases = 4;
+    for (int ph = 0; ph < 4; ++ph) {
+        Taps t = {};
+        t.n = 9;
+        for (int i = 0; i < 9; ++i) { t.dy[i] = i / 3 - 1; t.dx[i] = i % 3 - 1; t.widx[i] = ph * 9 + i; }
+        fill_taps2(a.ph[ph].taps, t);
+        a.ph[ph].rows = H; a.ph[ph].oy_off = ph >> 1; a.ph[ph].ox_off = ph & 1;
+    }
+    a.mode = kStoreAct; a.out = reinterpret_cast<__half*>(y_f16); a.out_H = 2 * H; a.out_W = 2 * W; a.out_C = O; a.oy_mul = a.ox_mul = 2;
+    a.bias = bias;
+    return run_conv2(x_f16, N, H, W, Ip, wpc_f16, Nw, O, a, H, as_stream(stream), 36);
 }

@@ -25,12 +25,36 @@ def _pack(layer, w_lat: torch.Tensor) -> torch.Tensor:
     return out
 
 
+COMPOSE_MAX_CIN = 64      # up layers with at most this many input channels run through FIR-composed weights
+
+
+def _pack_up_composed(layer_, w_lat: torch.Tensor) -> torch.Tensor:
+    """Up SynthesisLayer -> FIR-composed packed fp16 weights [Nw,36,O,Ipad] (4 output parities x 3x3 taps)."""
+    wf = layer_.folded_weight(w_lat)
+    Nw, O, I = wf.shape[:3]
+    Ip = (I + 63) // 64 * 64
+    out = torch.empty(Nw, 36, O, Ip, device=wf.device, dtype=torch.float16)
+    capi.check(capi.lib().r3dp_sr_tc_pack_weights_up_composed(capi.ptr(wf), Nw, O, I, capi.ptr(out, torch.float16), capi.stream()))
+    return out
+
+
+def pack_for(layer_, w_lat: torch.Tensor) -> torch.Tensor:
+    if layer_.up == 2 and layer_.in_channels <= COMPOSE_MAX_CIN:
+        return _pack_up_composed(layer_, w_lat)
+    return _pack(layer_, w_lat)
+
+
 def layer(x16: torch.Tensor, lay, wp: torch.Tensor, up: int) -> torch.Tensor:
     """x16 [N,H,W,Ipad] fp16 NHWC -> [N,H*up,W*up,O] fp16 NHWC."""
     N, H, W, _ = x16.shape
     O, Nw = lay.out_channels, wp.shape[0]
     L = capi.lib()
     y = torch.empty(N, H * up, W * up, O, device=x16.device, dtype=torch.float16)
+    if up == 2 and wp.shape[1] == 36:                             # FIR-composed weights
+        with capi.region('sr_conv'):
+            capi.check(L.r3dp_sr_tc_layer_up_composed(capi.ptr(x16, torch.float16), capi.ptr(wp, torch.float16), capi.ptr(capi.f32(lay.bias)), N, Nw,
+                                                      lay.in_channels, O, H, W, capi.ptr(y, torch.float16), capi.stream()))
+        return y
     scratch = None
     if up == 2:
         scratch = torch.empty(L.r3dp_sr_tc_scratch_bytes(N, O, H, W), device=x16.device, dtype=torch.uint8)
@@ -57,7 +81,7 @@ class Prepared:
     def __init__(self, sr, wsel: torch.Tensor):
         b0, b1 = sr.block0, sr.block1
         self.Nw = wsel.shape[0]
-        self.wp = [_pack(b0.conv0, wsel[:, 0]), _pack(b0.conv1, wsel[:, 1]), _pack(b1.conv0, wsel[:, 0]), _pack(b1.conv1, wsel[:, 1])]
+        self.wp = [pack_for(b0.conv0, wsel[:, 0]), pack_for(b0.conv1, wsel[:, 1]), pack_for(b1.conv0, wsel[:, 0]), pack_for(b1.conv1, wsel[:, 1])]
         self.wrgb0, self.wrgb1 = b0.torgb.folded_weight(wsel[:, 2]), b1.torgb.folded_weight(wsel[:, 2])
 
 

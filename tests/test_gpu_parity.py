@@ -178,7 +178,7 @@ def test_render_head_vs_oracle_with_per_sample_styles():
 #   single layer vs fp32 math on the SAME fp16-rounded operands: 2e-3 * max|y|  (only the fp16 rounding of the output differs)
 #   full SR image vs the fp32 reference: max-abs < 2e-2 on images of range ~[-6, 6] and PSNR > 60 dB
 # ---------------------------------------------------------------------------------------------------------------------
-def _tc_layer_case(up, I, O, H, W, N=2, shared=False, seed=0):
+def _tc_layer_case(up, I, O, H, W, N=2, shared=False, seed=0, composed=False):
     from real3dportrait_b200 import sr_tc
     g = torch.Generator().manual_seed(seed)
     lay = r3.SynthesisLayer(I, O, w_dim=512, resolution=W * up, up=up)
@@ -191,9 +191,10 @@ def _tc_layer_case(up, I, O, H, W, N=2, shared=False, seed=0):
     x16 = x.half()
     wp = sr_tc._pack(lay, w.to(DEV))                                         # [Nw,9,O,Ip] fp16, folded in fp32 first
     Ip = wp.shape[-1]
+    wp_run = sr_tc._pack_up_composed(lay, w.to(DEV)) if composed else wp
     xin = torch.zeros(N, H, W, Ip, dtype=torch.float16)
     xin[..., :I] = x16.permute(0, 2, 3, 1)
-    y = sr_tc.layer(xin.to(DEV), lay, wp, up)                                # [N,H*up,W*up,O] fp16
+    y = sr_tc.layer(xin.to(DEV), lay, wp_run, up)                            # [N,H*up,W*up,O] fp16
     torch.cuda.synchronize()
     # oracle on the same fp16-rounded operands, fp32 arithmetic
     wf16 = wp.float().cpu()[..., :I].reshape(-1, 3, 3, O, I).permute(0, 3, 4, 1, 2).contiguous()   # [Nw,O,I,3,3]
@@ -239,3 +240,10 @@ def test_sr_tc_per_sample_styles_vs_fp32_path():
         outs[mode] = sr.to(DEV)(fimg[:, :3].contiguous(), fimg, ws, noise_mode='none')
     err, rng = _maxdiff(outs['tc'], outs['fp32']), float(outs['fp32'].abs().max())
     assert err < 5e-3 * rng, (err, rng)
+
+
+def test_tc_up_layer_composed_weights_vs_oracle():
+    """block0.conv0 shape through the FIR-composed 4x3x3 weights (no intermediate / FIR pass) vs the two-step oracle."""
+    got, ref = _tc_layer_case(2, 32, 256, 6, 128, composed=True)
+    err = _maxdiff(got, ref)
+    assert err < 2e-3 * float(ref.abs().max()), (err, float(ref.abs().max()))

@@ -3,6 +3,7 @@
 //   triplane_sample           sample_from_planes (renderer.py:65-75): the HBM-roofline gather, write-dominated
 //   run_model                 ImportanceRenderer.run_model (renderer.py:169-188): gather + OSG decoder
 #include "render_core.cuh"
+#include <stdlib.h>
 
 namespace r3dp {
 
@@ -47,9 +48,11 @@ __global__ void __launch_bounds__(256) planes_to_cl_kernel(const float* __restri
 // ---- sample_from_planes ---------------------------------------------------------------------------------------------
 // Persistent grid-stride kernel: a warp handles 4 points per step (8 lanes x float4 = one 128 B texel line per tap),
 // 12 independent 16 B loads in flight per lane, outputs written with streaming stores (never re-read here).
-__global__ void __launch_bounds__(256) triplane_sample_kernel(const float* __restrict__ planes, int N, int H, int W,
-                                                              const float* __restrict__ coords, int P, float scale,
-                                                              float* __restrict__ out) {
+// MINB = resident CTAs per SM the register allocation targets; the grid is exactly MINB x #SM CTAs (one wave, no tail).
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) triplane_sample_kernel(const float* __restrict__ planes, int N, int H, int W,
+                                                                    const float* __restrict__ coords, int P, float scale,
+                                                                    float* __restrict__ out) {
     const int lane = threadIdx.x & 31, sub = lane >> 3, cq = lane & 7;
     const long long total4 = ((long long)N * P + 3) / 4;
     const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
@@ -163,11 +166,20 @@ extern "C" int r3dp_triplane_sample(const float* planes_cl, int N, int C, int H,
     R3DP_REQUIRE(C == kC, "triplane_sample: C must be %d (got %d)", kC, C);
     R3DP_REQUIRE(N > 0 && P > 0 && H > 0 && W > 0 && box_warp > 0.f, "triplane_sample: bad shape");
     const long long warps = ((long long)N * P + 3) / 4;
-    long long blocks = (warps + 7) / 8;
-    const long long cap = (long long)sm_count() * 8;                    // 8 resident CTAs of 256 threads per SM
-    if (blocks > cap) blocks = cap;
-    triplane_sample_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(planes_cl, N, H, W, coords, P, 2.0f / box_warp, out);
-    count_launches(1);
+    long long need = (warps + 7) / 8;
+    static int minb = -1;                          // R3DP_SAMPLE_MINB = 4 | 5 | 6 | 8 (register/occupancy trade-off, tuned on B200)
+    if (minb < 0) { const char* e = getenv("R3DP_SAMPLE_MINB"); minb = e ? atoi(e) : 4; if (minb != 4 && minb != 5 && minb != 6 && minb != 8) minb = 4; }
+    const long long cap = (long long)sm_count() * minb;
+    const unsigned blocks = (unsigned)(need < cap ? need : cap);
+    const float sc = 2.0f / box_warp;
+    cudaStream_t st = as_stream(stream);
+    switch (minb) {
+        case 4: triplane_sample_kernel<4><<<blocks, 256, 0, st>>>(planes_cl, N, H, W, coords, P, sc, out); break;
+        case 5: triplane_sample_kernel<5><<<blocks, 256, 0, st>>>(planes_cl, N, H, W, coords, P, sc, out); break;
+        case 8: triplane_sample_kernel<8><<<blocks, 256, 0, st>>>(planes_cl, N, H, W, coords, P, sc, out); break;
+        case 6: triplane_sample_kernel<6><<<blocks, 256, 0, st>>>(planes_cl, N, H, W, coords, P, sc, out); break;
+        default: triplane_sample_kernel<4><<<blocks, 256, 0, st>>>(planes_cl, N, H, W, coords, P, sc, out); break;
+    }
     R3DP_LAUNCH_CHECK();
     return 0;
 }

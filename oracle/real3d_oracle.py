@@ -389,3 +389,65 @@ def frame(planes, mlp, sr_params, cam2world, intrinsics, *, res=64, S=48, S_imp=
     sr = superres(fimg[:, :3], fimg, ws, sr_params)
     return {'image_raw': fimg[:, :3].clamp(-1, 1), 'image': sr.clamp(-1, 1), 'image_feature': fimg,
             'image_depth': feature_image(depth, res), 'weights_img': feature_image(wsum, res), 'is_ray_valid': valid}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# torso head                               modules/real3d/super_resolution/sr_with_ref.py:16-162 (fuse mode 'v2')
+# ----------------------------------------------------------------------------------------------------------------------
+
+def aa_down2(x: Tensor) -> Tensor:
+    """F.interpolate(scale 1/2, bilinear, align_corners=False, antialias=True) restated: triangle filter of support 2 around
+    centre 2(i+0.5): taps 2i-1..2i+2 with weights [1,3,3,1]/8, clipped to the image and renormalised (sr_with_ref.py:79-82)."""
+    def axis(t, dim):
+        n = t.shape[dim]
+        k = torch.tensor([0.25, 0.75, 0.75, 0.25])
+        idx = torch.arange(n // 2)[:, None] * 2 - 1 + torch.arange(4)[None, :]              # [n/2,4]
+        ok = (idx >= 0) & (idx < n)
+        w = (k[None, :] * ok) / (k[None, :] * ok).sum(1, keepdim=True)
+        g = t.index_select(dim, idx.clamp(0, n - 1).reshape(-1))
+        shp = list(t.shape); shp[dim:dim + 1] = [n // 2, 4]
+        g = g.reshape(shp)
+        wshape = [1] * g.ndim; wshape[dim] = n // 2; wshape[dim + 1] = 4
+        return (g * w.reshape(wshape)).sum(dim + 1)
+    return axis(axis(x, 2), 3)
+
+
+def conv_plain(x: Tensor, p: Dict[str, Tensor], name: str, act: Optional[float] = None) -> Tensor:
+    """nn.Conv2d(stride 1, 'same' padding) [+ nn.LeakyReLU(act)]."""
+    w = p[name + '.weight']
+    y = F.conv2d(x, w, p[name + '.bias'], padding=w.shape[-1] // 2)
+    return F.leaky_relu(y, act) if act is not None else y
+
+
+def synthesis_block_noup(x, img, ws3, p, prefix):
+    """SynthesisBlockNoUp.forward (superresolution.py:209-258): two non-upsampling layers, img += torgb (no upsampling of img)."""
+    x = synthesis_layer(x, ws3[:, 0], p, prefix + 'conv0.', up=1)
+    x = synthesis_layer(x, ws3[:, 1], p, prefix + 'conv1.', up=1)
+    return x, img + to_rgb(x, ws3[:, 2], p, prefix + 'torgb.')
+
+
+def superres_warp(rgb, x, ws, ref_torso_rgb, ref_bg_rgb, weights_img, segmap, kp_s, kp_d, p: Dict[str, Tensor], torso_model, head_threshold=0.9):
+    """SuperresolutionHybrid8XDC_Warp.forward, htbsr_head_weight_fuse_mode 'v2', torso_model_version 'v2' (sr_with_ref.py:67-136)."""
+    ws3 = ws[:, -1:, :].expand(rgb.shape[0], 3, -1)
+    if x.shape[-1] != 128:
+        x, rgb = resize_bilinear(x, 128), resize_bilinear(rgb, 128)
+    rgb_256 = resize_bilinear(rgb, 256)
+    weights_256 = resize_bilinear(weights_img, 256)
+    ref_torso_256, ref_bg_256 = aa_down2(ref_torso_rgb), aa_down2(ref_bg_rgb)
+    x, rgb = synthesis_block(x, rgb, ws3, p, 'block0.')
+    rgb_torso, ret = torso_model(ref_torso_256, segmap, kp_s, kp_d, rgb_256, weights_256, cal_loss=True, target_torso_mask=None)
+    x_torso = conv_plain(ret['deformed_torso_hid'], p, 'torso_encoder.0')
+    x_bg = conv_plain(conv_plain(conv_plain(ref_bg_256, p, 'bg_encoder.0', 0.01), p, 'bg_encoder.2', 0.01), p, 'bg_encoder.4')
+    alpha = weights_256                                                                    # :108-109 (the masked assignment is a no-op)
+    rgb = rgb * alpha + rgb_torso * (1 - alpha)
+    x = torch.cat([x * alpha, x_torso * (1 - alpha)], dim=1)
+    x = conv_plain(conv_plain(x, p, 'fuse_head_torso_convs.0', 0.01), p, 'fuse_head_torso_convs.2')
+    x, rgb = synthesis_block_noup(x, rgb, ws3, p, 'head_torso_block.')
+    head_occ = torch.where(alpha > head_threshold, torch.ones_like(alpha), alpha)
+    torso_occ = ret['occlusion_2'] if ret['occlusion_2'].shape[-1] == 256 else resize_bilinear(ret['occlusion_2'], 256)
+    person = (torso_occ + head_occ).clamp(0, 1)
+    rgb = rgb * person + ref_bg_256 * (1 - person)
+    x = torch.cat([x * person, x_bg * (1 - person)], dim=1)
+    x = conv_plain(conv_plain(conv_plain(x, p, 'fuse_fg_bg_convs.0', 0.01), p, 'fuse_fg_bg_convs.2', 0.01), p, 'fuse_fg_bg_convs.4')
+    x, rgb = synthesis_block(x, rgb, ws3, p, 'block1.')
+    return rgb, ret

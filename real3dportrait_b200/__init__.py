@@ -8,8 +8,9 @@ from .renderer import ImportanceRenderer, PlanesCL, generate_planes, planes_to_c
 from .ray_marcher import MipRayMarcher2
 from .decoder import FullyConnectedLayer, OSGDecoder
 from .superresolution import SuperresolutionHybrid8XDC, SynthesisBlock, SynthesisLayer, ToRGBLayer
+from .sr_with_ref import SuperresolutionHybrid8XDC_Warp, SynthesisBlockNoUp
 from .synthesis import RenderHead
 
 __all__ = ['RaySampler', 'ImportanceRenderer', 'PlanesCL', 'generate_planes', 'planes_to_channels_last',
            'sample_from_planes', 'MipRayMarcher2', 'FullyConnectedLayer', 'OSGDecoder', 'SuperresolutionHybrid8XDC',
-           'SynthesisBlock', 'SynthesisLayer', 'ToRGBLayer', 'RenderHead']
+           'SynthesisBlock', 'SynthesisLayer', 'ToRGBLayer', 'SuperresolutionHybrid8XDC_Warp', 'SynthesisBlockNoUp', 'RenderHead']

@@ -319,6 +319,8 @@ struct Conv2Args {
     int w_shared, mode;
     __half* out; int out_H, out_W, out_C, oy_mul, ox_mul;
     const float* bias; const float* wrgb; const float* brgb; const float* img_prev; float* img_out; int img_H, img_W;
+    float act_slope, act_gain;      // epilogue activation: v < 0 ? v*slope : v, then * gain  (0.2, sqrt2 = bias_act lrelu; 0.01, 1 = nn.LeakyReLU; 1, 1 = linear)
+    int skip_same_res;              // ToRGB skip image has the output resolution (SynthesisBlockNoUp) instead of half (FIR-upsampled)
 };
 
 template <int R> struct Cfg2 {
@@ -537,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc2_kernel(const __grid_cons
 #pragma unroll
                             for (int jj = 0; jj < 32; ++jj) {
                                 const float v = __uint_as_float(r[jj]) + s_bias[nblk * BN + c0 + jj];
-                                f[jj] = (v < 0.f ? v * 0.2f : v) * 1.4142135623730951f;      // bias_act lrelu, gain sqrt(2)
+                                f[jj] = (v < 0.f ? v * a.act_slope : v) * a.act_gain;        // bias_act lrelu*sqrt2 | nn.LeakyReLU | linear
                             }
                         }
                         if (a.mode != kToRgbFinal && in_img) store_half32(dst + c0, f);
@@ -559,8 +561,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc2_kernel(const __grid_cons
                     if (want_rgb && nblk == a.n_blocks - 1 && in_img) {
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            const float skip = a.img_prev ? upsampled_skip(a.img_prev + ((size_t)n * 3 + c) * (a.img_H / 2) * (a.img_W / 2),
-                                                                           a.img_H / 2, a.img_W / 2, Y, X) : 0.f;
+                            float skip = 0.f;
+                            if (a.img_prev) skip = a.skip_same_res ? __ldg(a.img_prev + (((size_t)n * 3 + c) * a.img_H + Y) * a.img_W + X)
+                                                                   : upsampled_skip(a.img_prev + ((size_t)n * 3 + c) * (a.img_H / 2) * (a.img_W / 2),
+                                                                                    a.img_H / 2, a.img_W / 2, Y, X);
                             a.img_out[(((size_t)n * 3 + c) * a.img_H + Y) * a.img_W + X] = rgb[j][c] + a.brgb[c] + skip;
                         }
                     }
@@ -802,7 +806,7 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
 #pragma unroll
                             for (int jj = 0; jj < 32; ++jj) {
                                 const float v = __uint_as_float(r[jj]) + s_bias[nblk * BN + c0 + jj];
-                                f[jj] = (v < 0.f ? v * 0.2f : v) * 1.4142135623730951f;      // bias_act lrelu, gain sqrt(2)
+                                f[jj] = (v < 0.f ? v * a.act_slope : v) * a.act_gain;        // bias_act lrelu*sqrt2 | nn.LeakyReLU | linear
                             }
                         }
                         if (a.mode != kToRgbFinal && in_img) store_half32(dst + c0, f);
@@ -831,8 +835,10 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                     if (want_rgb && nblk == a.n_blocks - 1 && in_img && cg == 0) {
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            const float skip = a.img_prev ? upsampled_skip(a.img_prev + ((size_t)n * 3 + c) * (a.img_H / 2) * (a.img_W / 2),
-                                                                           a.img_H / 2, a.img_W / 2, Y, X) : 0.f;
+                            float skip = 0.f;
+                            if (a.img_prev) skip = a.skip_same_res ? __ldg(a.img_prev + (((size_t)n * 3 + c) * a.img_H + Y) * a.img_W + X)
+                                                                   : upsampled_skip(a.img_prev + ((size_t)n * 3 + c) * (a.img_H / 2) * (a.img_W / 2),
+                                                                                    a.img_H / 2, a.img_W / 2, Y, X);
                             a.img_out[(((size_t)n * 3 + c) * a.img_H + Y) * a.img_W + X] = rgb[j][c] + a.brgb[c] + skip;
                         }
                     }
@@ -1234,6 +1240,7 @@ static int run_conv2(const void* x, int N, int H, int W, int Cp, const void* wp,
     if (make_map_4d_box(&tmA, x, (uint64_t)Cp, (uint64_t)W, (uint64_t)H, (uint64_t)N, A2_ROWS)) return 1;
     if (make_map_4d_box(&tmB, wp, (uint64_t)Cp, (uint64_t)O, (uint64_t)n_taps, (uint64_t)Nw, tc_pairs() ? BN / 2 : BN)) return 1;
     a.k_chunks = Cp / BK; a.tiles_x = W / BM; a.n_blocks = O / BN; a.n_images = N; a.w_shared = (Nw == 1);
+    if (a.act_gain == 0.f) { a.act_slope = 0.2f; a.act_gain = 1.4142135623730951f; }      // default: bias_act lrelu
     R3DP_REQUIRE(a.n_blocks >= 1 && a.n_blocks <= 2, "conv_tc2: 128 or 256 output channels");
     if (tc_pairs()) return tc_rows() == 1 ? launch_conv3_r<1>(tmA, tmB, a, max_rows, st) : launch_conv3_r<2>(tmA, tmB, a, max_rows, st);
     switch (tc_rows()) {
@@ -1522,4 +1529,150 @@ extern "C" int r3dp_sr_tc_layer_up_composed(const void* x_f16, const void* wpc_f
     a.mode = kStoreAct; a.out = reinterpret_cast<__half*>(y_f16); a.out_H = 2 * H; a.out_W = 2 * W; a.out_C = O; a.oy_mul = a.ox_mul = 2;
     a.bias = bias;
     return run_conv2(x_f16, N, H, W, Ip, wpc_f16, Nw, O, a, H, as_stream(stream), 36);
+}
+
+// ---- building blocks of the torso head (modules/real3d/super_resolution/sr_with_ref.py:16-162) --------------------------------
+// Plain nn.Conv2d (k = 1 or 3, stride 1, "same" padding) [+ activation] on the tensor-core path: x [N][H][W][Ip] fp16, weights packed by
+// r3dp_sr_tc_pack_weights from the [1][O][I][k][k] fp32 tensor (k = 1: the value sits in tap 4), y [N][H][W][O] fp16.
+// act: 0 = linear, 1 = lrelu(0.2)*sqrt2 (bias_act), 2 = nn.LeakyReLU() (slope 0.01).
+extern "C" int r3dp_sr_tc_conv(const void* x_f16, const void* wp_f16, const float* bias, int N, int Nw, int I, int O, int H, int W, int ksize,
+                               int act, void* y_f16, r3dp_stream_t stream) {
+    R3DP_REQUIRE(x_f16 && wp_f16 && bias && y_f16, "sr_tc_conv: null pointer");
+    R3DP_REQUIRE(N > 0 && (Nw == N || Nw == 1) && W % BM == 0 && O % BN == 0 && O <= 256 && (ksize == 1 || ksize == 3) && act >= 0 && act <= 2,
+                 "sr_tc_conv: bad shape / options");
+    R3DP_REQUIRE(tc_version() >= 2, "sr_tc_conv needs the persistent conv kernels");
+    const int Ip = (I + 63) / 64 * 64;
+    Conv2Args a = {};
+    Taps t = {};
+    if (ksize == 3) { t.n = 9; for (int i = 0; i < 9; ++i) { t.dy[i] = i / 3 - 1; t.dx[i] = i % 3 - 1; t.widx[i] = i; } }
+    else { t.n = 1; t.dy[0] = 0; t.dx[0] = 0; t.widx[0] = 4; }
+    a.n_phases = 1;
+    fill_taps2(a.ph[0].taps, t);
+    a.ph[0].rows = H;
+    a.mode = kStoreAct; a.out = reinterpret_cast<__half*>(y_f16); a.out_H = H; a.out_W = W; a.out_C = O; a.oy_mul = a.ox_mul = 1; a.bias = bias;
+    a.act_slope = act == 0 ? 1.0f : (act == 1 ? 0.2f : 0.01f);
+    a.act_gain = act == 1 ? 1.4142135623730951f : 1.0f;
+    return run_conv2(x_f16, N, H, W, Ip, wp_f16, Nw, O, a, H, as_stream(stream));
+}
+
+// SynthesisBlockNoUp tail (superresolution.py:159-258): conv3x3 (modulated, up == 1) + bias/lrelu -> y, and img_out = img_prev (SAME resolution)
+// + ToRGB(y) + brgb.
+extern "C" int r3dp_sr_tc_layer_torgb_noup(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
+                                           const float* img_prev, int N, int Nw, int I, int O, int H, int W, void* y_f16, float* img_out,
+                                           r3dp_stream_t stream) {
+    R3DP_REQUIRE(x_f16 && wp_f16 && bias && wrgb && brgb && y_f16 && img_out, "sr_tc_layer_torgb_noup: null pointer");
+    R3DP_REQUIRE(N > 0 && (Nw == N || Nw == 1) && W % BM == 0 && O % BN == 0 && O <= 256, "sr_tc_layer_torgb_noup: bad shape");
+    const int Ip = (I + 63) / 64 * 64;
+    Conv2Args a = {};
+    Taps t = {};
+    t.n = 9;
+    for (int i = 0; i < 9; ++i) { t.dy[i] = i / 3 - 1; t.dx[i] = i % 3 - 1; t.widx[i] = i; }
+    a.n_phases = 1;
+    fill_taps2(a.ph[0].taps, t);
+    a.ph[0].rows = H;
+    a.mode = kActRgb; a.out = reinterpret_cast<__half*>(y_f16); a.out_H = H; a.out_W = W; a.out_C = O; a.oy_mul = a.ox_mul = 1;
+    a.bias = bias; a.wrgb = wrgb; a.brgb = brgb; a.img_prev = img_prev; a.img_out = img_out; a.img_H = H; a.img_W = W; a.skip_same_res = 1;
+    return run_conv2(x_f16, N, H, W, Ip, wp_f16, Nw, O, a, H, as_stream(stream));
+}
+
+// out[n,y,x,:] = [ xa[n,y,x,0:Ca] * alpha[n,y,x] , xb[n,y,x,0:Cb] * (1 - alpha[n,y,x]) ]   (sr_with_ref.py:111,122: alpha-cat fusion), fp16 NHWC
+__global__ void alpha_cat_kernel(const __half* __restrict__ xa, int Ca, int sa, const __half* __restrict__ xb, int Cb, int sb,
+                                 const float* __restrict__ alpha, long long npix, __half* __restrict__ out) {
+    const int cv = (Ca + Cb) / 8;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npix * cv) return;
+    const long long pix = idx / cv; const int c8 = (int)(idx - pix * cv);
+    const float al = alpha[pix];
+    const bool first = c8 * 8 < Ca;
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(first ? xa + pix * sa + c8 * 8 : xb + pix * sb + (c8 * 8 - Ca)));
+    const float m = first ? al : 1.0f - al;
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    uint4 pk; __half2* ph = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); ph[j] = __floats2half2_rn(f.x * m, f.y * m); }
+    *reinterpret_cast<uint4*>(out + idx * 8) = pk;
+}
+extern "C" int r3dp_sr_alpha_cat(const void* xa_f16, int Ca, int stride_a, const void* xb_f16, int Cb, int stride_b, const float* alpha, int N,
+                                 int H, int W, void* out_f16, r3dp_stream_t stream) {
+    R3DP_REQUIRE(xa_f16 && xb_f16 && alpha && out_f16, "sr_alpha_cat: null pointer");
+    R3DP_REQUIRE(N > 0 && H > 0 && W > 0 && Ca % 8 == 0 && Cb % 8 == 0 && stride_a >= Ca && stride_b >= Cb && stride_a % 8 == 0 && stride_b % 8 == 0,
+                 "sr_alpha_cat: bad shape");
+    const long long npix = (long long)N * H * W, total = npix * ((Ca + Cb) / 8);
+    alpha_cat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(xa_f16), Ca, stride_a,
+        reinterpret_cast<const __half*>(xb_f16), Cb, stride_b, alpha, npix, reinterpret_cast<__half*>(out_f16));
+    R3DP_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+// out = a * alpha + b * (1 - alpha), fp32 NCHW [N,C,H,W] with alpha [N,1,H,W]  (sr_with_ref.py:110,132)
+__global__ void blend_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ alpha, int C, long long hw,
+                             long long total, float* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long long n = idx / (C * hw), p = idx % hw;
+    const float al = alpha[n * hw + p];
+    out[idx] = a[idx] * al + b[idx] * (1.0f - al);
+}
+extern "C" int r3dp_sr_blend(const float* a, const float* b, const float* alpha, int N, int C, int H, int W, float* out, r3dp_stream_t stream) {
+    R3DP_REQUIRE(a && b && alpha && out && N > 0 && C > 0 && H > 0 && W > 0, "sr_blend: bad arguments");
+    const long long hw = (long long)H * W, total = (long long)N * C * hw;
+    blend_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(a, b, alpha, C, hw, total, out);
+    R3DP_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+// person_occlusion = clamp(torso_occlusion + (w > threshold ? 1 : w), 0, 1)   (sr_with_ref.py:126-131)
+__global__ void person_occlusion_kernel(const float* __restrict__ w, const float* __restrict__ torso, float thr, long long total, float* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const float h = w[idx] > thr ? 1.0f : w[idx];
+    out[idx] = fminf(fmaxf(torso[idx] + h, 0.f), 1.f);
+}
+extern "C" int r3dp_sr_person_occlusion(const float* head_alpha, const float* torso_occlusion, float threshold, int N, int H, int W, float* out,
+                                        r3dp_stream_t stream) {
+    R3DP_REQUIRE(head_alpha && torso_occlusion && out && N > 0 && H > 0 && W > 0, "sr_person_occlusion: bad arguments");
+    const long long total = (long long)N * H * W;
+    person_occlusion_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(head_alpha, torso_occlusion, threshold, total, out);
+    R3DP_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+// F.interpolate(scale 1/2, bilinear, align_corners=False, antialias=True) (sr_with_ref.py:79-82): separable triangle filter of support 2,
+// taps [1,3,3,1]/8 in the interior, clipped and renormalised at the borders ([3,3,1]/7, [1,3,3]/7).  x [N*C][2h][2w] -> y [N*C][h][w], fp32.
+__global__ void aa_down2_kernel(const float* __restrict__ x, int NC, int h, int w, float* __restrict__ y) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)NC * h * w) return;
+    const int ox = (int)(idx % w), oy = (int)((idx / w) % h); const long long nc = idx / ((long long)w * h);
+    const int H2 = 2 * h, W2 = 2 * w;
+    const float* p = x + nc * H2 * W2;
+    const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+    float wy[4], wx[4], sy = 0.f, sx = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int yy = 2 * oy - 1 + t, xx = 2 * ox - 1 + t;
+        wy[t] = (yy >= 0 && yy < H2) ? k4[t] : 0.f; wx[t] = (xx >= 0 && xx < W2) ? k4[t] : 0.f;
+        sy += wy[t]; sx += wx[t];
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if (wy[u] == 0.f) continue;
+        const int yy = 2 * oy - 1 + u;
+        float row = 0.f;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { if (wx[v] != 0.f) row = fmaf(wx[v] / sx, p[(size_t)yy * W2 + 2 * ox - 1 + v], row); }
+        acc = fmaf(wy[u] / sy, row, acc);
+    }
+    y[idx] = acc;
+}
+extern "C" int r3dp_sr_resize_aa_down2(const float* x, int N, int C, int h_out, int w_out, float* y, r3dp_stream_t stream) {
+    R3DP_REQUIRE(x && y && N > 0 && C > 0 && h_out > 0 && w_out > 0, "sr_resize_aa_down2: bad arguments");
+    const long long total = (long long)N * C * h_out * w_out;
+    aa_down2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, N * C, h_out, w_out, y);
+    R3DP_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
 }

@@ -107,3 +107,68 @@ RENDERING_OPTIONS = {
     'depth_resolution_importance': 0, 'disparity_space_sampling': False, 'clamp_mode': 'softplus',
     'white_back': False,
 }
+
+
+# ---- torso head (config 5) ------------------------------------------------------------------------------------------------------
+class StubTorsoModel(torch.nn.Module):
+    """Parameter-free stand-in for the reference's WarpBasedTorsoModelMediaPipe (modules/real3d/facev2v_warp/model2.py:199-336) with the
+    same forward signature and the two outputs the SR head consumes.  The real torso warper is an opaque PyTorch child of
+    SuperresolutionHybrid8XDC_Warp (out of scope); parity of the head is tested with THIS module plugged into
+    both the reference and our implementation."""
+
+    def forward(self, torso_src_img, segmap, kp_s, kp_d, tgt_head_img, tgt_head_weights, cal_loss=False, target_torso_mask=None):
+        rgb_torso = (0.6 * torso_src_img + 0.4 * tgt_head_img.flip(-1)).clamp(-1, 1)
+        hid = 0.5 * torch.cat([torso_src_img.repeat(1, 21, 1, 1), tgt_head_weights], dim=1)            # [N,64,256,256]
+        seg = torch.nn.functional.avg_pool2d(segmap[:, 2:3].float(), 2)                                # [N,1,256,256]
+        occ = torch.sigmoid(6.0 * seg - 3.0 + 0.1 * (kp_d[:, :1, :1] - kp_s[:, :1, :1]).unsqueeze(-1))
+        return rgb_torso, {'deformed_torso_hid': hid, 'occlusion_2': occ}
+
+
+def make_sr_warp_params(seed: int = 6) -> Dict[str, torch.Tensor]:
+    """state_dict of SuperresolutionHybrid8XDC_Warp WITHOUT its torso_model child (sr_with_ref.py:16-66, fuse mode v2)."""
+    p = make_sr_params(seed=seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    f = p['block0.resample_filter']
+
+    def conv(name, o, i, k):
+        p[name + '.weight'] = torch.randn(o, i, k, k, generator=g) / math.sqrt(i * k * k)
+        p[name + '.bias'] = 0.1 * torch.randn(o, generator=g)
+
+    conv('torso_encoder.0', 256, 64, 1)
+    conv('bg_encoder.0', 64, 3, 3); conv('bg_encoder.2', 256, 64, 3); conv('bg_encoder.4', 256, 256, 3)
+    conv('head_torso_alpha_predictor.0', 32, 7, 3); conv('head_torso_alpha_predictor.2', 32, 32, 3); conv('head_torso_alpha_predictor.4', 1, 32, 3)
+    conv('fuse_head_torso_convs.0', 256, 512, 3); conv('fuse_head_torso_convs.2', 256, 256, 3)
+    conv('fuse_fg_bg_convs.0', 64, 512, 1); conv('fuse_fg_bg_convs.2', 256, 64, 3); conv('fuse_fg_bg_convs.4', 256, 256, 3)
+    blk = 'head_torso_block'
+    p[f'{blk}.resample_filter'] = f.clone()
+    for name in ('conv0', 'conv1'):
+        pre = f'{blk}.{name}.'
+        p[pre + 'weight'] = torch.randn(256, 256, 3, 3, generator=g)
+        p[pre + 'bias'] = 0.1 * torch.randn(256, generator=g)
+        p[pre + 'affine.weight'] = torch.randn(256, 512, generator=g)
+        p[pre + 'affine.bias'] = 1.0 + 0.1 * torch.randn(256, generator=g)
+        p[pre + 'noise_strength'] = torch.zeros([])
+        p[pre + 'noise_const'] = torch.randn(256, 256, generator=g)
+        p[pre + 'resample_filter'] = f.clone()
+    pre = f'{blk}.torgb.'
+    p[pre + 'weight'] = torch.randn(3, 256, 1, 1, generator=g)
+    p[pre + 'bias'] = 0.1 * torch.randn(3, generator=g)
+    p[pre + 'affine.weight'] = torch.randn(256, 512, generator=g)
+    p[pre + 'affine.bias'] = 1.0 + 0.1 * torch.randn(256, generator=g)
+    return p
+
+
+def make_warp_inputs(n: int, seed: int = 7) -> Dict[str, torch.Tensor]:
+    """ref_torso / ref_bg / segmap / key points of SURVEY.md §8d (config 5)."""
+    g = torch.Generator().manual_seed(seed)
+    return {
+        'ref_torso_rgb': torch.randn(n, 3, 512, 512, generator=g).clamp(-1, 1),
+        'ref_bg_rgb': torch.randn(n, 3, 512, 512, generator=g).clamp(-1, 1),
+        'segmap': torch.rand(n, 6, 512, 512, generator=g),
+        'kp_s': torch.rand(n, 68, 3, generator=g) * 2 - 1,
+        'kp_d': torch.rand(n, 68, 3, generator=g) * 2 - 1,
+    }
+
+
+WARP_HPARAMS = {'torso_model_version': 'v2', 'htbsr_head_weight_fuse_mode': 'v2', 'htbsr_head_threshold': 0.9, 'torso_kp_num': 4,
+                'torso_inp_mode': 'rgb_alpha', 'weight_fuse': True}

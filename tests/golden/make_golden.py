@@ -163,8 +163,37 @@ def layer_cases():
     save('sr_layers', **out)
 
 
+def warp_case():
+    """BASELINE config 5's SR head (SuperresolutionHybrid8XDC_Warp, fuse mode v2) at N=1 with the reference class; its torso_model child is
+    replaced by synthetic.StubTorsoModel (the real warper is an opaque child outside the hot path)."""
+    import types
+    sys.modules.setdefault('imageio', types.ModuleType('imageio'))
+    hparams.update(syn.WARP_HPARAMS)
+    from modules.real3d.super_resolution.sr_with_ref import SuperresolutionHybrid8XDC_Warp
+    m = SuperresolutionHybrid8XDC_Warp(channels=32, img_resolution=512, sr_num_fp16_res=0, sr_antialias=True, channel_base=32768,
+                                       channel_max=512, fused_modconv_default='inference_only').eval()
+    m.torso_model = syn.StubTorsoModel()
+    res = m.load_state_dict(syn.make_sr_warp_params(seed=6), strict=True)
+    g = load('render_full48')
+    feat = torch.from_numpy(g['rgb'])
+    fimg = feat.permute(0, 2, 1).reshape(1, 32, 64, 64).contiguous()
+    wimg = torch.from_numpy(g['wsum']).permute(0, 2, 1).reshape(1, 1, 64, 64).contiguous()
+    inp = syn.make_warp_inputs(1, seed=7)
+    img, ret = m(fimg[:, :3], fimg, torch.ones(1, 14, 512), inp['ref_torso_rgb'], inp['ref_bg_rgb'], wimg, inp['segmap'], inp['kp_s'], inp['kp_d'],
+                 noise_mode='none')
+    save('sr_warp_full', image=img, seeds=np.array([6, 7]))
+
+
+def load(name):
+    return np.load(os.path.join(HERE, name + '.npz'))
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'warp':
+        warp_case()
+        sys.exit(0)
     small_cases()
     layer_cases()
     full_cases()
+    warp_case()

@@ -58,3 +58,16 @@ def test_synthetic_cameras_hit_the_box():
     o, d = orc.gen_rays(c2w, K, 64)
     _, _, valid = orc.auto_limits(o, d, 1.0)
     assert bool(valid.all())
+
+
+def test_torso_head_state_dict_layout():
+    """SuperresolutionHybrid8XDC_Warp (minus the caller-supplied torso_model child) has the reference's keys: the REFERENCE class accepted
+    exactly this dict with strict=True in tests/golden/make_golden.py::warp_case."""
+    m = r3.SuperresolutionHybrid8XDC_Warp(channels=32, img_resolution=512, sr_num_fp16_res=0, sr_antialias=True, hp=syn.WARP_HPARAMS)
+    want = set(syn.make_sr_warp_params())
+    assert set(m.state_dict().keys()) == want, set(m.state_dict().keys()) ^ want
+    m.load_state_dict(syn.make_sr_warp_params(), strict=True)
+    assert sum(p.numel() for p in m.parameters()) == 6532912          # probe of the reference class (without torso_model)
+    with pytest.raises(NotImplementedError):
+        r3.SuperresolutionHybrid8XDC_Warp(channels=32, img_resolution=512, sr_num_fp16_res=0, sr_antialias=True,
+                                          hp=dict(syn.WARP_HPARAMS, htbsr_head_weight_fuse_mode='v3'))

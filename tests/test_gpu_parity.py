@@ -247,3 +247,28 @@ def test_tc_up_layer_composed_weights_vs_oracle():
     got, ref = _tc_layer_case(2, 32, 256, 6, 128, composed=True)
     err = _maxdiff(got, ref)
     assert err < 2e-3 * float(ref.abs().max()), (err, float(ref.abs().max()))
+
+
+def test_torso_head_vs_reference(golden):
+    """BASELINE config 5's SR head (SuperresolutionHybrid8XDC_Warp, fuse mode v2) at N=1: tensor-core path vs the REFERENCE class's fp32 image
+    (both with synthetic.StubTorsoModel as the torso child).  Tolerance as for the plain SR: max-abs < 2e-2, PSNR > 60 dB."""
+    g = golden('render_full48')
+    fimg, wimg = orc.feature_image(g['rgb'], 64).to(DEV), orc.feature_image(g['wsum'], 64).to(DEV)
+    inp = {k: v.to(DEV) for k, v in syn.make_warp_inputs(1, seed=7).items()}
+    m = r3.SuperresolutionHybrid8XDC_Warp(channels=32, img_resolution=512, sr_num_fp16_res=0, sr_antialias=True, hp=syn.WARP_HPARAMS,
+                                          torso_model=syn.StubTorsoModel())
+    m.load_state_dict(syn.make_sr_warp_params(seed=6), strict=True)
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        img, ret = m(fimg[:, :3].contiguous(), fimg, torch.ones(1, 14, 512, device=DEV), inp['ref_torso_rgb'], inp['ref_bg_rgb'], wimg, inp['segmap'],
+                     inp['kp_s'], inp['kp_d'], noise_mode='none')
+    ref = golden('sr_warp_full')['image']
+    assert 'occlusion_2' in ret and img.shape == (1, 3, 512, 512)
+    err = _maxdiff(img, ref)
+    mse = float(((img.cpu() - ref) ** 2).mean())
+    psnr = 10 * torch.log10(torch.tensor(float(ref.max() - ref.min()) ** 2 / mse)).item()
+    print(f'torso head (tc): max-abs {err:.3e} on range [{float(ref.min()):.2f},{float(ref.max()):.2f}], PSNR {psnr:.1f} dB')
+    assert err < 2e-2 and psnr > 60.0, (err, psnr)
+    # the antialiased 1/2 resize kernel alone, exact
+    lib = torch.nn.functional.interpolate(inp['ref_bg_rgb'].cpu(), size=(256, 256), mode='bilinear', align_corners=False, antialias=True)
+    assert _maxdiff(m._aa_down2(inp['ref_bg_rgb']), lib) < 1e-5

@@ -71,3 +71,18 @@ def test_sr_full(golden):
     img = orc.superres(fimg[:, :3], fimg, torch.ones(1, 14, 512), syn.make_sr_params(seed=5))
     ref = golden('sr_full')['image']
     assert _maxdiff(img, ref) < 2e-4 * float(ref.abs().max())
+
+
+def test_sr_warp_full(golden):
+    """Torso head (SuperresolutionHybrid8XDC_Warp, fuse mode v2) at N=1 vs the reference class run with the stub torso model."""
+    g = golden('render_full48')
+    fimg = orc.feature_image(g['rgb'], 64)
+    wimg = orc.feature_image(g['wsum'], 64)
+    inp = syn.make_warp_inputs(1, seed=7)
+    # the antialiased 1/2 resize restated == the library op the reference calls
+    lib = torch.nn.functional.interpolate(inp['ref_bg_rgb'], size=(256, 256), mode='bilinear', align_corners=False, antialias=True)
+    assert _maxdiff(orc.aa_down2(inp['ref_bg_rgb']), lib) < 1e-5
+    img, _ = orc.superres_warp(fimg[:, :3], fimg, torch.ones(1, 14, 512), inp['ref_torso_rgb'], inp['ref_bg_rgb'], wimg, inp['segmap'],
+                               inp['kp_s'], inp['kp_d'], syn.make_sr_warp_params(seed=6), syn.StubTorsoModel())
+    ref = golden('sr_warp_full')['image']
+    assert _maxdiff(img, ref) < 2e-4 * float(ref.abs().max())

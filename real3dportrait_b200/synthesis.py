@@ -11,6 +11,7 @@ from .decoder import OSGDecoder
 from .ray_sampler import RaySampler
 from .renderer import ImportanceRenderer
 from .superresolution import SuperresolutionHybrid8XDC
+from .sr_with_ref import SuperresolutionHybrid8XDC_Warp
 
 DEFAULT_HPARAMS = {
     'neural_rendering_resolution': 64, 'w_dim': 512, 'final_resolution': 512, 'triplane_hid_dim': 32,
@@ -23,16 +24,22 @@ class RenderHead(torch.nn.Module):
     """Child module names (`decoder`, `superresolution`, `renderer`, `ray_sampler`) match the reference model, so the
     corresponding slices of a released checkpoint load unchanged."""
 
-    def __init__(self, hp: Optional[dict] = None, sr_mode: str = 'fp32'):
+    def __init__(self, hp: Optional[dict] = None, sr_mode: str = 'fp32', torso_model: Optional[torch.nn.Module] = None):
+        """torso_model given (or hp['torso'] true) -> the OSAvatarSECC_Img2plane_Torso head (secc_img2plane_torso.py:7-18): the SR module is
+        SuperresolutionHybrid8XDC_Warp and synthesis() needs `cond` with ref_torso_img, bg_img, segmap, kp_s, kp_d."""
         super().__init__()
         self.hparams = dict(DEFAULT_HPARAMS, **(hp or {}))
         hp = self.hparams
+        self.torso = torso_model is not None or bool(hp.get('torso', False))
         self.neural_rendering_resolution = hp['neural_rendering_resolution']
         c = hp['triplane_hid_dim']
         self.decoder = OSGDecoder(c, {'decoder_lr_mul': 1, 'decoder_output_dim': c})
-        self.superresolution = SuperresolutionHybrid8XDC(channels=c, img_resolution=hp['final_resolution'], sr_num_fp16_res=0,
-                                                         sr_antialias=True, sr_mode=sr_mode, channel_base=hp['base_channel'],
-                                                         channel_max=hp['max_channel'], fused_modconv_default='inference_only')
+        sr_kwargs = dict(channels=c, img_resolution=hp['final_resolution'], sr_num_fp16_res=0, sr_antialias=True, channel_base=hp['base_channel'],
+                         channel_max=hp['max_channel'], fused_modconv_default='inference_only')
+        if self.torso:
+            self.superresolution = SuperresolutionHybrid8XDC_Warp(hp=hp, torso_model=torso_model, sr_mode='tc', **sr_kwargs)
+        else:
+            self.superresolution = SuperresolutionHybrid8XDC(sr_mode=sr_mode, **sr_kwargs)
         self.renderer = ImportanceRenderer(hp=hp)
         self.ray_sampler = RaySampler()
         self.rendering_kwargs = {
@@ -43,7 +50,7 @@ class RenderHead(torch.nn.Module):
         }
 
     @torch.no_grad()
-    def synthesis(self, planes, camera: torch.Tensor, ret: Optional[Dict] = None, **render_overrides) -> Dict[str, torch.Tensor]:
+    def synthesis(self, planes, camera: torch.Tensor, ret: Optional[Dict] = None, cond: Optional[Dict] = None, **render_overrides) -> Dict[str, torch.Tensor]:
         """planes [N,3,C,H,W], camera [N,25] -> ret dict with the reference's keys (secc_img2plane.py:134-136)."""
         if ret is None:
             ret = {}
@@ -64,8 +71,13 @@ class RenderHead(torch.nn.Module):
         rgb_image = feature_image[:, :3]
         ret['weights_img'] = weights_image
         ones_ws = torch.ones(N, 14, self.hparams['w_dim'], device=feature_image.device)
-        extra = {'x_nhwc': feat.view(N, res, res, feat.shape[-1])} if self.superresolution.sr_mode == 'tc' else {}
-        sr_image = self.superresolution(rgb_image, feature_image, ones_ws, noise_mode='none', **extra)
+        if self.torso:                                               # secc_img2plane_torso.py:13-18
+            sr_image, facev2v_ret = self.superresolution(rgb_image, feature_image, ones_ws, cond['ref_torso_img'], cond['bg_img'], weights_image,
+                                                         cond['segmap'], cond['kp_s'], cond['kp_d'], cond.get('target_torso_mask'), noise_mode='none')
+            ret.update(facev2v_ret)
+        else:
+            extra = {'x_nhwc': feat.view(N, res, res, feat.shape[-1])} if self.superresolution.sr_mode == 'tc' else {}
+            sr_image = self.superresolution(rgb_image, feature_image, ones_ws, noise_mode='none', **extra)
         ret.update({'image_raw': rgb_image.clamp(-1, 1), 'image_depth': depth_image, 'image': sr_image.clamp(-1, 1),
                     'image_feature': feature_image[:, 3:], 'plane': planes, 'is_ray_valid': valid})
         return ret

@@ -272,3 +272,30 @@ def test_torso_head_vs_reference(golden):
     # the antialiased 1/2 resize kernel alone, exact
     lib = torch.nn.functional.interpolate(inp['ref_bg_rgb'].cpu(), size=(256, 256), mode='bilinear', align_corners=False, antialias=True)
     assert _maxdiff(m._aa_down2(inp['ref_bg_rgb']), lib) < 1e-5
+
+
+def test_torso_render_head_config5_vs_oracle():
+    """Config 5 path for one frame: 48+48 importance render -> torso SR head, whole head vs the oracle (stub torso child on both sides)."""
+    N = 1
+    planes, cam = syn.make_planes(N, seed=40), syn.make_cameras(N, seed=41)
+    u_c, u_f = syn.make_jitter(N, 4096, 48, 48, seed=42)
+    mlp, srp = syn.make_decoder_params(seed=4), syn.make_sr_warp_params(seed=6)
+    inp = syn.make_warp_inputs(N, seed=43)
+    c2w, K = syn.split_camera(cam)
+    o, d = orc.gen_rays(c2w, K, 64)
+    feat, depth, wsum, _ = orc.render(planes, mlp, o, d, S=48, S_imp=48, u_coarse=u_c, u_fine=u_f, lib=True)
+    fimg, wimg = orc.feature_image(feat, 64), orc.feature_image(wsum, 64)
+    ref, _ = orc.superres_warp(fimg[:, :3], fimg, torch.ones(N, 14, 512), inp['ref_torso_rgb'], inp['ref_bg_rgb'], wimg, inp['segmap'], inp['kp_s'],
+                               inp['kp_d'], srp, syn.StubTorsoModel())
+    head = r3.RenderHead(hp=dict(syn.WARP_HPARAMS, num_samples_fine=48), torso_model=syn.StubTorsoModel())
+    sd = {'decoder.' + k: v for k, v in mlp.items()}
+    sd.update({'superresolution.' + k: v for k, v in srp.items()})
+    head.load_state_dict(sd, strict=True)
+    head = head.to(DEV).eval()
+    cond = {'ref_torso_img': inp['ref_torso_rgb'].to(DEV), 'bg_img': inp['ref_bg_rgb'].to(DEV), 'segmap': inp['segmap'].to(DEV),
+            'kp_s': inp['kp_s'].to(DEV), 'kp_d': inp['kp_d'].to(DEV)}
+    out = head.synthesis(planes.to(DEV), cam.to(DEV), cond=cond, u_coarse=u_c.to(DEV), u_fine=u_f.to(DEV))
+    assert _maxdiff(out['image_raw'], fimg[:, :3].clamp(-1, 1)) < RGB_TOL
+    assert 'occlusion_2' in out
+    err = _maxdiff(out['image'], ref.clamp(-1, 1))
+    assert err < 2e-2, err

@@ -207,7 +207,6 @@ def main():
     launches = L.r3dp_launch_count() - launches0
     if eng.graph is not None:                       # kernels replayed from the captured graph are not re-counted by the library
         launches += eng.launches_per_step * args.steps
-    clocks = sampler.summary()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -237,6 +236,7 @@ def main():
     e1.record()
     barrier()
     e2e_wall_ms = (time.perf_counter() - t_host0) * 1e3
+    clocks = sampler.summary()                    # sampled from the start of the timed region to the end of the e2e region (GPU busy throughout)
     te = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

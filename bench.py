@@ -249,8 +249,16 @@ def main():
             dist.destroy_process_group()
         return
     pk = peaks()
+    # dominant kernel = the tensor-core conv (4 launches/step); its time is measured by CUDA-event pairs around every launch (library hook),
+    # falling back to the whole SR-conv stage for the fp32 path
+    if prof.get('conv_kernel_ms'):
+        k_ms_per_step, k_launches = prof['conv_kernel_ms'] / args.steps, prof['conv_launches'] / args.steps
+    else:
+        k_ms_per_step, k_launches = prof['sr_conv_ms'] / args.steps, None
     sr_ms_per_step = prof['sr_conv_ms'] / args.steps
-    sr_tflops = SR_GFLOP_PER_FRAME * B / sr_ms_per_step                  # GFLOP / ms == TFLOP/s
+    sr_tflops = SR_GFLOP_PER_FRAME * B / k_ms_per_step                   # GFLOP / ms == TFLOP/s  (algorithmic: the reference's 197.63 GFLOP/frame)
+    # dram__bytes_read+write of the 4 conv launches of one step from the committed ncu --set full capture (profiles/r1_ncu_full_summaries_2.md), N = 4
+    NCU_TRAFFIC_PER_STEP = (9.1 + 80.8) + (136.4 + 90.9) + (144.3 + 215.7) + (272.0 + 12.4)          # MB
     line = {
         'metric': 'rendered frames/sec @512^2 (64^2 NeRF, 48 samples/ray)', 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -262,9 +270,12 @@ def main():
         'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': ksteps,
                 'host_wall_ms': e2e_wall_ms, 'note': 'step_host(): pinned host in/out, copies of step i+1 overlap compute of step i'},
         'roofline': {'bound': 'tensor', 'achieved': sr_tflops, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
-                     'frac': sr_tflops / pk['tf_sustained'], 'traffic': None, 'kernel': prof['sr_kernel'],
+                     'frac': sr_tflops / pk['tf_sustained'],
+                     'traffic': (NCU_TRAFFIC_PER_STEP * 1e6 / 4 if (sr_mode == 'tc' and B == 4) else None),
+                     'traffic_note': 'bytes per launch: dram read+write averaged over the 4 conv launches of a step (ncu --set full)',
+                     'kernel': prof['sr_kernel'], 'launches_per_step': k_launches, 'kernel_ms_per_step': k_ms_per_step,
                      'peak_source': pk['src'] + ' bf16 sustained', 'algorithmic': f'{SR_GFLOP_PER_FRAME} GFLOP/frame x {B} frames/step',
-                     'share_of_step': sr_ms_per_step / (prof['total_ms'] / args.steps)},
+                     'share_of_step': k_ms_per_step / (prof['total_ms'] / args.steps), 'sr_stage_ms_per_step': sr_ms_per_step},
         'stage_ms_per_step': {k: v / args.steps for k, v in prof['stages'].items()},
     }
     if not args.no_cpu_baseline:

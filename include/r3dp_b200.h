@@ -174,6 +174,10 @@ int r3dp_sr_tc_input_nhwc(const float* x_nhwc, int N, int C, int h, int w, int s
 int r3dp_sr_tc_last_layer(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
                           const float* img_prev, int N, int Nw, int I, int H, int W, float* img_out, r3dp_stream_t stream);
 
+/* Measurement hooks (bench.py): time every tensor-core conv launch with a CUDA-event pair on its launching stream. */
+int r3dp_sr_tc_prof(int enable);
+int r3dp_sr_tc_prof_read(float* total_ms, int* launches);
+
 /* ------------------------------------------------------- torso head: SuperresolutionHybrid8XDC_Warp building blocks ---
  * (modules/real3d/super_resolution/sr_with_ref.py:16-162; the torso warper itself stays the caller's PyTorch module)
  * r3dp_sr_tc_conv              nn.Conv2d k=1|3, stride 1, same padding (+bias) [+ act: 0 linear, 1 lrelu(0.2)*sqrt2, 2 nn.LeakyReLU 0.01]

@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <mutex>
+#include <vector>
 #include <stdlib.h>
 
 namespace r3dp {
@@ -1161,6 +1162,15 @@ static int launch_conv(const void* x, int N, int H, int W, int Cp, const void* w
 }
 
 
+// ---- optional in-library timing of the conv launches (bench.py's roofline): CUDA events on the launching stream around each launch --------
+struct ConvProf { bool on = false; std::vector<cudaEvent_t> ev; size_t used = 0; };
+static ConvProf g_prof;
+static void prof_mark(cudaStream_t st) {
+    if (!g_prof.on) return;
+    if (g_prof.used == g_prof.ev.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; g_prof.ev.push_back(e); }
+    cudaEventRecord(g_prof.ev[g_prof.used++], st);
+}
+
 static int tc_version() {                      // R3DP_TC_KERNEL=1: simple v1 kernel; 2: single-CTA persistent v2; 3 (default): CTA pairs
     static int v = -1;
     if (v < 0) { const char* e = getenv("R3DP_TC_KERNEL"); v = (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 3); }
@@ -1192,7 +1202,9 @@ static int launch_conv3_r(const CUtensorMap& tmA, const CUtensorMap& tmB, Conv2A
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    prof_mark(st);
     R3DP_CUDA(cudaLaunchKernelEx(&cfg, conv_tc3_kernel<R>, tmA, tmB, a));
+    prof_mark(st);
     count_launches(1);
     return 0;
 }
@@ -1208,7 +1220,9 @@ static int launch_conv2_r(const CUtensorMap& tmA, const CUtensorMap& tmB, Conv2A
     a.row_groups = (max_rows + R - 1) / R;
     a.total_units = a.n_images * a.n_phases * a.row_groups * a.tiles_x;
     const int grid = a.total_units < sm_count() ? a.total_units : sm_count();
+    prof_mark(st);
     conv_tc2_kernel<R><<<grid, kThreads, C::SMEM, st>>>(tmA, tmB, a);
+    prof_mark(st);
     R3DP_LAUNCH_CHECK();
     count_launches(1);
     return 0;
@@ -1674,5 +1688,21 @@ extern "C" int r3dp_sr_resize_aa_down2(const float* x, int N, int C, int h_out, 
     aa_down2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, N * C, h_out, w_out, y);
     R3DP_LAUNCH_CHECK();
     count_launches(1);
+    return 0;
+}
+
+// Timing of the tensor-core conv launches: r3dp_sr_tc_prof(1) starts recording a CUDA-event pair around every conv_tc2/3 launch,
+// r3dp_sr_tc_prof(0) stops; r3dp_sr_tc_prof_read synchronises the recorded events and returns their summed duration and count.
+extern "C" int r3dp_sr_tc_prof(int enable) { g_prof.on = enable != 0; if (enable) g_prof.used = 0; return 0; }
+extern "C" int r3dp_sr_tc_prof_read(float* total_ms, int* launches) {
+    float sum = 0.f;
+    for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+        R3DP_CUDA(cudaEventSynchronize(g_prof.ev[i + 1]));
+        float ms = 0.f;
+        R3DP_CUDA(cudaEventElapsedTime(&ms, g_prof.ev[i], g_prof.ev[i + 1]));
+        sum += ms;
+    }
+    if (total_ms) *total_ms = sum;
+    if (launches) *launches = (int)(g_prof.used / 2);
     return 0;
 }

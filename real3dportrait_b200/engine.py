@@ -156,6 +156,10 @@ class FrameEngine:
         self.step(*inputs(first))                                   # eager warm-up: one-time lazy initialisations stay out of the stage times
         torch.cuda.synchronize()
         capi.PROF = capi.Profiler()
+        L = capi.lib()
+        tc = self.head.superresolution.sr_mode == 'tc'
+        if tc:
+            L.r3dp_sr_tc_prof(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for i in range(steps):
@@ -164,5 +168,13 @@ class FrameEngine:
         torch.cuda.synchronize()
         stages = capi.PROF.totals()
         capi.PROF = None
-        kernel = 'conv_tc3_kernel<2> (tcgen05 cta_group::2 implicit-GEMM conv; stage also holds the FIR + edge kernels of block1.conv0)' if self.head.superresolution.sr_mode == 'tc' else 'conv_taps_kernel (fp32 CUDA-core direct conv)'
-        return {'stages': stages, 'sr_conv_ms': stages.get('sr_conv', float('nan')), 'total_ms': a.elapsed_time(b), 'sr_kernel': kernel}
+        conv_ms, conv_n = None, 0
+        if tc:
+            import ctypes as C
+            ms, n = C.c_float(0), C.c_int(0)
+            capi.check(L.r3dp_sr_tc_prof_read(C.byref(ms), C.byref(n)))
+            L.r3dp_sr_tc_prof(0)
+            conv_ms, conv_n = float(ms.value), int(n.value)
+        kernel = 'conv_tc3_kernel<2> (tcgen05 cta_group::2 implicit-GEMM conv)' if self.head.superresolution.sr_mode == 'tc' else 'conv_taps_kernel (fp32 CUDA-core direct conv)'
+        return {'stages': stages, 'sr_conv_ms': stages.get('sr_conv', float('nan')), 'total_ms': a.elapsed_time(b), 'sr_kernel': kernel,
+                'conv_kernel_ms': conv_ms, 'conv_launches': conv_n}

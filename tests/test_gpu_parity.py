@@ -299,3 +299,36 @@ def test_torso_render_head_config5_vs_oracle():
     assert 'occlusion_2' in out
     err = _maxdiff(out['image'], ref.clamp(-1, 1))
     assert err < 2e-2, err
+
+
+@pytest.mark.parametrize('N,M,S,S_imp,H,W', [(3, 100, 7, 0, 20, 36), (2, 37, 24, 9, 48, 16), (1, 5, 130, 0, 8, 8), (2, 64, 48, 48, 32, 32)])
+def test_render_ragged_shapes_vs_oracle(N, M, S, S_imp, H, W):
+    """Edge shapes the reference accepts: ray counts that are not an image, non-square planes, odd sample counts, importance pass with
+    S_imp != S, rays that miss the box (random directions)."""
+    g = torch.Generator().manual_seed(N * 1000 + M)
+    planes = torch.randn(N, 3, 32, H, W, generator=g)
+    o = torch.tensor([0.0, 0.0, 1.6]).expand(N, M, 3).contiguous() + 0.05 * torch.randn(N, M, 3, generator=g)
+    d = torch.nn.functional.normalize(torch.tensor([0.0, 0.0, -1.0]) + 0.45 * torch.randn(N, M, 3, generator=g), dim=-1)
+    u_c = torch.rand(N, M, S, 1, generator=g)
+    u_f = torch.rand(N * M, S_imp, generator=g) if S_imp else None
+    mlp = syn.make_decoder_params(seed=4)
+    ref = orc.render(planes, mlp, o, d, S=S, S_imp=S_imp, u_coarse=u_c, u_fine=u_f)
+    out = r3.ImportanceRenderer()(planes.to(DEV), _decoder(mlp), o.to(DEV), d.to(DEV), _opts(S, S_imp, False, u_c, u_f))
+    assert torch.equal(out[3].cpu(), ref[3])
+    assert 0 < int(ref[3].sum()) <= ref[3].numel()
+    assert _maxdiff(out[0], ref[0]) < RGB_TOL and _maxdiff(out[2], ref[2]) < RGB_TOL and _maxdiff(out[1], ref[1]) < 1e-3
+
+
+def test_sample_far_and_degenerate_points():
+    """Points far outside the box sample zeros (zero padding); border points match the oracle; non-finite / huge coordinates give finite zeros
+    for the planes they index (our documented behaviour; the reference's grid_sample is undefined there)."""
+    planes = syn.make_planes(1, h=16, w=16, seed=3).to(DEV)
+    pts = torch.tensor([[[0.0, 0.0, 0.0], [5.0, -7.0, 0.3], [0.4999, -0.4999, 0.5], [-0.53, 0.2, 0.49]]])
+    ref = orc.sample_planes(planes.cpu(), pts, 1.0)
+    got = r3.sample_from_planes(None, planes, pts.to(DEV), box_warp=1.0)
+    assert _maxdiff(got, ref) < 1e-5
+    assert float(got[:, :, 1].abs().max()) == 0.0
+    bad = torch.tensor([[[float('nan'), 0.1, 0.2], [1e30, 0.0, 0.0], [float('inf'), 0.0, 0.0]]])
+    g2 = r3.sample_from_planes(None, planes, bad.to(DEV), box_warp=1.0)
+    assert bool(torch.isfinite(g2).all()) and float(g2[:, :, :, :].abs().max()) < 10.0
+    assert float(g2[:, 0].abs().max()) == 0.0 and float(g2[:, 2].abs().max()) == 0.0      # planes 0 (x,y) and 2 (z,x) use the bad x

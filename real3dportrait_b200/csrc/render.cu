@@ -14,7 +14,7 @@ __global__ void mlp_to_const_kernel(const r3dp_mlp_t m, MlpConst* dst) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
     const float g1 = 0.17677669529663687f, g2 = 0.125f;        // 1/sqrt(32), 1/sqrt(64)  (networks_stylegan2.py:113)
     for (int i = tid; i < kHidden * kC; i += nt) dst->w1[i] = m.w1[i] * g1;
-    for (int i = tid; i < kHidden * kOut; i += nt) { const int j = i / kOut, o = i - j * kOut; dst->w2[i] = m.w2[o * kHidden + j] * g2; }
+    for (int i = tid; i < kHidden * (kOut + 1); i += nt) { const int j = i / (kOut + 1), o = i - j * (kOut + 1); dst->w2[i] = o < kOut ? m.w2[o * kHidden + j] * g2 : 0.f; }
     for (int i = tid; i < kHidden; i += nt) dst->b1[i] = m.b1[i];
     for (int i = tid; i < kOut; i += nt) dst->b2[i] = m.b2[i];
 }

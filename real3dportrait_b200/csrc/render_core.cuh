@@ -109,7 +109,8 @@ __device__ __forceinline__ float4 bilinear_cl(const float* __restrict__ plane, i
     if (finite && oky0 && okx1) b = ldg_nc_f4(p00 + kC);
     if (finite && oky1 && okx0) c = ldg_nc_f4(p00 + (size_t)W * kC);
     if (finite && oky1 && okx1) d = ldg_nc_f4(p00 + (size_t)W * kC + kC);
-    const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+    // non-finite coordinates contribute nothing (their weights would be NaN)
+    const float w00 = finite ? wx0 * wy0 : 0.f, w10 = finite ? wx1 * wy0 : 0.f, w01 = finite ? wx0 * wy1 : 0.f, w11 = finite ? wx1 * wy1 : 0.f;
     float4 r;
     r.x = a.x * w00 + b.x * w10 + c.x * w01 + d.x * w11;
     r.y = a.y * w00 + b.y * w10 + c.y * w01 + d.y * w11;
@@ -214,22 +215,55 @@ __device__ __forceinline__ void decode_pair(const MlpSmem& w, float* __restrict_
 struct MlpConst {
     float w1[kHidden * kC];      // [j][c]   W1 * 1/sqrt(32)
     float b1[kHidden];
-    float w2[kHidden * kOut];    // [j][o]   (W2 * 1/sqrt(64))^T
+    float w2[kHidden * (kOut + 1)];   // [j][o]   (W2 * 1/sqrt(64))^T, rows padded to 34 floats (f32x2 pairs)
     float b2[kOut];
 };
 static __constant__ MlpConst c_mlp;      // one copy per translation unit; only render.cu uses it
 
+// packed 2 x fp32 FMA (sm_100 fma.rn.f32x2): (d0,d1) += (a0,a1) * (b0,b1); ptxas keeps the pairs in aligned register pairs
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
+#ifndef R3DP_MLP_FFMA2
+#define R3DP_MLP_FFMA2 1
+#endif
+
 __device__ __forceinline__ void decode_one_const(float* __restrict__ row) {
-    float x[kC], y[kOut];
+    float x[kC], y[kOut + 1];
 #pragma unroll
     for (int c = 0; c < kC; ++c) x[c] = row[c];
 #pragma unroll
     for (int o = 0; o < kOut; ++o) y[o] = c_mlp.b2[o];
-    // 16 rolled iterations x 4 hidden units: the body (~600 instructions) stays in the instruction cache (fully unrolled it is
-    // ~100 KB and ncu shows no_instruction stalls), and the four independent softplus chains overlap their MUFU latencies
+    y[kOut] = 0.f;
+    // 16 rolled iterations x 4 hidden units: the body stays in the instruction cache (fully unrolled it is ~100 KB and ncu shows
+    // no_instruction stalls), and the four independent softplus chains overlap their MUFU latencies.  With R3DP_MLP_FFMA2 the dot
+    // products run as packed f32x2 FMAs: even/odd-channel partial sums for layer 1, adjacent output pairs for layer 2.
 #pragma unroll 1
     for (int j0 = 0; j0 < kHidden; j0 += 4) {
         float h[4];
+#if R3DP_MLP_FFMA2
+        float he[4], ho[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { he[u] = c_mlp.b1[j0 + u]; ho[u] = 0.f; }
+#pragma unroll
+        for (int c = 0; c < kC; c += 2) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ffma2(he[u], ho[u], x[c], x[c + 1], c_mlp.w1[(j0 + u) * kC + c], c_mlp.w1[(j0 + u) * kC + c + 1]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h[u] = softplus_fast(he[u] + ho[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int o = 0; o < kOut + 1; o += 2)
+                ffma2(y[o], y[o + 1], h[u], h[u], c_mlp.w2[(j0 + u) * (kOut + 1) + o], c_mlp.w2[(j0 + u) * (kOut + 1) + o + 1]);
+        }
+#else
 #pragma unroll
         for (int u = 0; u < 4; ++u) h[u] = c_mlp.b1[j0 + u];
 #pragma unroll
@@ -242,8 +276,9 @@ __device__ __forceinline__ void decode_one_const(float* __restrict__ row) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
 #pragma unroll
-            for (int o = 0; o < kOut; ++o) y[o] = fmaf(h[u], c_mlp.w2[(j0 + u) * kOut + o], y[o]);
+            for (int o = 0; o < kOut; ++o) y[o] = fmaf(h[u], c_mlp.w2[(j0 + u) * (kOut + 1) + o], y[o]);
         }
+#endif
     }
     row[0] = y[0];
 #pragma unroll

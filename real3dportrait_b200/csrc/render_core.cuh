@@ -102,7 +102,7 @@ __device__ __forceinline__ float4 bilinear_cl(const float* __restrict__ plane, i
     const int x0 = (int)fminf(fmaxf(fx0, -2.0f), (float)W + 1.0f), y0 = (int)fminf(fmaxf(fy0, -2.0f), (float)H + 1.0f);
     const bool okx0 = (unsigned)x0 < (unsigned)W, okx1 = (unsigned)(x0 + 1) < (unsigned)W;
     const bool oky0 = (unsigned)y0 < (unsigned)H, oky1 = (unsigned)(y0 + 1) < (unsigned)H;
-    const bool finite = (px == px) && (py == py);
+    const bool finite = (fabsf(px) <= 3.0e38f) && (fabsf(py) <= 3.0e38f);    // false for NaN and +-inf
     const float* p00 = plane + ((size_t)y0 * W + x0) * kC + cq * 4;
     float4 a = make_float4(0, 0, 0, 0), b = a, c = a, d = a;
     if (finite && oky0 && okx0) a = ldg_nc_f4(p00);

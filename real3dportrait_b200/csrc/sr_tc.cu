@@ -734,17 +734,19 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                                 const uint64_t db = umma_desc_sw128(smem_u32(b_ring + bslot * B3_BYTES));
                                 const int sh = tp.shift[t];
                                 const uint32_t first = (uint32_t)(kc | t);
+                                uint64_t da[R];
 #pragma unroll
-                                for (int j = 0; j < R; ++j) {
-                                    const uint32_t sq = a_base + j + d;
-                                    const uint64_t da = umma_desc_sw128(smem_u32(a_ring + (sq % C::NA) * A2_SLOT) + 128 * sh);
-                                    if (elect_one()) {
+                                for (int j = 0; j < R; ++j) da[j] = umma_desc_sw128(smem_u32(a_ring + ((a_base + j + d) % C::NA) * A2_SLOT) + 128 * sh);
+                                if (elect_one()) {
+                                    // k-step outer, row inner: consecutive MMAs accumulate into DIFFERENT TMEM tiles
 #pragma unroll
-                                        for (int k = 0; k < BK / UMMA_K; ++k)
-                                            tc_mma_f16_2sm(acc0 + j * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc3, first | (uint32_t)k);
+                                    for (int k = 0; k < BK / UMMA_K; ++k) {
+#pragma unroll
+                                        for (int j = 0; j < R; ++j)
+                                            tc_mma_f16_2sm(acc0 + j * BN, da[j] + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc3, first | (uint32_t)k);
                                     }
+                                    tc_commit_2sm(&b_empty[bslot]);
                                 }
-                                if (elect_one()) tc_commit_2sm(&b_empty[bslot]);
                             }
                             __syncwarp();
                         }

@@ -956,6 +956,14 @@ __global__ void __launch_bounds__(256) upconv_edge_kernel(const __half* __restri
 constexpr int FIR_TW = 32, FIR_TH = 8, FIR_BW = FIR_TW + 3, FIR_BH = FIR_TH + 3;
 constexpr int FIR_BOX_BYTES = FIR_BW * FIR_BH * 128, FIR_SLOT = (FIR_BOX_BYTES + 1023) / 1024 * 1024;
 constexpr int FIR_SMEM = 2 * FIR_SLOT + 1024 + 64;
+// packed 2 x fp32 FMA (sm_100 fma.rn.f32x2): (d0,d1) += (a0,a1) * (b0,b1)
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 __global__ void __launch_bounds__(256) fir_tma_kernel(const __grid_constant__ CUtensorMap tmY, const float* __restrict__ bias, int N, int OH,
                                                       int OW, int C, __half* __restrict__ y) {
     extern __shared__ uint8_t smem_raw[];
@@ -1011,7 +1019,7 @@ __global__ void __launch_bounds__(256) fir_tma_kernel(const __grid_constant__ CU
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float2 f = __half22float2(h[j]);
-                    win[3][2 * j] = fmaf(k4[v], f.x, win[3][2 * j]); win[3][2 * j + 1] = fmaf(k4[v], f.y, win[3][2 * j + 1]);
+                    ffma2(win[3][2 * j], win[3][2 * j + 1], k4[v], k4[v], f.x, f.y);      // packed f32x2: the kernel is issue-bound
                 }
             }
             if (ry >= 3) {
@@ -1022,7 +1030,7 @@ __global__ void __launch_bounds__(256) fir_tma_kernel(const __grid_constant__ CU
                     for (int j = 0; j < 4; ++j) {
                         float a0 = b[2 * j], a1 = b[2 * j + 1];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) { a0 = fmaf(k4[u], win[u][2 * j], a0); a1 = fmaf(k4[u], win[u][2 * j + 1], a1); }
+                        for (int u = 0; u < 4; ++u) ffma2(a0, a1, k4[u], k4[u], win[u][2 * j], win[u][2 * j + 1]);
                         a0 = (a0 < 0.f ? a0 * 0.2f : a0) * 1.4142135623730951f; a1 = (a1 < 0.f ? a1 * 0.2f : a1) * 1.4142135623730951f;
                         ph[j] = __floats2half2_rn(a0, a1);
                     }

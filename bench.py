@@ -201,6 +201,7 @@ def main():
     ev0.record()
     for i in range(args.steps):
         step(args.warmup + i)
+    eng.wait_gather()                              # the last steps' frame exchanges (side stream) are inside the timed region
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)

@@ -93,10 +93,42 @@ class FrameEngine:
                 over['u_fine'] = u_fine
             out = self.head.synthesis(planes, cameras, **over)['image']
         if self.world > 1:
-            with capi.region('allgather'):
-                self.dist.all_gather_into_tensor(self.gathered, out.contiguous())
-            return self.gathered
+            if capi.PROF is not None:                                   # profiling pass: serial, so the region time is the collective's own
+                with capi.region('allgather'):
+                    self.dist.all_gather_into_tensor(self.gathered, out.contiguous())
+                return self.gathered
+            return self._gather_async(out)
         return out
+
+    def _gather_async(self, out: torch.Tensor) -> torch.Tensor:
+        """Frame exchange of step i on a side stream so it runs under the compute of step i+1: the step's frames are copied to one of two
+        staging slots (the graph's output buffer is rewritten by the next replay), NCCL all-gathers slot -> gathered[slot] on `comm`.
+        The returned tensor is complete once `wait_gather()` (or a device sync) has run; a slot is reused two steps later."""
+        if getattr(self, '_ga', None) is None:
+            self._ga = {'comm': torch.cuda.Stream(device=self.device), 'k': 0,
+                        'stage': [torch.empty_like(out) for _ in range(2)],
+                        'dst': [torch.empty(self.world * self.batch, 3, 512, 512, device=self.device) for _ in range(2)],
+                        'done': [torch.cuda.Event() for _ in range(2)], 'ready': [torch.cuda.Event() for _ in range(2)]}
+            cur0 = torch.cuda.current_stream()
+            for e in self._ga['done']:
+                e.record(cur0)
+        ga = self._ga
+        k = ga['k'] & 1
+        ga['k'] += 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ga['done'][k])                                   # the collective that last used this slot has finished
+        ga['stage'][k].copy_(out, non_blocking=True)
+        ga['ready'][k].record(cur)
+        with torch.cuda.stream(ga['comm']):
+            ga['comm'].wait_event(ga['ready'][k])
+            self.dist.all_gather_into_tensor(ga['dst'][k], ga['stage'][k])
+            ga['done'][k].record(ga['comm'])
+        return ga['dst'][k]
+
+    def wait_gather(self) -> None:
+        """Make the current stream wait for every frame exchange issued so far (call before consuming step()'s result when world > 1)."""
+        if getattr(self, '_ga', None) is not None:
+            torch.cuda.current_stream().wait_stream(self._ga['comm'])
 
     # ---- host-buffer entry point: H2D / compute / D2H of consecutive steps overlap on three streams -----------------------
     def _host_pipeline(self):
@@ -131,6 +163,7 @@ class FrameEngine:
             hp['in_ready'][k].record(hp['copy_in'])
         cur.wait_event(hp['in_ready'][k])
         out = self.step(sp, sc, su)
+        self.wait_gather()
         hp['in_free'][k].record(cur)
         cur.wait_event(hp['out_free'][k])
         mine = out[self.rank * self.batch:(self.rank + 1) * self.batch] if out.shape[0] > self.batch else out

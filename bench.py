@@ -245,11 +245,35 @@ def main():
     h2d = h_planes.numel() * 4 + h_cams.numel() * 4 + h_u.numel() * 4
     d2h = h_out.numel() * 4
 
+    # ---- north_star's HBM roofline: the stand-alone sample_from_planes op on one step's render samples (L2 flushed between iterations)
+    hbm = None
+    if rank == 0:
+        from real3dportrait_b200 import renderer as _ren
+        pcl = _ren.planes_to_channels_last(planes[:B])
+        ro, rd = r3.RaySampler()(cams[:B, :16].reshape(-1, 4, 4), cams[:B, 16:25].reshape(-1, 3, 3), 64)
+        depth_mid = 2.15 + 1.1 * (torch.arange(48, device=dev).view(1, 1, 48, 1) + u_c[:B]) / 47.0            # samples spread through the box
+        coords = (ro.unsqueeze(-2) + depth_mid * rd.unsqueeze(-2)).reshape(B, -1, 3).contiguous()
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        ts = []
+        for it in range(13):
+            flush.zero_()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(); _ren.sample_from_planes(None, pcl, coords, box_warp=1.0); a1.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                ts.append(a0.elapsed_time(a1))
+        ts.sort()
+        t_ms = ts[len(ts) // 2]
+        hbm = {'kernel': 'triplane_sample_kernel (sample_from_planes contract, mean NOT fused)', 'ms': t_ms, 'algorithmic_bytes': SAMPLE_BYTES_PER_FRAME * B,
+               'achieved': SAMPLE_BYTES_PER_FRAME * B / (t_ms * 1e-3) / 1e9, 'unit': 'GB/s'}
+        del flush
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
     pk = peaks()
+    hbm.update({'peak': pk['hbm_gbs'], 'frac': hbm['achieved'] / pk['hbm_gbs'], 'peak_source': pk['src'] + ' copy bandwidth', 'bound': 'hbm',
+                'timing': '10 timed iterations, L2 flushed (256 MB write) before each, CUDA events, median'})
     # dominant kernel = the tensor-core conv (4 launches/step); its time is measured by CUDA-event pairs around every launch (library hook),
     # falling back to the whole SR-conv stage for the fp32 path
     if prof.get('conv_kernel_ms'):
@@ -278,6 +302,7 @@ def main():
                      'peak_source': pk['src'] + ' bf16 sustained', 'algorithmic': f'{SR_GFLOP_PER_FRAME} GFLOP/frame x {B} frames/step',
                      'share_of_step': k_ms_per_step / (prof['total_ms'] / args.steps), 'sr_stage_ms_per_step': sr_ms_per_step},
         'stage_ms_per_step': {k: v / args.steps for k, v in prof['stages'].items()},
+        'roofline_hbm': hbm,
     }
     if not args.no_cpu_baseline:
         cpu_fps, ts, nthr = time_cpu(1, 5, 1)

@@ -602,7 +602,7 @@ template <int R> struct Cfg3 {
     static constexpr int NA = 8, NB = 8;
     static constexpr int NACC = (R * BN * 2 <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (R * BN * NACC <= 128) ? 128 : (R * BN * NACC <= 256 ? 256 : 512);
-    static constexpr int SMEM = NA * A2_SLOT + NB * B3_BYTES + 1024 + 8192;
+    static constexpr int SMEM = NA * A2_SLOT + NB * B3_BYTES + 1024 + (R > 2 ? 12288 : 8192);   // tail: barriers, bias, ToRGB weights, [R][128][3] partial sums
 };
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -1266,7 +1266,7 @@ static int run_conv2(const void* x, int N, int H, int W, int Cp, const void* wp,
     a.k_chunks = Cp / BK; a.tiles_x = W / BM; a.n_blocks = O / BN; a.n_images = N; a.w_shared = (Nw == 1);
     if (a.act_gain == 0.f) { a.act_slope = 0.2f; a.act_gain = 1.4142135623730951f; }      // default: bias_act lrelu
     R3DP_REQUIRE(a.n_blocks >= 1 && a.n_blocks <= 2, "conv_tc2: 128 or 256 output channels");
-    if (tc_pairs()) return tc_rows() == 1 ? launch_conv3_r<1>(tmA, tmB, a, max_rows, st) : launch_conv3_r<2>(tmA, tmB, a, max_rows, st);
+    if (tc_pairs()) return tc_rows() == 1 ? launch_conv3_r<1>(tmA, tmB, a, max_rows, st) : (tc_rows() == 4 ? launch_conv3_r<4>(tmA, tmB, a, max_rows, st) : launch_conv3_r<2>(tmA, tmB, a, max_rows, st));
     switch (tc_rows()) {
         case 1: return launch_conv2_r<1>(tmA, tmB, a, max_rows, st);
         case 4: return launch_conv2_r<4>(tmA, tmB, a, max_rows, st);

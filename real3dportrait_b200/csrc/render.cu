@@ -14,7 +14,7 @@ __global__ void mlp_to_const_kernel(const r3dp_mlp_t m, MlpConst* dst) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
     const float g1 = 0.17677669529663687f, g2 = 0.125f;        // 1/sqrt(32), 1/sqrt(64)  (networks_stylegan2.py:113)
     for (int i = tid; i < kHidden * kC; i += nt) dst->w1[i] = m.w1[i] * g1;
-    for (int i = tid; i < kHidden * (kOut + 1); i += nt) { const int j = i / (kOut + 1), o = i - j * (kOut + 1); dst->w2[i] = o < kOut ? m.w2[o * kHidden + j] * g2 : 0.f; }
+    for (int i = tid; i < kHidden * kW2Row; i += nt) { const int j = i / kW2Row, o = i - j * kW2Row; dst->w2[i] = o < kOut ? m.w2[o * kHidden + j] * g2 : 0.f; }
     for (int i = tid; i < kHidden; i += nt) dst->b1[i] = m.b1[i];
     for (int i = tid; i < kOut; i += nt) dst->b2[i] = m.b2[i];
 }
@@ -114,8 +114,10 @@ __device__ __forceinline__ int ray_of(const RenderArgs& a, int tile, int r) {
 }
 
 // CONST = decoder weights from the constant bank (1 sample/thread, 4 CTAs/SM); else staged in smem (2 samples/thread, 2 CTAs/SM)
-template <int R, bool CONST>
-__global__ void __launch_bounds__(kRenderThreads, CONST ? 4 : 2) render_kernel(const RenderArgs a) {
+// PAIR (CONST only) = two samples per thread in the decoder (halves the constant-load traffic; ~160 regs, 2 CTAs/SM) - used when every
+// pass gives each thread a full pair; otherwise one sample per thread at 80 regs, 4 CTAs/SM
+template <int R, bool CONST, bool PAIR>
+__global__ void __launch_bounds__(kRenderThreads, (CONST && !PAIR) ? 4 : 2) render_kernel(const RenderArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int ST = a.S + a.S_imp;                         // samples per ray after the optional importance pass
     MlpSmem& mlp = *reinterpret_cast<MlpSmem*>(smem);
@@ -220,9 +222,24 @@ __global__ void __launch_bounds__(kRenderThreads, CONST ? 4 : 2) render_kernel(c
         }
         __syncthreads();
         if (CONST) {
-            for (int q = tid; q < nsamp; q += kRenderThreads) {
-                const int r = q / kn, k = k0 + (q - r * kn);
-                decode_one_const(rows + (size_t)(r * ST + k) * kRow);
+            if (PAIR) {
+                const int halfc = (nsamp + 1) >> 1;
+                for (int p = tid; p < halfc; p += kRenderThreads) {
+                    const int qa = p, qb = p + halfc;
+                    const int ra = qa / kn, ka = k0 + (qa - ra * kn);
+                    float* rowa = rows + (size_t)(ra * ST + ka) * kRow;
+                    if (qb < nsamp) {
+                        const int rb = qb / kn, kb = k0 + (qb - rb * kn);
+                        decode_two_const(rowa, rows + (size_t)(rb * ST + kb) * kRow);
+                    } else {
+                        decode_one_const(rowa);
+                    }
+                }
+            } else {
+                for (int q = tid; q < nsamp; q += kRenderThreads) {
+                    const int r = q / kn, k = k0 + (q - r * kn);
+                    decode_one_const(rows + (size_t)(r * ST + k) * kRow);
+                }
             }
             __syncthreads();
             return;
@@ -403,10 +420,10 @@ static bool mlp_in_const() {                       // R3DP_MLP=smem selects the 
     return v == 1;
 }
 
-template <int R, bool CONST>
+template <int R, bool CONST, bool PAIR>
 static int launch_render_v(const RenderArgs& a, cudaStream_t st) {
     const size_t smem = render_smem_bytes(R, a.S + a.S_imp, CONST);
-    R3DP_CUDA(cudaFuncSetAttribute(render_kernel<R, CONST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    R3DP_CUDA(cudaFuncSetAttribute(render_kernel<R, CONST, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (CONST) {
         MlpConst* dst = nullptr;
         R3DP_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&dst), c_mlp));
@@ -414,13 +431,15 @@ static int launch_render_v(const RenderArgs& a, cudaStream_t st) {
         count_launches(1);
     }
     dim3 grid(a.tiles_per_frame, a.N);
-    render_kernel<R, CONST><<<grid, kRenderThreads, smem, st>>>(a);
+    render_kernel<R, CONST, PAIR><<<grid, kRenderThreads, smem, st>>>(a);
     R3DP_LAUNCH_CHECK();
     return 0;
 }
 template <int R>
 static int launch_render(const RenderArgs& a, cudaStream_t st) {
-    return mlp_in_const() ? launch_render_v<R, true>(a, st) : launch_render_v<R, false>(a, st);
+    if (!mlp_in_const()) return launch_render_v<R, false, false>(a, st);
+    const int per_pass = R * (a.S_imp > 0 && a.S_imp < a.S ? a.S_imp : a.S);          // the smaller pass decides
+    return per_pass >= 2 * kRenderThreads ? launch_render_v<R, true, true>(a, st) : launch_render_v<R, true, false>(a, st);
 }
 
 }  // namespace r3dp

@@ -332,3 +332,32 @@ def test_sample_far_and_degenerate_points():
     g2 = r3.sample_from_planes(None, planes, bad.to(DEV), box_warp=1.0)
     assert bool(torch.isfinite(g2).all()) and float(g2[:, :, :, :].abs().max()) < 10.0
     assert float(g2[:, 0].abs().max()) == 0.0 and float(g2[:, 2].abs().max()) == 0.0      # planes 0 (x,y) and 2 (z,x) use the bad x
+
+
+def test_frame_engine_graph_and_host_pipeline_match_eager():
+    """What bench.py times: FrameEngine.step() replaying ONE CUDA graph per step, and step_host() (pinned host in/out, 3-stream pipeline), must
+    give exactly the frames of the eager module path, for changing inputs, and the clip helper must place them at the right indices."""
+    from real3dportrait_b200 import engine
+    from real3dportrait_b200.clip import render_clip
+    B, F = 2, 6
+    planes, cams = syn.make_planes(F, seed=50).to(DEV), syn.make_cameras(F, seed=51).to(DEV)
+    u = syn.make_jitter(F, 4096, 48, 0, seed=52)[0].to(DEV)
+    mlp, srp = syn.make_decoder_params(seed=4), syn.make_sr_params(seed=5)
+    eng = engine.FrameEngine(batch=B, sr_mode='tc', use_graph=True)
+    eng.load_params(mlp, srp)
+    eager = engine.FrameEngine(batch=B, sr_mode='tc', use_graph=False)
+    eager.load_params(mlp, srp)
+    ref = torch.cat([eager.step(planes[i:i + B], cams[i:i + B], u[i:i + B]).clone() for i in range(0, F, B)])
+    got = torch.cat([eng.step(planes[i:i + B], cams[i:i + B], u[i:i + B]).clone() for i in range(0, F, B)])
+    assert eng.graph is not None and eng.launches_per_step > 0
+    assert torch.equal(got, ref)                                              # same kernels, same order: bit-identical
+    # pipelined host-buffer entry point
+    hp, hc, hu = planes.cpu().pin_memory(), cams.cpu().pin_memory(), u.cpu().pin_memory()
+    outs = [torch.empty(B, 3, 512, 512).pin_memory() for _ in range(F // B)]
+    for k, i in enumerate(range(0, F, B)):
+        eng.step_host(hp[i:i + B], hc[i:i + B], hu[i:i + B], outs[k])
+    eng.sync_host()
+    assert torch.equal(torch.cat(outs), ref.cpu())
+    # clip helper (world = 1): frames land at their global indices
+    clip = render_clip(lambda idx: eng.step(planes[idx.to(DEV)], cams[idx.to(DEV)], u[idx.to(DEV)]).clone(), F, B, 1, 0)
+    assert torch.equal(clip, ref)

@@ -1,19 +1,21 @@
-// Tensor-core super-resolution path for sm_100a: the four modulated 3x3 convolutions of SuperresolutionHybrid8XDC
-// (197.6 GFLOP/frame) as TMA-fed tcgen05 implicit GEMMs.
+// Tensor-core super-resolution path for sm_100a: the modulated 3x3 convolutions of SuperresolutionHybrid8XDC (197.6 GFLOP/frame,
+// SURVEY.md §8d) and the plain convolutions of the torso head as TMA-fed tcgen05 implicit GEMMs.
 //
 //   activations  NHWC fp16, channels padded to a multiple of 64 (one 128-byte swizzle row = 64 channels)
 //   weights      per-sample folded (modulated+demodulated) fp16, packed [n][tap][Cout][Cin_pad]  (K-major B operand)
-//   accumulate   fp32 in TMEM; epilogue in fp32 (bias, lrelu*sqrt2, ToRGB) then fp16 / fp32 stores
+//   accumulate   fp32 in TMEM; epilogue in fp32 (bias, lrelu*sqrt2, ToRGB + skip) then fp16 / fp32 stores
 //
-// One CTA = one 128(pixels) x 128(couts) output tile: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane,
-// tcgen05.mma cta_group::1 kind::f16), warps 2-5 = epilogue (tcgen05.ld of their 32-lane TMEM quarter).  The im2col
-// is done by TMA itself: each (tap, 64-channel chunk) of the K loop is one 4-D box load {64 ch, 128 px, 1 row, 1 img}
-// at the tap's shifted coordinates, zero-filled outside the image (= the conv's zero padding).  Two CTAs are resident
-// per SM (96 KB smem, 128 TMEM columns each) so one CTA's epilogue overlaps the other's main loop.
+// Three generations of the conv kernel live here (selected by R3DP_TC_KERNEL, default 3):
+//   v3 conv_tc3_kernel  persistent CTA PAIRS (cta_group::2): M256 x N128 x K16 MMAs, half weight tile per CTA, A row strips reused by the
+//                       horizontal taps through row-shifted descriptors, double-buffered TMEM accumulators, 8 epilogue warps    <- DEFAULT
+//   v2 conv_tc2_kernel  the same persistent design on single CTAs (4 epilogue warps)
+//   v1 conv_tc_kernel   one 128x128 tile per CTA, 3-stage ring, 2 CTAs/SM (first working version; kept for A/B runs)
+// In all of them the im2col is done by TMA itself: every (tap, 64-channel chunk) of the K loop is a box load at the tap's shifted
+// coordinates, zero-filled outside the image (= the conv's zero padding); one elected lane issues the MMAs.
 //
-// The stride-2 transposed convolution of the up layers (conv2d_resample.py:116-133) is run as its four output-parity
-// phases, each an implicit GEMM over the low-resolution grid with 4/2/2/1 taps; its (2H+1)x(2W+1) result is then
-// FIR-filtered (+bias, lrelu) by a bandwidth-bound kernel, exactly the reference's operation order.
+// The stride-2 transposed convolution of the up layers (conv2d_resample.py:116-133) keeps the reference's operation order for large Cin:
+// four output-parity phases (4/2/2/1 taps) as units of ONE launch -> (2H+1)x(2W+1) fp16 result -> fir_tma_kernel (TMA-staged 4x4 FIR +
+// bias + lrelu) + upconv_edge_kernel (last column).  For small Cin (block0.conv0) the FIR is composed into the weights instead.
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>

@@ -306,7 +306,11 @@ def main():
     }
     if not args.no_cpu_baseline:
         cpu_fps, ts, nthr = time_cpu(1, 5, 1)
-        line['cpu_baseline'] = {'value': cpu_fps, 'unit': 'frames/s', 'cores': nthr, 'kind': 'port',
+        torch.set_num_threads(1)                                   # also report the 1-thread figure (one frame, no warm-up repeat)
+        fn1 = cpu_frame_fn(1)
+        t1 = time.perf_counter(); fn1(); one_thread_fps = 1.0 / (time.perf_counter() - t1)
+        torch.set_num_threads(nthr)
+        line['cpu_baseline'] = {'value': cpu_fps, 'unit': 'frames/s', 'cores': nthr, 'kind': 'port', 'one_thread_value': one_thread_fps,
                                 'sample': f'{len(ts)} x 1 frame of the same workload (oracle = port of the reference PyTorch CPU path), '
                                           f'{nthr} torch threads of {host_threads()} usable, median'}
     print(json.dumps(line))

@@ -282,8 +282,8 @@ def main():
         k_ms_per_step, k_launches = prof['sr_conv_ms'] / args.steps, None
     sr_ms_per_step = prof['sr_conv_ms'] / args.steps
     sr_tflops = SR_GFLOP_PER_FRAME * B / k_ms_per_step                   # GFLOP / ms == TFLOP/s  (algorithmic: the reference's 197.63 GFLOP/frame)
-    # dram__bytes_read+write of the 4 conv launches of one step from the committed ncu --set full capture (profiles/r1_ncu_full_summaries_2.md), N = 4
-    NCU_TRAFFIC_PER_STEP = (9.1 + 80.8) + (136.4 + 90.9) + (144.3 + 215.7) + (272.0 + 12.4)          # MB
+    # dram__bytes_read+write of the 4 conv launches of one step from the committed ncu --set full capture (profiles/r1_ncu_full_summaries_3.md), N = 4
+    NCU_TRAFFIC_PER_STEP = (13.2 + 82.0) + (140.0 + 97.9) + (161.9 + 226.8) + (272.8 + 12.2)         # MB
     line = {
         'metric': 'rendered frames/sec @512^2 (64^2 NeRF, 48 samples/ray)', 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',

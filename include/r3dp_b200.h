@@ -177,6 +177,8 @@ int r3dp_sr_tc_last_layer(const void* x_f16, const void* wp_f16, const float* bi
 /* Measurement hooks (bench.py): time every tensor-core conv launch with a CUDA-event pair on its launching stream. */
 int r3dp_sr_tc_prof(int enable);
 int r3dp_sr_tc_prof_read(float* total_ms, int* launches);
+/* Debug builds only (-DR3DP_TC_DEBUG_TIMING=1): 32 x 24 uint64 device buffer; row i receives the MMA / epilogue warps' clock sums of the i-th conv launch (NULL = off). */
+int r3dp_sr_tc_debug_buffer(void* buf);
 
 /* ------------------------------------------------------- torso head: SuperresolutionHybrid8XDC_Warp building blocks ---
  * (modules/real3d/super_resolution/sr_with_ref.py:16-162; the torso warper itself stays the caller's PyTorch module)

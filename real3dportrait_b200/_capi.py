@@ -11,7 +11,8 @@ import torch
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
-LIB_PATH = os.path.join(PKG, 'lib', 'libr3dp_b200.so')
+#: R3DP_LIB overrides the library file (profiling builds, e.g. lib/libr3dp_b200_dbg.so); it is still this library or nothing
+LIB_PATH = os.environ.get('R3DP_LIB') or os.path.join(PKG, 'lib', 'libr3dp_b200.so')
 HEADER = os.path.join(ROOT, 'include', 'r3dp_b200.h')
 
 _lib: Optional[C.CDLL] = None
@@ -60,6 +61,7 @@ _SIGNATURES = {
     'r3dp_sr_person_occlusion': (_I, [_P, _P, _F, _I, _I, _I, _P, _P]),
     'r3dp_sr_resize_aa_down2': (_I, [_P, _I, _I, _I, _I, _P, _P]),
     'r3dp_sr_tc_prof': (_I, [_I]),
+    'r3dp_sr_tc_debug_buffer': (_I, [_P]),
     'r3dp_sr_tc_prof_read': (_I, [C.POINTER(C.c_float), C.POINTER(_I)]),
     'r3dp_sr_tc_last_layer': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
 }

@@ -65,5 +65,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_debug_timing() -> str:
+    """lib/libr3dp_b200_dbg.so: the same library with -DR3DP_TC_DEBUG_TIMING=1 (clock64 probes in the conv kernel's MMA and epilogue
+    warps, read by tools/conv_issue_timing.py through R3DP_LIB=<path>).  Never loaded by default."""
+    build()
+    out = os.path.join(LIB_DIR, 'libr3dp_b200_dbg.so')
+    obj = os.path.join(LIB_DIR, 'sr_tc_dbg.o')
+    subprocess.run([_nvcc(), *NVCC_FLAGS, '-DR3DP_TC_DEBUG_TIMING=1', '-c', os.path.join(CSRC, 'sr_tc.cu'), '-o', obj], check=True)
+    objs = [obj] + [os.path.join(LIB_DIR, os.path.basename(s)[:-3] + '.o') for s in sources() if not s.endswith('sr_tc.cu')]
+    subprocess.run([_nvcc(), '-shared', '-o', out, *objs, '-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart_static', '-ldl', '-lrt',
+                    '-lpthread'], check=True)
+    return out
+
+
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    if '--debug-timing' in sys.argv:
+        print(build_debug_timing())
+    else:
+        print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -23,6 +23,9 @@
 #include <vector>
 #include <stdlib.h>
 
+#ifndef R3DP_TC_DEBUG_TIMING
+#define R3DP_TC_DEBUG_TIMING 0
+#endif
 namespace r3dp {
 namespace tc {
 
@@ -324,6 +327,7 @@ struct Conv2Args {
     const float* bias; const float* wrgb; const float* brgb; const float* img_prev; float* img_out; int img_H, img_W;
     float act_slope, act_gain;      // epilogue activation: v < 0 ? v*slope : v, then * gain  (0.2, sqrt2 = bias_act lrelu; 0.01, 1 = nn.LeakyReLU; 1, 1 = linear)
     int skip_same_res;              // ToRGB skip image has the output resolution (SynthesisBlockNoUp) instead of half (FIR-upsampled)
+    unsigned long long* debug;      // R3DP_TC_DEBUG_TIMING builds: [acc wait, strip wait, tap wait, issue, total, #CTAs] clock sums of the MMA warp
 };
 
 template <int R> struct Cfg2 {
@@ -352,6 +356,58 @@ __device__ __forceinline__ float upsampled_skip(const float* __restrict__ ip, in
         acc = fmaf(k4[u], rowv, acc);
     }
     return acc;
+}
+
+// the same sum as upsampled_skip without branches: the two rows / columns of the half-resolution image that reach (Y, X) are (Y-1)>>1
+// and its successor with weights (.25,.75) for even Y and (.75,.25) for odd Y; out-of-range taps get weight 0 and a clamped address, so
+// the four loads are independent (one L2 round trip) and the fma order - hence the bits - are those of the loop above.
+__device__ __forceinline__ float upsampled_skip_bf(const float* __restrict__ ip, int h, int w, int Y, int X) {
+    const int y0 = (Y - 1) >> 1, x0 = (X - 1) >> 1;
+    const float ky0 = (y0 >= 0 && y0 < h) ? ((Y & 1) ? 0.75f : 0.25f) : 0.f, ky1 = (y0 + 1 < h) ? ((Y & 1) ? 0.25f : 0.75f) : 0.f;
+    const float kx0 = (x0 >= 0 && x0 < w) ? ((X & 1) ? 0.75f : 0.25f) : 0.f, kx1 = (x0 + 1 < w) ? ((X & 1) ? 0.25f : 0.75f) : 0.f;
+    const int ya = min(max(y0, 0), h - 1), yb = min(y0 + 1, h - 1), xa = min(max(x0, 0), w - 1), xb = min(x0 + 1, w - 1);
+    const float v00 = __ldg(ip + (size_t)ya * w + xa), v01 = __ldg(ip + (size_t)ya * w + xb);
+    const float v10 = __ldg(ip + (size_t)yb * w + xa), v11 = __ldg(ip + (size_t)yb * w + xb);
+    const float r0 = fmaf(kx1, v01, fmaf(kx0, v00, 0.f)), r1 = fmaf(kx1, v11, fmaf(kx0, v10, 0.f));
+    return fmaf(ky1, r1, fmaf(ky0, r0, 0.f));
+}
+
+// packed 2 x fp32 arithmetic (sm_100 f32x2): one issue slot for two lanes of the epilogue's bias / lrelu / ToRGB work
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rc, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rc, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+
+__device__ __forceinline__ uint4 pack_half8(const float* f) {
+    __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+    __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+    uint4 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+    return pk;
 }
 
 __device__ __forceinline__ void store_half32(__half* dst, const float* f) {
@@ -601,10 +657,12 @@ constexpr int kThreads3 = 64 + 256;                                          // 
 constexpr int B3_BYTES = (BN / 2) * BK * 2;                                  // 64 couts x 64 ch fp16 = 8 KB per CTA
 constexpr uint32_t kIdesc3 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);    // M = 256 across the pair
 template <int R> struct Cfg3 {
-    static constexpr int NA = 8, NB = 8;
+    static constexpr int NA = (R > 2) ? 7 : 8, NB = 8;   // R = 4 gives up one strip slot so the staging buffer fits in 227 KB
     static constexpr int NACC = (R * BN * 2 <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (R * BN * NACC <= 128) ? 128 : (R * BN * NACC <= 256 ? 256 : 512);
-    static constexpr int SMEM = NA * A2_SLOT + NB * B3_BYTES + 1024 + (R > 2 ? 12288 : 8192);   // tail: barriers, bias, ToRGB weights, [R][128][3] partial sums
+    static constexpr int TAIL = (R > 2 ? 12288 : 8192);                      // barriers, bias, ToRGB weights, [R][128][3] partial sums
+    static constexpr int STAGE = 8 * 32 * 64;                                // fp16 store staging: 8 epilogue warps x 32 px x 64 B
+    static constexpr int SMEM = NA * A2_SLOT + NB * B3_BYTES + 1024 + TAIL + STAGE;
 };
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -645,6 +703,7 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
     float* s_bias = reinterpret_cast<float*>(tail + 512);                    // [256]
     float* s_wrgb = s_bias + 256;                                            // [3][n_blocks*128]
     float* s_part = s_wrgb + 768;                                            // [R][128][3] ToRGB partial sums of the second column group
+    uint4* s_stage = reinterpret_cast<uint4*>(tail + C::TAIL);               // [8 warps][32 px][4 x 16 B] fp16 store staging (XOR-swizzled)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t cta_rank;
@@ -714,24 +773,39 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
         // ===== MMA issuer: the leader CTA issues for the pair (M = 256: rows 0-127 from CTA0's strips, 128-255 from CTA1's) =====
         if (leader) {
         uint32_t aq = 0, bq = 0, it = 0;
+#if R3DP_TC_DEBUG_TIMING
+        long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0, t_tot0 = clock64(), tt; unsigned long long ns0, ns1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+#define DT_BEGIN() tt = clock64()
+#define DT_END(x) x += clock64() - tt
+#else
+#define DT_BEGIN()
+#define DT_END(x)
+#endif
         for (int unit = (blockIdx.x & ~1) + (int)cta_rank; unit < a.total_units; unit += gridDim.x) {
             int n, ph, row0, col0; decode(unit, n, ph, row0, col0);
             const Taps2& tp = a.ph[ph].taps;
             const int DY = tp.ngroups, NS = R + DY - 1;
             for (int nblk = 0; nblk < a.n_blocks; ++nblk, ++it) {
                 const int buf = it % C::NACC;
+                DT_BEGIN();
                 mbar_wait(&acc_empty[buf], (((it / C::NACC) & 1) ^ 1));
                 tc_fence_after();
+                DT_END(t_acc);
                 const uint32_t acc0 = tmem_base + buf * (R * BN);
                 for (int kc = 0; kc < a.k_chunks; ++kc) {
                     const uint32_t a_base = aq;                               // sequence number of strip 0 of this chunk
                     for (int d = 0; d < DY; ++d) {
                         const int s_lo = d == 0 ? 0 : R - 1 + d, s_hi = R - 1 + d;
+                        DT_BEGIN();
                         for (int s = s_lo; s <= s_hi; ++s, ++aq) mbar_wait(&a_full[aq % C::NA], (aq / C::NA) & 1);
+                        DT_END(t_a);
                         for (int t = tp.gstart[d]; t < tp.gstart[d + 1]; ++t, ++bq) {
                             const int bslot = bq % C::NB;
+                            DT_BEGIN();
                             mbar_wait(&b_full[bslot], (bq / C::NB) & 1);
                             tc_fence_after();
+                            DT_END(t_b);
+                            DT_BEGIN();
                             {
                                 const uint64_t db = umma_desc_sw128(smem_u32(b_ring + bslot * B3_BYTES));
                                 const int sh = tp.shift[t];
@@ -751,6 +825,7 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                                 }
                             }
                             __syncwarp();
+                            DT_END(t_issue);
                         }
                         // strips no later group needs: strip d after group d; everything left after the last group
                         if (d < DY - 1) {
@@ -765,6 +840,14 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                 __syncwarp();
             }
         }
+#if R3DP_TC_DEBUG_TIMING
+        if (lane == 0 && a.debug) {
+            atomicAdd((unsigned long long*)a.debug + 0, (unsigned long long)t_acc); atomicAdd((unsigned long long*)a.debug + 1, (unsigned long long)t_a);
+            atomicAdd((unsigned long long*)a.debug + 2, (unsigned long long)t_b); atomicAdd((unsigned long long*)a.debug + 3, (unsigned long long)t_issue);
+            atomicAdd((unsigned long long*)a.debug + 4, (unsigned long long)(clock64() - t_tot0)); atomicAdd((unsigned long long*)a.debug + 5, 1ull);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1)); atomicAdd((unsigned long long*)a.debug + 6, ns1 - ns0); atomicAdd((unsigned long long*)a.debug + 7, (unsigned long long)it);
+        }
+#endif
         }
     } else {
         // ===== epilogue: warps 2..9; warp w reads TMEM lanes [32*(w%4), +32); warps 2-5 take columns 0-63 of each accumulator, 6-9 columns 64-127 =====
@@ -772,8 +855,18 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
         const int cg = (warp - 2) >> 2;                                       // column group
         const bool want_rgb = (a.mode == kToRgbFinal) || (a.mode == kActRgb);
         const int CW = a.n_blocks * BN;                                      // channels ToRGB sums over
+        float brgb[3] = {0.f, 0.f, 0.f};
+        if (want_rgb) { brgb[0] = a.brgb[0]; brgb[1] = a.brgb[1]; brgb[2] = a.brgb[2]; }
         uint32_t it = 0;
         int n_loaded = -1;
+#if R3DP_TC_DEBUG_TIMING
+        long long e_full = 0, e_ld = 0, e_math = 0, e_xchg = 0, e_fin = 0, e_pre = 0, e_tot0 = clock64(), et;
+#define ET_BEGIN() et = clock64()
+#define ET_END(x) x += clock64() - et
+#else
+#define ET_BEGIN()
+#define ET_END(x)
+#endif
         for (int unit = (blockIdx.x & ~1) + (int)cta_rank; unit < a.total_units; unit += gridDim.x) {
             int n, ph, row0, col0; decode(unit, n, ph, row0, col0);
             const Phase2& P = a.ph[ph];
@@ -785,68 +878,146 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                 n_loaded = wn;
             }
             const int gcol = col0 + m, X = gcol * a.ox_mul + P.ox_off;
-            float rgb[R][3];
+            float2 rgb2[R][3];                                               // ToRGB sums, even / odd channels in the two halves
 #pragma unroll
-            for (int j = 0; j < R; ++j) { rgb[j][0] = 0.f; rgb[j][1] = 0.f; rgb[j][2] = 0.f; }
+            for (int j = 0; j < R; ++j) { rgb2[j][0] = make_float2(0.f, 0.f); rgb2[j][1] = make_float2(0.f, 0.f); rgb2[j][2] = make_float2(0.f, 0.f); }
+            ET_BEGIN();
+            // skip-image taps of this thread's pixels, fetched by the SECOND column group (it idles at the exchange barrier anyway) and
+            // added to its partial sums.  Issued before the accumulator wait, all loads in one basic block (clamped addresses, zero
+            // weights outside the image), so their L2 latency overlaps and hides behind the MMAs.
+            float skipv[R][3];
+#pragma unroll
+            for (int j = 0; j < R; ++j) { skipv[j][0] = 0.f; skipv[j][1] = 0.f; skipv[j][2] = 0.f; }
+            if (want_rgb && cg == 1 && a.img_prev) {
+                if (a.skip_same_res) {
+                    const int Xc = min(X, a.img_W - 1);
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        const int Yc = min((row0 + j) * a.oy_mul + P.oy_off, a.img_H - 1);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) skipv[j][c] = __ldg(a.img_prev + (((size_t)n * 3 + c) * a.img_H + Yc) * a.img_W + Xc);
+                    }
+                } else {
+                    const int h = a.img_H / 2, w = a.img_W / 2;
+                    const int x0 = (X - 1) >> 1;
+                    const float kx0 = (x0 >= 0 && x0 < w) ? ((X & 1) ? 0.75f : 0.25f) : 0.f, kx1 = (x0 + 1 < w) ? ((X & 1) ? 0.25f : 0.75f) : 0.f;
+                    const int xa = min(max(x0, 0), w - 1), xb = min(max(x0 + 1, 0), w - 1);
+                    float v[R][3][4], ky0[R], ky1[R];
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        const int Y = (row0 + j) * a.oy_mul + P.oy_off, y0 = (Y - 1) >> 1;
+                        ky0[j] = (y0 >= 0 && y0 < h) ? ((Y & 1) ? 0.75f : 0.25f) : 0.f;
+                        ky1[j] = (y0 + 1 < h) ? ((Y & 1) ? 0.25f : 0.75f) : 0.f;
+                        const int ya = min(max(y0, 0), h - 1), yb = min(max(y0 + 1, 0), h - 1);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float* ip = a.img_prev + ((size_t)n * 3 + c) * h * w;
+                            v[j][c][0] = __ldg(ip + ya * w + xa); v[j][c][1] = __ldg(ip + ya * w + xb);
+                            v[j][c][2] = __ldg(ip + yb * w + xa); v[j][c][3] = __ldg(ip + yb * w + xb);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < R; ++j)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {                        // the fma order of upsampled_skip
+                            const float r0 = fmaf(kx1, v[j][c][1], fmaf(kx0, v[j][c][0], 0.f)), r1 = fmaf(kx1, v[j][c][3], fmaf(kx0, v[j][c][2], 0.f));
+                            skipv[j][c] = fmaf(ky1[j], r1, fmaf(ky0[j], r0, 0.f));
+                        }
+                }
+            }
+            ET_END(e_pre);
             for (int nblk = 0; nblk < a.n_blocks; ++nblk, ++it) {
                 const int buf = it % C::NACC;
+                ET_BEGIN();
                 mbar_wait(&acc_full[buf], (it / C::NACC) & 1);
                 tc_fence_after();
+                ET_END(e_full);
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
                     const int row = row0 + j;
                     const int Y = row * a.oy_mul + P.oy_off;
-                    const bool in_img = (row < P.rows) && (Y < a.out_H) && (X < a.out_W);
+                    const bool row_ok = (row < P.rows) && (Y < a.out_H);
+                    const bool in_img = row_ok && (X < a.out_W);
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (R * BN) + j * BN;
-                    __half* dst = a.out + (((size_t)n * a.out_H + Y) * a.out_W + X) * a.out_C + nblk * BN;
+                    __half* dst_row = a.out + ((size_t)n * a.out_H + Y) * a.out_W * a.out_C + nblk * BN;
 #pragma unroll 1
                     for (int c0 = cg * (BN / 2); c0 < (cg + 1) * (BN / 2); c0 += 32) {
                         uint32_t r[32];
+                        ET_BEGIN();
                         tc_ld32(taddr + c0, r);
-                        float f[32];
+                        ET_END(e_ld);
+                        ET_BEGIN();
+                        float2 f2[16];
                         if (a.mode == kStoreRaw) {
 #pragma unroll
-                            for (int jj = 0; jj < 32; ++jj) f[jj] = __uint_as_float(r[jj]);
+                            for (int i = 0; i < 16; ++i) f2[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
                         } else {
+                            // bias, leaky relu as max(v, v*slope) (slope <= 1), gain: bias_act lrelu*sqrt2 | nn.LeakyReLU | linear
+                            const float2* b2 = reinterpret_cast<const float2*>(s_bias + nblk * BN + c0);
+                            const float2 sl2 = make_float2(a.act_slope, a.act_slope), g2 = make_float2(a.act_gain, a.act_gain);
 #pragma unroll
-                            for (int jj = 0; jj < 32; ++jj) {
-                                const float v = __uint_as_float(r[jj]) + s_bias[nblk * BN + c0 + jj];
-                                f[jj] = (v < 0.f ? v * a.act_slope : v) * a.act_gain;        // bias_act lrelu*sqrt2 | nn.LeakyReLU | linear
+                            for (int i = 0; i < 16; ++i) {
+                                const float2 v = add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), b2[i]);
+                                const float2 t = mul2(v, sl2);
+                                f2[i] = mul2(make_float2(fmaxf(v.x, t.x), fmaxf(v.y, t.y)), g2);
                             }
                         }
-                        if (a.mode != kToRgbFinal && in_img) store_half32(dst + c0, f);
+                        const float* f = reinterpret_cast<const float*>(f2);
+                        if (a.mode != kToRgbFinal) {
+                            // NHWC fp16 store through smem: the thread owns a pixel (32 channels = 64 B); written directly, every
+                            // STG.128 of the warp would touch 32 different lines.  Staged, 4 lanes write one pixel's 64 contiguous bytes.
+                            uint4* st = s_stage + (warp - 2) * 128;
+                            const int sw = (lane >> 1) & 3;
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) st[lane * 4 + (v ^ sw)] = pack_half8(f + 8 * v);
+                            __syncwarp();
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int p = i * 8 + (lane >> 2), cch = lane & 3;
+                                const uint4 pk = st[p * 4 + (cch ^ ((p >> 1) & 3))];
+                                const int Xp = (col0 + q * 32 + p) * a.ox_mul + P.ox_off;
+                                if (row_ok && Xp < a.out_W) *reinterpret_cast<uint4*>(dst_row + (size_t)Xp * a.out_C + c0 + cch * 8) = pk;
+                            }
+                            __syncwarp();
+                        }
                         if (want_rgb) {
 #pragma unroll
                             for (int c = 0; c < 3; ++c) {
                                 const float4* w4 = reinterpret_cast<const float4*>(s_wrgb + c * CW + nblk * BN + c0);
-                                float acc = rgb[j][c];
+                                float2 acc = rgb2[j][c];
 #pragma unroll
                                 for (int j4 = 0; j4 < 8; ++j4) {
                                     const float4 w = w4[j4];
-                                    acc = fmaf(f[4 * j4 + 0], w.x, acc); acc = fmaf(f[4 * j4 + 1], w.y, acc);
-                                    acc = fmaf(f[4 * j4 + 2], w.z, acc); acc = fmaf(f[4 * j4 + 3], w.w, acc);
+                                    acc = fma2(f2[2 * j4], make_float2(w.x, w.y), acc);
+                                    acc = fma2(f2[2 * j4 + 1], make_float2(w.z, w.w), acc);
                                 }
-                                rgb[j][c] = acc;
+                                rgb2[j][c] = acc;
                             }
                         }
+                        ET_END(e_math);
                     }
+                    ET_BEGIN();
                     if (want_rgb && nblk == a.n_blocks - 1) {
                         // the two column groups hold partial ToRGB sums of the same pixel: group 1 hands its sums to group 0 through smem
-                        if (cg == 1) { s_part[(j * BM + m) * 3 + 0] = rgb[j][0]; s_part[(j * BM + m) * 3 + 1] = rgb[j][1]; s_part[(j * BM + m) * 3 + 2] = rgb[j][2]; }
+                        if (cg == 1) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) s_part[(j * BM + m) * 3 + c] = (rgb2[j][c].x + rgb2[j][c].y) + skipv[j][c];
+                        }
                         asm volatile("bar.sync 2, 256;" ::: "memory");
-                        if (cg == 0) { rgb[j][0] += s_part[(j * BM + m) * 3 + 0]; rgb[j][1] += s_part[(j * BM + m) * 3 + 1]; rgb[j][2] += s_part[(j * BM + m) * 3 + 2]; }
+                        if (cg == 0) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) rgb2[j][c].x = (rgb2[j][c].x + rgb2[j][c].y) + s_part[(j * BM + m) * 3 + c];
+                        }
                         asm volatile("bar.sync 3, 256;" ::: "memory");
                     }
+                    ET_END(e_xchg);
+                    ET_BEGIN();
                     if (want_rgb && nblk == a.n_blocks - 1 && in_img && cg == 0) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            float skip = 0.f;
-                            if (a.img_prev) skip = a.skip_same_res ? __ldg(a.img_prev + (((size_t)n * 3 + c) * a.img_H + Y) * a.img_W + X)
-                                                                   : upsampled_skip(a.img_prev + ((size_t)n * 3 + c) * (a.img_H / 2) * (a.img_W / 2),
-                                                                                    a.img_H / 2, a.img_W / 2, Y, X);
-                            a.img_out[(((size_t)n * 3 + c) * a.img_H + Y) * a.img_W + X] = rgb[j][c] + a.brgb[c] + skip;
-                        }
+                        for (int c = 0; c < 3; ++c)
+                            a.img_out[(((size_t)n * 3 + c) * a.img_H + Y) * a.img_W + X] = rgb2[j][c].x + brgb[c];
                     }
+                    ET_END(e_fin);
                 }
                 // this warp is done reading the accumulator buffer
                 tc_fence_before();
@@ -854,6 +1025,14 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf]) & 0xFEFFFFFFu) : "memory");
             }
         }
+#if R3DP_TC_DEBUG_TIMING
+        if (lane == 0 && a.debug && (warp == 2 || warp == 6) && cta_rank == 0) {
+            unsigned long long* d = a.debug + 8 + (warp == 6 ? 8 : 0);
+            atomicAdd(d + 0, (unsigned long long)e_full); atomicAdd(d + 1, (unsigned long long)e_ld); atomicAdd(d + 2, (unsigned long long)e_math);
+            atomicAdd(d + 3, (unsigned long long)e_xchg); atomicAdd(d + 4, (unsigned long long)e_fin); atomicAdd(d + 5, (unsigned long long)(clock64() - e_tot0));
+            atomicAdd(d + 6, (unsigned long long)it); atomicAdd(d + 7, (unsigned long long)e_pre);
+        }
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -1183,6 +1362,8 @@ static void prof_mark(cudaStream_t st) {
     cudaEventRecord(g_prof.ev[g_prof.used++], st);
 }
 
+static unsigned long long* g_debug_buf = nullptr;
+static int g_debug_launch = 0;
 static int tc_version() {                      // R3DP_TC_KERNEL=1: simple v1 kernel; 2: single-CTA persistent v2; 3 (default): CTA pairs
     static int v = -1;
     if (v < 0) { const char* e = getenv("R3DP_TC_KERNEL"); v = (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 3); }
@@ -1203,6 +1384,7 @@ static int launch_conv3_r(const CUtensorMap& tmA, const CUtensorMap& tmB, Conv2A
         R3DP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
+    a.debug = g_debug_buf ? g_debug_buf + 24 * (g_debug_launch++ % 32) : nullptr;
     a.row_groups = (max_rows + R - 1) / R;
     if ((a.row_groups * a.tiles_x) & 1) a.row_groups += 1;       // the two CTAs of a pair must work on units of the same (image, phase)
     a.total_units = a.n_images * a.n_phases * a.row_groups * a.tiles_x;
@@ -1718,3 +1900,6 @@ extern "C" int r3dp_sr_tc_prof_read(float* total_ms, int* launches) {
     if (launches) *launches = (int)(g_prof.used / 2);
     return 0;
 }
+
+// debug builds (-DR3DP_TC_DEBUG_TIMING=1): device buffer of 32 x 24 uint64; the i-th conv_tc3 launch after this call adds clock sums to row i: [0,8) MMA warp, [8,16) epilogue warp 2 (columns 0-63), [16,24) epilogue warp 6 (columns 64-127)
+extern "C" int r3dp_sr_tc_debug_buffer(void* buf) { g_debug_buf = reinterpret_cast<unsigned long long*>(buf); g_debug_launch = 0; return 0; }

@@ -4,6 +4,7 @@
 //   3. depth_clamp_kernel  NaN->inf, clamp depth to the call-wide [min,max] sample depth (ray_marcher.py:49-50)
 // plus gen_rays (RaySampler.forward) and a stand-alone ray marcher.
 #include "render_core.cuh"
+#include "tc_prims.cuh"
 #include <stdlib.h>
 
 namespace r3dp {
@@ -18,6 +19,55 @@ __global__ void mlp_to_const_kernel(const r3dp_mlp_t m, MlpConst* dst) {
     for (int i = tid; i < kHidden; i += nt) dst->b1[i] = m.b1[i];
     for (int i = tid; i < kOut; i += nt) dst->b2[i] = m.b2[i];
 }
+
+// ---- tensor-core decoder (R3DP_MLP=tc, default for single-pass renders) -----------------------------------------------------------
+// The OSG decoder is two GEMMs over the samples: [M x 32] x [32 x 64] -> softplus -> [M x 64] x [64 x 33].  They run on tcgen05 with
+// fp16 operands and fp32 accumulation in TMEM; fp32 accuracy is kept by splitting every operand into two fp16 halves
+// (v = hi + lo exactly to 2^-22 |v|) and summing the three significant partial products hi*hi + lo*hi + hi*lo (lo*lo ~ 2^-22 is dropped).
+// Operand images (K-major, 128-byte swizzle: one 128 B row = 64 fp16, 8-row groups 1024 B apart):
+//   A1 tile  128 samples x [x_hi(32) | x_lo(32)]             written by the gather
+//   W1       64 hidden   x [w_hi(32) | w_lo(32)]             k-steps 0,1 = hi, 2,3 = lo
+//   A2 tile  128 samples x [h_hi(64)] , [h_lo(64)]           two atoms, written by the layer-1 epilogue
+//   W2       48 outputs  x [w_hi(64)] , [w_lo(64)]           two atoms, rows >= 33 are zero (UMMA N must be a multiple of 16)
+struct alignas(16) MlpTcImage {
+    uint8_t w1[kHidden * 128];
+    uint8_t w2hi[48 * 128];
+    uint8_t w2lo[48 * 128];
+    float b1[kHidden];
+    float b2[48];
+};
+static_assert(sizeof(MlpTcImage) == 8192 + 6144 + 6144 + 256 + 192, "MlpTcImage layout");
+__device__ MlpTcImage g_mlp_tc;
+
+__device__ __forceinline__ uint32_t sw128_off(int row, int k) {                // byte offset of fp16 element (row, k) of a swizzled atom
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7))) << 4) + (k & 7) * 2);
+}
+__global__ void mlp_to_tc_kernel(const r3dp_mlp_t m, MlpTcImage* dst) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    const float g1 = 0.17677669529663687f, g2 = 0.125f;        // 1/sqrt(32), 1/sqrt(64)  (networks_stylegan2.py:113)
+    for (int i = tid; i < kHidden * kC; i += nt) {
+        const int j = i / kC, c = i - j * kC;
+        const float w = m.w1[i] * g1;
+        const __half hi = __float2half_rn(w), lo = __float2half_rn(w - __half2float(hi));
+        *reinterpret_cast<__half*>(dst->w1 + sw128_off(j, c)) = hi;
+        *reinterpret_cast<__half*>(dst->w1 + sw128_off(j, kC + c)) = lo;
+    }
+    for (int i = tid; i < 48 * kHidden; i += nt) {
+        const int o = i / kHidden, j = i - o * kHidden;
+        const float w = o < kOut ? m.w2[o * kHidden + j] * g2 : 0.f;
+        const __half hi = __float2half_rn(w), lo = __float2half_rn(w - __half2float(hi));
+        *reinterpret_cast<__half*>(dst->w2hi + sw128_off(o, j)) = hi;
+        *reinterpret_cast<__half*>(dst->w2lo + sw128_off(o, j)) = lo;
+    }
+    for (int i = tid; i < kHidden; i += nt) dst->b1[i] = m.b1[i];
+    for (int i = tid; i < 48; i += nt) dst->b2[i] = i < kOut ? m.b2[i] : 0.f;
+}
+constexpr int kTcThreads = 256;                          // 8 warps: TMEM lane quadrant = warp % 4, column half = warp / 4
+constexpr int kTcMaxTiles = 3;                           // 128-sample tiles per pass (TMEM: 64 columns each)
+constexpr int kTcA1Bytes = 51200;                        // 3 x 16 KB A1 tiles; later the [R*ST][33] fp32 decoded rows (<= 384 x 132 B)
+constexpr int kTcA2Bytes = 32768;                        // two 16 KB atoms; before the decode: tap descriptors [nsamp][16]; after: march scratch
+constexpr uint32_t kIdescL1 = (1u << 4) | ((uint32_t)(kHidden >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);    // M128 N64, f16 x f16 -> f32
+constexpr uint32_t kIdescL2 = (1u << 4) | ((uint32_t)(48 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);         // M128 N48
 
 struct RenderWs {          // lives at the start of the caller's workspace
     unsigned t0_min, t0_max;   // ordered-uint encoded floats over valid rays
@@ -116,9 +166,11 @@ __device__ __forceinline__ int ray_of(const RenderArgs& a, int tile, int r) {
 // CONST = decoder weights from the constant bank (1 sample/thread, 4 CTAs/SM); else staged in smem (2 samples/thread, 2 CTAs/SM)
 // PAIR (CONST only) = two samples per thread in the decoder (halves the constant-load traffic; ~160 regs, 2 CTAs/SM) - used when every
 // pass gives each thread a full pair; otherwise one sample per thread at 80 regs, 4 CTAs/SM
-template <int R, bool CONST, bool PAIR>
-__global__ void __launch_bounds__(kRenderThreads, (CONST && !PAIR) ? 4 : 2) render_kernel(const RenderArgs a) {
+// TC = decoder on tcgen05 (single-pass renders with R*S <= 384; 256 threads, 2 CTAs/SM); see the MlpTcImage comment
+template <int R, bool CONST, bool PAIR, bool TC = false>
+__global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((CONST && !PAIR) ? 4 : 2)) render_kernel(const RenderArgs a) {
     extern __shared__ __align__(16) float smem[];
+    constexpr int kRenderThreads = TC ? kTcThreads : r3dp::kRenderThreads;     // shadows the namespace constant inside this kernel
     const int ST = a.S + a.S_imp;                         // samples per ray after the optional importance pass
     MlpSmem& mlp = *reinterpret_cast<MlpSmem*>(smem);
     float* rows = smem + (CONST ? 0 : sizeof(MlpSmem) / 4); // [R*ST][kRow]   features -> (sigma, colours)
@@ -127,12 +179,49 @@ __global__ void __launch_bounds__(kRenderThreads, (CONST && !PAIR) ? 4 : 2) rend
     float* cdf = wts + R * ST;                             // [R*ST]          importance cdf
     float* rayf = cdf + R * ST;                            // [R][8]          ox oy oz dx dy dz t0 t1
     int* ord = reinterpret_cast<int*>(rayf + R * 8);       // [R*ST]          depth order of the merged samples
+    // TC layout (1024-aligned): [A1 tiles | decoded rows] [A2 atoms | tap descriptors | march scratch] [W image + biases] dep rayf barriers
+    uint8_t* a1 = nullptr; uint8_t* a2 = nullptr; uint8_t* wimg = nullptr; float* dsc = nullptr; float* b1s = nullptr; float* b2s = nullptr;
+    uint64_t* bar1 = nullptr; uint64_t* bar2 = nullptr; uint32_t* tmem_slot = nullptr;
+    if (TC) {
+        a1 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+        a2 = a1 + kTcA1Bytes;
+        wimg = a2 + kTcA2Bytes;
+        rows = reinterpret_cast<float*>(a1);
+        dsc = reinterpret_cast<float*>(a2);                                   // [nsamp][16]  (<= 24 KB)
+        wts = reinterpret_cast<float*>(a2 + 24576);                           // [R*ST]  march scratch (the atoms are dead by then)
+        cdf = wts + R * ST;
+        b1s = reinterpret_cast<float*>(wimg + 20480); b2s = b1s + kHidden;
+        dep = b2s + 48;
+        rayf = dep + R * ST;
+        bar1 = reinterpret_cast<uint64_t*>(rayf + R * 8); bar2 = bar1 + kTcMaxTiles;
+        tmem_slot = reinterpret_cast<uint32_t*>(bar2 + kTcMaxTiles);
+        ord = nullptr;                                                        // single pass only
+    }
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kRenderThreads / 32;
     const int n = blockIdx.y, tile = blockIdx.x;
 
     if (!CONST) load_mlp_smem(mlp, a.mlp, tid, kRenderThreads);
+    uint32_t tmem_base = 0;
+    if (TC) {
+        if (tid == 0) {
+            for (int i = 0; i < kTcMaxTiles; ++i) { tc::mbar_init(&bar1[i], 1); tc::mbar_init(&bar2[i], 1); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(256) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        // decoder weight image (pre-swizzled fp16 hi/lo atoms + biases): 20 928 B from L2
+        const uint4* src = reinterpret_cast<const uint4*>(&g_mlp_tc);
+        uint4* dst = reinterpret_cast<uint4*>(wimg);
+        for (int i = tid; i < (int)(sizeof(MlpTcImage) / 16); i += kRenderThreads) dst[i] = __ldg(src + i);
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+        tmem_base = *tmem_slot;
+    }
 
     // ---- rays + limits -------------------------------------------------------------------------------------
     if (tid < R) {
@@ -185,7 +274,7 @@ __global__ void __launch_bounds__(kRenderThreads, (CONST && !PAIR) ? 4 : 2) rend
             const float y = __fadd_rn(rf[1], __fmul_rn(d, rf[4]));
             const float z = __fadd_rn(rf[2], __fmul_rn(d, rf[5]));
             const float gx = pv.scale * x, gy = pv.scale * y, gz = pv.scale * z;
-            float* row = rows + (size_t)(r * ST + k) * kRow;
+            float* row = TC ? dsc + q * 16 : rows + (size_t)(r * ST + k) * kRow;
             tap_desc(gx, gy, pv.H, pv.W, 0, row);                      // plane 0 <- (x, y)   (renderer.py:30-63)
             tap_desc(gx, gz, pv.H, pv.W, 1, row + 5);                  // plane 1 <- (x, z)
             tap_desc(gz, gx, pv.H, pv.W, 2, row + 10);                 // plane 2 <- (z, x)
@@ -198,7 +287,7 @@ __global__ void __launch_bounds__(kRenderThreads, (CONST && !PAIR) ? 4 : 2) rend
             const int q = q4 + sub;
             if (q < nsamp) {
                 const int r = q / kn, k = k0 + (q - r * kn);
-                float* row = rows + (size_t)(r * ST + k) * kRow;
+                float* row = TC ? dsc + q * 16 : rows + (size_t)(r * ST + k) * kRow;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 float dsc[15];
 #pragma unroll
@@ -214,11 +303,127 @@ __global__ void __launch_bounds__(kRenderThreads, (CONST && !PAIR) ? 4 : 2) rend
                     acc.z += t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
                     acc.w += t00.w * w00 + t10.w * w10 + t01.w * w01 + t11.w * w11;
                 }
-                __syncwarp(__activemask());
                 const float third = 1.0f / 3.0f;
-                row[cq * 4 + 0] = acc.x * third; row[cq * 4 + 1] = acc.y * third;
-                row[cq * 4 + 2] = acc.z * third; row[cq * 4 + 3] = acc.w * third;
+                if (TC) {
+                    // mean features as fp16 hi + lo halves straight into the swizzled A1 tile: lane cq owns K = [4cq, 4cq+4) of both halves
+                    const float f0 = acc.x * third, f1 = acc.y * third, f2 = acc.z * third, f3 = acc.w * third;
+                    const __half2 h01 = __floats2half2_rn(f0, f1), h23 = __floats2half2_rn(f2, f3);
+                    const float2 g01 = __half22float2(h01), g23 = __half22float2(h23);
+                    const __half2 l01 = __floats2half2_rn(f0 - g01.x, f1 - g01.y), l23 = __floats2half2_rn(f2 - g23.x, f3 - g23.y);
+                    const int trow = q & 127;
+                    uint8_t* rp = a1 + (q >> 7) * 16384 + (trow >> 3) * 1024 + (trow & 7) * 128 + (cq & 1) * 8;
+                    uint2 hv, lv;
+                    hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                    lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                    *reinterpret_cast<uint2*>(rp + (((cq >> 1) ^ (trow & 7)) << 4)) = hv;
+                    *reinterpret_cast<uint2*>(rp + (((4 + (cq >> 1)) ^ (trow & 7)) << 4)) = lv;
+                } else {
+                    __syncwarp(__activemask());
+                    row[cq * 4 + 0] = acc.x * third; row[cq * 4 + 1] = acc.y * third;
+                    row[cq * 4 + 2] = acc.z * third; row[cq * 4 + 3] = acc.w * third;
+                }
             }
+        }
+        if (TC) {
+            // ---- decoder on the tensor core ---------------------------------------------------------------------------------------------
+            const int nt = (nsamp + 127) >> 7;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // this thread's A1 (and W) stores -> visible to the async proxy
+            tc::tc_fence_before();
+            __syncthreads();
+            const uint32_t a1_s = tc::smem_u32(a1), a2_s = tc::smem_u32(a2), w_s = tc::smem_u32(wimg);
+            if (warp == 0) {                                                   // layer 1 of every tile: 3 partial products x 2 k-steps
+                tc::tc_fence_after();
+                for (int t = 0; t < nt; ++t) {
+                    if (tc::elect_one()) {
+                        uint32_t accum = 0;
+#pragma unroll
+                        for (int term = 0; term < 3; ++term) {
+                            const uint32_t ao = term == 1 ? 64u : 0u, bo = term == 2 ? 64u : 0u;     // x_hi w_hi + x_lo w_hi + x_hi w_lo
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                tc::tc_mma_f16(tmem_base + 64 * t, tc::umma_desc_sw128(a1_s + t * 16384 + ao + ks * 32),
+                                               tc::umma_desc_sw128(w_s + bo + ks * 32), kIdescL1, accum);
+                                accum = 1;
+                            }
+                        }
+                        tc::tc_commit(&bar1[t]);
+                    }
+                    __syncwarp();
+                }
+            }
+            const int qd = warp & 3, g = warp >> 2, trow = qd * 32 + lane;      // TMEM lane quadrant, column half, row of the tile
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
+            for (int t = 0; t <= nt; ++t) {
+                if (t < nt) {
+                    tc::mbar_wait(&bar1[t], 0);
+                    tc::tc_fence_after();
+                    uint32_t v[32];
+                    tc::tc_ld32(lane_addr + 64 * t + 32 * g, v);                // hidden units [32g, 32g+32) of this sample, pre-activation
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float h0 = softplus_fast(__uint_as_float(v[2 * i]) + b1s[32 * g + 2 * i]);
+                        const float h1 = softplus_fast(__uint_as_float(v[2 * i + 1]) + b1s[32 * g + 2 * i + 1]);
+                        const __half2 hh = __floats2half2_rn(h0, h1);
+                        const float2 hf = __half22float2(hh);
+                        const __half2 ll = __floats2half2_rn(h0 - hf.x, h1 - hf.y);
+                        hi[i] = *reinterpret_cast<const uint32_t*>(&hh); lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
+                    }
+                    if (t >= 1) { tc::mbar_wait(&bar2[t - 1], 0); tc::tc_fence_after(); }   // layer 2 of the previous tile has read A2
+                    uint8_t* rp = a2 + (trow >> 3) * 1024 + (trow & 7) * 128;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int off = ((4 * g + c) ^ (trow & 7)) << 4;
+                        *reinterpret_cast<uint4*>(rp + off) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(rp + 16384 + off) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    tc::tc_fence_before();
+                    __syncthreads();
+                    if (warp == 0) {                                           // layer 2: h_hi w_hi + h_lo w_hi + h_hi w_lo, 4 k-steps each
+                        tc::tc_fence_after();
+                        if (tc::elect_one()) {
+                            uint32_t accum = 0;
+#pragma unroll
+                            for (int term = 0; term < 3; ++term) {
+                                const uint32_t ao = term == 1 ? 16384u : 0u, bo = term == 2 ? (8192u + 6144u) : 8192u;
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    tc::tc_mma_f16(tmem_base + 64 * t, tc::umma_desc_sw128(a2_s + ao + ks * 32),
+                                                   tc::umma_desc_sw128(w_s + bo + ks * 32), kIdescL2, accum);
+                                    accum = 1;
+                                }
+                            }
+                            tc::tc_commit(&bar2[t]);
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (t >= 1) {
+                    // outputs of tile t-1 (its layer 2 overlapped the epilogue above): bias, sigma raw, colours through the scaled sigmoid
+                    if (t == 1) tc::mbar_wait(&bar1[nt - 1], 0);                // rows alias the A1 tiles: every layer-1 MMA must have retired
+                    if (t == nt) tc::mbar_wait(&bar2[nt - 1], 0);
+                    tc::tc_fence_after();
+                    uint32_t v[32];
+                    tc::tc_ld32(lane_addr + 64 * (t - 1) + 16 * g, v);
+                    const int sidx = (t - 1) * 128 + trow;
+                    if (sidx < nsamp) {
+                        const int r = sidx / kn, k = k0 + (sidx - r * kn);
+                        float* out = rows + (size_t)(r * ST + k) * kRow;
+                        if (g == 0) {
+                            out[0] = __uint_as_float(v[0]) + b2s[0];
+#pragma unroll
+                            for (int o = 1; o < 16; ++o) out[o] = sigmoid_fast(__uint_as_float(v[o]) + b2s[o]) * 1.002f - 0.001f;
+                        } else {
+#pragma unroll
+                            for (int o = 16; o < kOut; ++o) out[o] = sigmoid_fast(__uint_as_float(v[o - 16]) + b2s[o]) * 1.002f - 0.001f;
+                        }
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncthreads();
+            return;
         }
         __syncthreads();
         if (CONST) {
@@ -376,6 +581,14 @@ __global__ void __launch_bounds__(kRenderThreads, (CONST && !PAIR) ? 4 : 2) rend
     // call-wide min/max of the sample depths (ray_marcher.py:50)
     dmin = warp_min(dmin); dmax = warp_max(dmax);
     if (lane == 0 && dmin <= dmax) { atomicMin(&a.ws->d_min, f2ord(dmin)); atomicMax(&a.ws->d_max, f2ord(dmax)); }
+    if (TC) {
+        tc::tc_fence_before();
+        __syncthreads();
+        if (warp == 0) {
+            tc::tc_fence_after();
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+        }
+    }
 }
 
 // Stand-alone marcher: one warp per ray, lane = channel (C <= 32 per pass, loops for wider C).
@@ -414,10 +627,25 @@ static size_t render_smem_bytes(int R, int ST, bool cst) {
     return (cst ? 0 : sizeof(MlpSmem)) + (size_t)R * ST * kRow * 4 + 3 * (size_t)R * ST * 4 + (size_t)R * 8 * 4 + (size_t)R * ST * 4;
 }
 
-static bool mlp_in_const() {                       // R3DP_MLP=smem selects the shared-memory decoder variant (A/B comparison)
+static int mlp_variant() {                         // R3DP_MLP = tc (default) | const | smem: decoder variant, for A/B comparison
     static int v = -1;
-    if (v < 0) { const char* e = getenv("R3DP_MLP"); v = (e && e[0] == 's') ? 0 : 1; }
-    return v == 1;
+    if (v < 0) { const char* e = getenv("R3DP_MLP"); v = !e ? 2 : e[0] == 's' ? 0 : e[0] == 'c' ? 1 : 2; }
+    return v;
+}
+static bool mlp_in_const() { return mlp_variant() != 0; }
+
+template <int R>
+static int launch_render_tc(const RenderArgs& a, cudaStream_t st) {
+    const size_t smem = 1024 + kTcA1Bytes + kTcA2Bytes + 20480 + (kHidden + 48) * 4 + (size_t)R * (a.S + 8) * 4 + 2 * kTcMaxTiles * 8 + 16;
+    R3DP_CUDA(cudaFuncSetAttribute(render_kernel<R, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MlpTcImage* dst = nullptr;
+    R3DP_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&dst), g_mlp_tc));
+    mlp_to_tc_kernel<<<4, 256, 0, st>>>(a.mlp, dst);
+    count_launches(1);
+    dim3 grid(a.tiles_per_frame, a.N);
+    render_kernel<R, true, false, true><<<grid, kTcThreads, smem, st>>>(a);
+    R3DP_LAUNCH_CHECK();
+    return 0;
 }
 
 template <int R, bool CONST, bool PAIR>
@@ -438,6 +666,8 @@ static int launch_render_v(const RenderArgs& a, cudaStream_t st) {
 template <int R>
 static int launch_render(const RenderArgs& a, cudaStream_t st) {
     if (!mlp_in_const()) return launch_render_v<R, false, false>(a, st);
+    // tensor-core decoder: single-pass renders whose CTA tile fits three 128-sample MMA tiles
+    if (mlp_variant() == 2 && a.S_imp == 0 && R * a.S <= 128 * kTcMaxTiles && R * a.S * kRow * 4 <= kTcA1Bytes) return launch_render_tc<R>(a, st);
     const int per_pass = R * (a.S_imp > 0 && a.S_imp < a.S ? a.S_imp : a.S);          // the smaller pass decides
     return per_pass >= 2 * kRenderThreads ? launch_render_v<R, true, true>(a, st) : launch_render_v<R, true, false>(a, st);
 }

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
     uint8_t* a1 = nullptr; uint8_t* a2 = nullptr; uint8_t* wimg = nullptr; float* dsc = nullptr; float* b1s = nullptr; float* b2s = nullptr;
     uint64_t* bar1 = nullptr; uint64_t* bar2 = nullptr; uint32_t* tmem_slot = nullptr;
     if (TC) {
-        a1 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+        a1 = tc::align_smem_1024(reinterpret_cast<uint8_t*>(smem));
         a2 = a1 + kTcA1Bytes;
         wimg = a2 + kTcA2Bytes;
         rows = reinterpret_cast<float*>(a1);
@@ -216,7 +216,9 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
         // decoder weight image (pre-swizzled fp16 hi/lo atoms + biases): 20 928 B from L2
         const uint4* src = reinterpret_cast<const uint4*>(&g_mlp_tc);
         uint4* dst = reinterpret_cast<uint4*>(wimg);
-        for (int i = tid; i < (int)(sizeof(MlpTcImage) / 16); i += kRenderThreads) dst[i] = __ldg(src + i);
+        for (int i = tid; i < (int)(sizeof(MlpTcImage) / 16); i += kRenderThreads)       // LDGSTS: lands while the rays / depths / taps are computed
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(dst + i)), "l"(src + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
         tc::tc_fence_before();
         __syncthreads();
         tc::tc_fence_after();
@@ -327,6 +329,7 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
         if (TC) {
             // ---- decoder on the tensor core ---------------------------------------------------------------------------------------------
             const int nt = (nsamp + 127) >> 7;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");                // the weight image has landed
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // this thread's A1 (and W) stores -> visible to the async proxy
             tc::tc_fence_before();
             __syncthreads();

@@ -60,7 +60,7 @@ struct ConvArgs {
 __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = align_smem_1024(smem_raw);
     uint8_t* stage_base = smem;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc2_kernel(const __grid_cons
                                                                const __grid_constant__ CUtensorMap tmB, const Conv2Args a) {
     using C = Cfg2<R>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = align_smem_1024(smem_raw);
     uint8_t* a_ring = smem;
     uint8_t* b_ring = smem + C::NA * A2_SLOT;
     uint8_t* tail = b_ring + C::NB * B_BYTES;
@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                                                                const __grid_constant__ CUtensorMap tmB, const Conv2Args a) {
     using C = Cfg3<R>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = align_smem_1024(smem_raw);
     uint8_t* a_ring = smem;
     uint8_t* b_ring = smem + C::NA * A2_SLOT;
     uint8_t* tail = b_ring + C::NB * B3_BYTES;
@@ -1083,7 +1083,7 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
 __global__ void __launch_bounds__(256) fir_tma_kernel(const __grid_constant__ CUtensorMap tmY, const float* __restrict__ bias, int N, int OH,
                                                       int OW, int C, __half* __restrict__ y) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = align_smem_1024(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * FIR_SLOT);
     const int tid = threadIdx.x, px = tid >> 3, c8 = tid & 7;
     const int tiles_x = OW / FIR_TW, tiles_y = (OH + FIR_TH - 1) / FIR_TH, cgs = C / 64;

@@ -11,6 +11,10 @@ namespace tc {
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// first 1024-byte boundary of the dynamic shared memory window (SWIZZLE_128B atoms need it).  The offset is computed from the shared-window
+// address and ADDED to the original pointer: rounding through uintptr_t makes the compiler lose the address space and emit generic
+// LD/ST (LD.E / ST.E, `lg` stalls) for every later smem access.
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* p) { return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
 }

@@ -3,12 +3,48 @@ a batch of tri-planes + cameras + jitter in, 512^2 frames out, one process per G
 an NCCL all-gather of that step's frames (the only collective of the path: frames are independent)."""
 from __future__ import annotations
 
+import contextlib
+import os
 from typing import Callable, Dict, Optional
 
 import torch
 
 from . import _capi as capi
 from .synthesis import RenderHead
+
+
+@contextlib.contextmanager
+def gpu_local_cpus(device_index: int = 0):
+    """Run the body on CPUs of the GPU's NUMA node (as far as the process may use them), then restore the affinity.
+
+    Pinned host buffers are placed on the node of the allocating thread; staging buffers on the far socket cost a third of the
+    PCIe rate on two-socket hosts.  Wrap only the ALLOCATION: `with gpu_local_cpus(i): buf = torch.empty(..., pin_memory=True)`.
+    Anything unexpected (no sysfs entry, empty intersection, no permission) leaves the affinity untouched."""
+    old = None
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        addr = f'{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0'
+        txt = open(f'/sys/bus/pci/devices/{addr}/local_cpulist').read().strip()
+        local = set()
+        for part in txt.split(','):
+            if part:
+                lo, _, hi = part.partition('-')
+                local.update(range(int(lo), int(hi or lo) + 1))
+        cur = os.sched_getaffinity(0)
+        both = cur & local
+        if both and both != cur:
+            os.sched_setaffinity(0, both)
+            old = cur
+    except Exception:
+        old = None
+    try:
+        yield
+    finally:
+        if old is not None:
+            try:
+                os.sched_setaffinity(0, old)
+            except Exception:
+                pass
 
 
 def default_sr_mode() -> str:
@@ -34,12 +70,15 @@ class FrameEngine:
         self.graph = None
         self.launches_per_step = 0
         self.s_planes = self.s_cams = self.s_u = self.s_out = None
+        self.inplace = {}                 # (planes ptr, cameras ptr, jitter ptr) -> (graph, output, the input tensors kept alive): see prepare()
+        self._pool = None
 
     def load_params(self, decoder_params: Dict[str, torch.Tensor], sr_params: Dict[str, torch.Tensor]) -> None:
         sd = {'decoder.' + k: v for k, v in decoder_params.items()}
         sd.update({'superresolution.' + k: v for k, v in sr_params.items()})
         self.head.load_state_dict(sd, strict=True)
         self.graph = None
+        self.inplace = {}
         sr = self.head.superresolution
         sr.static_prepared = None
         if self.static_styles and sr.sr_mode == 'tc':
@@ -50,23 +89,48 @@ class FrameEngine:
 
     @torch.no_grad()
     def _body(self, planes, cameras, u_coarse) -> torch.Tensor:
-        return self.head.synthesis(planes, cameras, u_coarse=u_coarse)['image']
+        return self.head.synthesis(planes, cameras, u_coarse=u_coarse, lean=True)['image']
 
-    def _capture(self, planes, cameras, u_coarse) -> None:
-        self.s_planes, self.s_cams, self.s_u = planes.clone(), cameras.clone(), u_coarse.clone()
+    def _capture_graph(self, planes, cameras, u_coarse):
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):                                       # warm-up outside capture: lazy inits (func attributes, driver entry points)
-                self._body(self.s_planes, self.s_cams, self.s_u)
+                self._body(planes, cameras, u_coarse)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()               # all step graphs share one pool: they never run concurrently
         c0 = capi.lib().r3dp_launch_count()
-        with torch.cuda.graph(g):
-            self.s_out = self._body(self.s_planes, self.s_cams, self.s_u)
+        with torch.cuda.graph(g, pool=self._pool):
+            out = self._body(planes, cameras, u_coarse)
         self.launches_per_step = int(capi.lib().r3dp_launch_count() - c0)      # libr3dp kernels inside one replay
-        self.graph = g
+        return g, out
+
+    def _capture(self, planes, cameras, u_coarse) -> None:
+        self.s_planes, self.s_cams, self.s_u = planes.clone(), cameras.clone(), u_coarse.clone()
+        self.graph, self.s_out = self._capture_graph(self.s_planes, self.s_cams, self.s_u)
+
+    @staticmethod
+    def _key(planes, cameras, u_coarse):
+        return (planes.data_ptr(), cameras.data_ptr(), u_coarse.data_ptr())
+
+    @torch.no_grad()
+    def prepare(self, inputs, max_graphs: int = 32) -> int:
+        """Zero-copy steps for RESIDENT inputs: capture one step graph per (planes, cameras, u_coarse) triple that reads those very
+        buffers, so `step()` on them replays without first copying 100 MB of planes into the static graph inputs.  The tensors are
+        kept referenced (their addresses stay valid); refill them in place between steps.  Returns the number of graphs held."""
+        if not self.use_graph:
+            return 0
+        for planes, cameras, u_coarse in inputs:
+            k = self._key(planes, cameras, u_coarse)
+            if k in self.inplace or len(self.inplace) >= max_graphs or planes.shape[0] != self.batch:
+                continue
+            assert planes.is_contiguous() and cameras.is_contiguous() and u_coarse.is_contiguous()
+            g, out = self._capture_graph(planes, cameras, u_coarse)
+            self.inplace[k] = (g, out, (planes, cameras, u_coarse))
+        return len(self.inplace)
 
     @torch.no_grad()
     def step(self, planes: torch.Tensor, cameras: torch.Tensor, u_coarse: Optional[torch.Tensor] = None, u_fine=None) -> torch.Tensor:
@@ -76,7 +140,11 @@ class FrameEngine:
             S = self.head.rendering_kwargs['depth_resolution']
             u_coarse = torch.rand(planes.shape[0], self.head.neural_rendering_resolution ** 2, S, 1, device=planes.device)
         graphable = self.use_graph and capi.PROF is None and u_fine is None and planes.shape[0] == self.batch
-        if graphable:
+        hit = self.inplace.get(self._key(planes, cameras, u_coarse)) if (graphable and self.inplace) else None
+        if hit is not None:
+            hit[0].replay()
+            out = hit[1]
+        elif graphable:
             if self.graph is None:
                 self._capture(planes, cameras, u_coarse)
             if planes.data_ptr() != self.s_planes.data_ptr():
@@ -155,6 +223,7 @@ class FrameEngine:
             hp['stage'][k] = (torch.empty_like(h_planes, device=self.device), torch.empty_like(h_cameras, device=self.device),
                               torch.empty_like(h_u, device=self.device))
             hp['out'][k] = torch.empty(self.batch, 3, 512, 512, device=self.device)
+            self.prepare([hp['stage'][k]])                             # the step reads the staging slot in place (no device-side input copy)
             hp['in_free'][k].record(cur); hp['out_free'][k].record(cur)
         sp, sc, su = hp['stage'][k]
         with torch.cuda.stream(hp['copy_in']):

@@ -59,8 +59,19 @@ class RenderHead(torch.nn.Module):
         res = self.neural_rendering_resolution
         ray_o, ray_d = self.ray_sampler(cam2world, intrinsics, res)
         N = ray_o.shape[0]
+        lean = bool(render_overrides.pop('lean', False))
         opts = dict(self.rendering_kwargs, **render_overrides)
         feat, depth, wsum, valid = self.renderer(planes, self.decoder, ray_o, ray_d, opts)
+        if lean and not self.torso and self.superresolution.sr_mode == 'tc' and not self.hparams.get('mask_invalid_rays', False):
+            # frame-loop fast path (FrameEngine): only ret['image'] is wanted, so the NCHW copies of the feature / weight images, the
+            # clamped raw image and the per-call ones_ws are not materialised; the SR reads the renderer's channels-last output directly
+            x_nhwc = feat.view(N, res, res, feat.shape[-1])
+            if getattr(self, '_ones_ws', None) is None or self._ones_ws.shape[0] != N or self._ones_ws.device != feat.device:
+                self._ones_ws = torch.ones(N, 14, self.hparams['w_dim'], device=feat.device)
+            sr_image = self.superresolution(x_nhwc[..., :3].permute(0, 3, 1, 2), x_nhwc.permute(0, 3, 1, 2), self._ones_ws, noise_mode='none',
+                                            x_nhwc=x_nhwc)
+            ret.update({'image': sr_image.clamp_(-1, 1), 'is_ray_valid': valid})
+            return ret
         feature_image = feat.permute(0, 2, 1).reshape(N, feat.shape[-1], res, res).contiguous()
         weights_image = wsum.permute(0, 2, 1).reshape(N, 1, res, res).contiguous()
         depth_image = depth.permute(0, 2, 1).reshape(N, 1, res, res)

@@ -358,6 +358,15 @@ def test_frame_engine_graph_and_host_pipeline_match_eager():
         eng.step_host(hp[i:i + B], hc[i:i + B], hu[i:i + B], outs[k])
     eng.sync_host()
     assert torch.equal(torch.cat(outs), ref.cpu())
+    # zero-copy resident inputs: one graph per prepared (planes, cameras, jitter) triple, replayed on the caller's own buffers
+    n_graphs = eng.prepare([(planes[i:i + B], cams[i:i + B], u[i:i + B]) for i in range(0, F, B)])
+    assert n_graphs >= F // B
+    got2 = torch.cat([eng.step(planes[i:i + B], cams[i:i + B], u[i:i + B]).clone() for i in range(0, F, B)])
+    assert torch.equal(got2, ref)
+    planes[0:B].mul_(0.5)                                                     # refilled in place -> the same graph sees the new data
+    ref0 = eager.step(planes[0:B], cams[0:B], u[0:B]).clone()
+    assert torch.equal(eng.step(planes[0:B], cams[0:B], u[0:B]), ref0)
+    planes[0:B].mul_(2.0)
     # clip helper (world = 1): frames land at their global indices
     clip = render_clip(lambda idx: eng.step(planes[idx.to(DEV)], cams[idx.to(DEV)], u[idx.to(DEV)]).clone(), F, B, 1, 0)
     assert torch.equal(clip, ref)

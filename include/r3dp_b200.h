@@ -89,7 +89,12 @@ int r3dp_decode(const float* feat, int N, int K, int P, int C, const r3dp_mlp_t*
  * outputs: rgb [N,M,out_dim] (already scaled to [-1,1]), depth [N,M,1], weights_sum [N,M,1], is_ray_valid [N,M]
  * (uint8 0/1).  Batch-global quirks are reproduced per call: invalid rays inherit min/max of the valid ray starts
  * (renderer.py:123-126) and depth is clamped to the call-wide [min,max] sample depth (ray_marcher.py:50).
- * workspace: r3dp_render_workspace_bytes(N, M) bytes of scratch. */
+ * workspace: r3dp_render_workspace_bytes(N, M) bytes of scratch.
+ * Decoder arithmetic: single-pass renders (S_imp == 0, 8*S <= 384) run the OSGDecoder GEMMs on tcgen05 with every fp32 operand split
+ * into two fp16 halves (three partial products, fp32 accumulation in TMEM) - fp32-grade results (rgb within 1e-6 of the CUDA-core
+ * decoder); two-pass renders use the fp32 CUDA-core decoder.  R3DP_MLP=const|smem forces the CUDA-core variants.  The scaled decoder
+ * weights are staged in process-wide device storage at the start of every call: calls with DIFFERENT decoders must not overlap on
+ * different streams of one process. */
 size_t r3dp_render_workspace_bytes(int N, int M);
 int r3dp_render(const float* planes_cl, int N, int C, int H, int W,
                 const float* ray_o, const float* ray_d, const float* camera, int M, int res,

@@ -90,9 +90,10 @@ int r3dp_decode(const float* feat, int N, int K, int P, int C, const r3dp_mlp_t*
  * (uint8 0/1).  Batch-global quirks are reproduced per call: invalid rays inherit min/max of the valid ray starts
  * (renderer.py:123-126) and depth is clamped to the call-wide [min,max] sample depth (ray_marcher.py:50).
  * workspace: r3dp_render_workspace_bytes(N, M) bytes of scratch.
- * Decoder arithmetic: single-pass renders (S_imp == 0, 8*S <= 384) run the OSGDecoder GEMMs on tcgen05 with every fp32 operand split
- * into two fp16 halves (three partial products, fp32 accumulation in TMEM) - fp32-grade results (rgb within 1e-6 of the CUDA-core
- * decoder); two-pass renders use the fp32 CUDA-core decoder.  R3DP_MLP=const|smem forces the CUDA-core variants.  The scaled decoder
+ * Decoder arithmetic: the OSGDecoder GEMMs run on tcgen05 with every fp32 operand split into two fp16 halves (three partial products,
+ * fp32 accumulation in TMEM) - fp32-grade results (rgb within 2e-6 of the CUDA-core decoder) - whenever the CTA's ray tile fits
+ * (single pass: R*S <= 384 samples; two passes: <= 256 samples per pass); other shapes, and R3DP_MLP=const|smem, use the fp32
+ * CUDA-core decoder.  The scaled decoder
  * weights are staged in process-wide device storage at the start of every call: calls with DIFFERENT decoders must not overlap on
  * different streams of one process. */
 size_t r3dp_render_workspace_bytes(int N, int M);

@@ -182,20 +182,36 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
     // TC layout (1024-aligned): [A1 tiles | decoded rows] [A2 atoms | tap descriptors | march scratch] [W image + biases] dep rayf barriers
     uint8_t* a1 = nullptr; uint8_t* a2 = nullptr; uint8_t* wimg = nullptr; float* dsc = nullptr; float* b1s = nullptr; float* b2s = nullptr;
     uint64_t* bar1 = nullptr; uint64_t* bar2 = nullptr; uint32_t* tmem_slot = nullptr;
+    // TC, two passes (importance sampling): the decoded rows of pass 1 must survive pass 2, so they get their own region (and hold the
+    // tap descriptors of the samples in flight, like the CUDA-core variants); A2 reuses the (by then consumed) A1 tiles instead:
+    //   [A1 tiles (2) = A2 atoms] [W image + biases] rows dep wts cdf rayf ord barriers
+    const bool two_pass = TC && a.S_imp > 0;
     if (TC) {
         a1 = tc::align_smem_1024(reinterpret_cast<uint8_t*>(smem));
-        a2 = a1 + kTcA1Bytes;
-        wimg = a2 + kTcA2Bytes;
-        rows = reinterpret_cast<float*>(a1);
-        dsc = reinterpret_cast<float*>(a2);                                   // [nsamp][16]  (<= 24 KB)
-        wts = reinterpret_cast<float*>(a2 + 24576);                           // [R*ST]  march scratch (the atoms are dead by then)
-        cdf = wts + R * ST;
-        b1s = reinterpret_cast<float*>(wimg + 20480); b2s = b1s + kHidden;
-        dep = b2s + 48;
-        rayf = dep + R * ST;
-        bar1 = reinterpret_cast<uint64_t*>(rayf + R * 8); bar2 = bar1 + kTcMaxTiles;
+        if (!two_pass) {
+            a2 = a1 + kTcA1Bytes;
+            wimg = a2 + kTcA2Bytes;
+            rows = reinterpret_cast<float*>(a1);
+            dsc = reinterpret_cast<float*>(a2);                               // [nsamp][16]  (<= 24 KB)
+            wts = reinterpret_cast<float*>(a2 + 24576);                       // [R*ST]  march scratch (the atoms are dead by then)
+            cdf = wts + R * ST;
+            b1s = reinterpret_cast<float*>(wimg + 20480); b2s = b1s + kHidden;
+            dep = b2s + 48;
+            rayf = dep + R * ST;
+            bar1 = reinterpret_cast<uint64_t*>(rayf + R * 8);
+            ord = nullptr;
+        } else {
+            a2 = a1;
+            wimg = a1 + kTcA2Bytes;
+            b1s = reinterpret_cast<float*>(wimg + 20480); b2s = b1s + kHidden;
+            rows = b2s + 48;
+            dep = rows + R * ST * kRow; wts = dep + R * ST; cdf = wts + R * ST;
+            rayf = cdf + R * ST;
+            ord = reinterpret_cast<int*>(rayf + R * 8);
+            bar1 = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(a1) + ((reinterpret_cast<uint8_t*>(ord + R * ST) - a1 + 7) & ~7));
+        }
+        bar2 = bar1 + kTcMaxTiles;
         tmem_slot = reinterpret_cast<uint32_t*>(bar2 + kTcMaxTiles);
-        ord = nullptr;                                                        // single pass only
     }
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -276,7 +292,7 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
             const float y = __fadd_rn(rf[1], __fmul_rn(d, rf[4]));
             const float z = __fadd_rn(rf[2], __fmul_rn(d, rf[5]));
             const float gx = pv.scale * x, gy = pv.scale * y, gz = pv.scale * z;
-            float* row = TC ? dsc + q * 16 : rows + (size_t)(r * ST + k) * kRow;
+            float* row = (TC && !two_pass) ? dsc + q * 16 : rows + (size_t)(r * ST + k) * kRow;
             tap_desc(gx, gy, pv.H, pv.W, 0, row);                      // plane 0 <- (x, y)   (renderer.py:30-63)
             tap_desc(gx, gz, pv.H, pv.W, 1, row + 5);                  // plane 1 <- (x, z)
             tap_desc(gz, gx, pv.H, pv.W, 2, row + 10);                 // plane 2 <- (z, x)
@@ -289,7 +305,7 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
             const int q = q4 + sub;
             if (q < nsamp) {
                 const int r = q / kn, k = k0 + (q - r * kn);
-                float* row = TC ? dsc + q * 16 : rows + (size_t)(r * ST + k) * kRow;
+                float* row = (TC && !two_pass) ? dsc + q * 16 : rows + (size_t)(r * ST + k) * kRow;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 float dsc[15];
 #pragma unroll
@@ -329,6 +345,7 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
         if (TC) {
             // ---- decoder on the tensor core ---------------------------------------------------------------------------------------------
             const int nt = (nsamp + 127) >> 7;
+            const uint32_t ph = k0 > 0 ? 1u : 0u;                               // every barrier completes once per pass
             asm volatile("cp.async.wait_group 0;" ::: "memory");                // the weight image has landed
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // this thread's A1 (and W) stores -> visible to the async proxy
             tc::tc_fence_before();
@@ -358,7 +375,7 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
             const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
             for (int t = 0; t <= nt; ++t) {
                 if (t < nt) {
-                    tc::mbar_wait(&bar1[t], 0);
+                    tc::mbar_wait(&bar1[t], ph);
                     tc::tc_fence_after();
                     uint32_t v[32];
                     tc::tc_ld32(lane_addr + 64 * t + 32 * g, v);                // hidden units [32g, 32g+32) of this sample, pre-activation
@@ -372,7 +389,8 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
                         const __half2 ll = __floats2half2_rn(h0 - hf.x, h1 - hf.y);
                         hi[i] = *reinterpret_cast<const uint32_t*>(&hh); lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
                     }
-                    if (t >= 1) { tc::mbar_wait(&bar2[t - 1], 0); tc::tc_fence_after(); }   // layer 2 of the previous tile has read A2
+                    if (t >= 1) { tc::mbar_wait(&bar2[t - 1], ph); tc::tc_fence_after(); }  // layer 2 of the previous tile has read A2
+                    else if (two_pass) tc::mbar_wait(&bar1[nt - 1], ph);        // A2 overlays the A1 tiles: every layer-1 MMA must have retired
                     uint8_t* rp = a2 + (trow >> 3) * 1024 + (trow & 7) * 128;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -404,8 +422,8 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
                 }
                 if (t >= 1) {
                     // outputs of tile t-1 (its layer 2 overlapped the epilogue above): bias, sigma raw, colours through the scaled sigmoid
-                    if (t == 1) tc::mbar_wait(&bar1[nt - 1], 0);                // rows alias the A1 tiles: every layer-1 MMA must have retired
-                    if (t == nt) tc::mbar_wait(&bar2[nt - 1], 0);
+                    if (t == 1) tc::mbar_wait(&bar1[nt - 1], ph);               // rows alias the A1 tiles: every layer-1 MMA must have retired
+                    if (t == nt) tc::mbar_wait(&bar2[nt - 1], ph);
                     tc::tc_fence_after();
                     uint32_t v[32];
                     tc::tc_ld32(lane_addr + 64 * (t - 1) + 16 * g, v);
@@ -637,9 +655,21 @@ static int mlp_variant() {                         // R3DP_MLP = tc (default) | 
 }
 static bool mlp_in_const() { return mlp_variant() != 0; }
 
+static size_t render_tc_smem(int R, int S, int S_imp) {
+    const int ST = S + S_imp;
+    if (S_imp == 0) return 1024 + kTcA1Bytes + kTcA2Bytes + 20480 + (kHidden + 48) * 4 + (size_t)R * (S + 8) * 4 + 2 * kTcMaxTiles * 8 + 16;
+    return 1024 + kTcA2Bytes + 20480 + (kHidden + 48) * 4 + (size_t)R * ST * (kRow + 4) * 4 + (size_t)R * 8 * 4 + 8 + 2 * kTcMaxTiles * 8 + 16;
+}
+// the tensor-core decoder needs its CTA tile to fit the A tiles: three 128-sample tiles for single-pass renders (decoded rows overlay
+// them), two per pass for importance renders; and two CTAs per SM (TMEM: 2 x 256 columns)
+static bool render_tc_fits(int R, int S, int S_imp) {
+    if (S_imp == 0) return R * S <= 128 * kTcMaxTiles && R * S * kRow * 4 <= kTcA1Bytes;
+    const int per_pass = R * (S > S_imp ? S : S_imp);
+    return per_pass <= 256 && render_tc_smem(R, S, S_imp) <= 113 * 1024;
+}
 template <int R>
 static int launch_render_tc(const RenderArgs& a, cudaStream_t st) {
-    const size_t smem = 1024 + kTcA1Bytes + kTcA2Bytes + 20480 + (kHidden + 48) * 4 + (size_t)R * (a.S + 8) * 4 + 2 * kTcMaxTiles * 8 + 16;
+    const size_t smem = render_tc_smem(R, a.S, a.S_imp);
     R3DP_CUDA(cudaFuncSetAttribute(render_kernel<R, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MlpTcImage* dst = nullptr;
     R3DP_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&dst), g_mlp_tc));
@@ -669,8 +699,7 @@ static int launch_render_v(const RenderArgs& a, cudaStream_t st) {
 template <int R>
 static int launch_render(const RenderArgs& a, cudaStream_t st) {
     if (!mlp_in_const()) return launch_render_v<R, false, false>(a, st);
-    // tensor-core decoder: single-pass renders whose CTA tile fits three 128-sample MMA tiles
-    if (mlp_variant() == 2 && a.S_imp == 0 && R * a.S <= 128 * kTcMaxTiles && R * a.S * kRow * 4 <= kTcA1Bytes) return launch_render_tc<R>(a, st);
+    if (mlp_variant() == 2 && render_tc_fits(R, a.S, a.S_imp)) return launch_render_tc<R>(a, st);
     const int per_pass = R * (a.S_imp > 0 && a.S_imp < a.S ? a.S_imp : a.S);          // the smaller pass decides
     return per_pass >= 2 * kRenderThreads ? launch_render_v<R, true, true>(a, st) : launch_render_v<R, true, false>(a, st);
 }

@@ -315,7 +315,7 @@ def main():
     line = {
         'metric': 'rendered frames/sec @512^2 (64^2 NeRF, 48 samples/ray)', 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32 render; SR ' + ('f16 operands / f32 accumulate (tcgen05)' if sr_mode == 'tc' else 'f32'),
+        'vs_baseline': None, 'dtype': 'f32 render (decoder GEMMs: split-fp16 operands on tcgen05, f32 accumulate, f32-grade results); SR ' + ('f16 operands / f32 accumulate (tcgen05)' if sr_mode == 'tc' else 'f32'),
         'data': 'synthetic',
         'config': config_of(args, {'sr_mode': sr_mode, 'cuda_graph': not args.no_graph, 'l2_policy': f'inputs larger than L2: {P} distinct resident frames/GPU '
                                    f'({P * 25.2:.0f} MB) cycled', 'timing': 'CUDA events on the launch stream, barrier+sync both sides, max over ranks'}),

@@ -71,3 +71,27 @@ def test_torso_head_state_dict_layout():
     with pytest.raises(NotImplementedError):
         r3.SuperresolutionHybrid8XDC_Warp(channels=32, img_resolution=512, sr_num_fp16_res=0, sr_antialias=True,
                                           hp=dict(syn.WARP_HPARAMS, htbsr_head_weight_fuse_mode='v3'))
+
+
+def test_gpu_local_cpus_is_a_noop_without_a_gpu_and_restores_affinity():
+    """engine.gpu_local_cpus(): anything unexpected (no CUDA device, no sysfs entry) must leave the CPU affinity untouched."""
+    import os
+    from real3dportrait_b200 import engine
+    before = os.sched_getaffinity(0)
+    with engine.gpu_local_cpus(0):
+        inside = os.sched_getaffinity(0)
+    assert os.sched_getaffinity(0) == before and inside <= before
+
+
+def test_bench_clock_sampler_reports_without_nvml():
+    """bench.ClockSampler must come up and summarise even when neither NVML nor nvidia-smi can be reached (CPU container)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    s.start()
+    out = s.summary()
+    assert set(out) >= {'sm_mhz', 'sm_max_mhz', 'reasons', 'samples', 'source'} and out['source'] in ('nvml', 'nvidia-smi')
+    assert bench.host_threads() >= 1

@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
 
     if (!CONST) load_mlp_smem(mlp, a.mlp, tid, kRenderThreads);
     uint32_t tmem_base = 0;
+    uint32_t tc_par = 0;                                   // bit t = parity of the phase bar1[t] / bar2[t] complete next (one use per pass)
     if (TC) {
         if (tid == 0) {
             for (int i = 0; i < kTcMaxTiles; ++i) { tc::mbar_init(&bar1[i], 1); tc::mbar_init(&bar2[i], 1); }
@@ -345,7 +346,10 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
         if (TC) {
             // ---- decoder on the tensor core ---------------------------------------------------------------------------------------------
             const int nt = (nsamp + 127) >> 7;
-            const uint32_t ph = k0 > 0 ? 1u : 0u;                               // every barrier completes once per pass
+            // barriers t < nt complete once in this pass; a pass with fewer tiles leaves the others untouched, so the parity is kept per
+            // barrier (a wait on the wrong parity of a never-used barrier would fall through)
+            const uint32_t par = tc_par;
+            tc_par ^= (1u << nt) - 1u;
             asm volatile("cp.async.wait_group 0;" ::: "memory");                // the weight image has landed
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // this thread's A1 (and W) stores -> visible to the async proxy
             tc::tc_fence_before();
@@ -375,7 +379,7 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
             const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
             for (int t = 0; t <= nt; ++t) {
                 if (t < nt) {
-                    tc::mbar_wait(&bar1[t], ph);
+                    tc::mbar_wait(&bar1[t], (par >> t) & 1u);
                     tc::tc_fence_after();
                     uint32_t v[32];
                     tc::tc_ld32(lane_addr + 64 * t + 32 * g, v);                // hidden units [32g, 32g+32) of this sample, pre-activation
@@ -389,8 +393,8 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
                         const __half2 ll = __floats2half2_rn(h0 - hf.x, h1 - hf.y);
                         hi[i] = *reinterpret_cast<const uint32_t*>(&hh); lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
                     }
-                    if (t >= 1) { tc::mbar_wait(&bar2[t - 1], ph); tc::tc_fence_after(); }  // layer 2 of the previous tile has read A2
-                    else if (two_pass) tc::mbar_wait(&bar1[nt - 1], ph);        // A2 overlays the A1 tiles: every layer-1 MMA must have retired
+                    if (t >= 1) { tc::mbar_wait(&bar2[t - 1], (par >> (t - 1)) & 1u); tc::tc_fence_after(); }  // layer 2 of the previous tile has read A2
+                    else if (two_pass) tc::mbar_wait(&bar1[nt - 1], (par >> (nt - 1)) & 1u);        // A2 overlays the A1 tiles: every layer-1 MMA must have retired
                     uint8_t* rp = a2 + (trow >> 3) * 1024 + (trow & 7) * 128;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -422,8 +426,8 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
                 }
                 if (t >= 1) {
                     // outputs of tile t-1 (its layer 2 overlapped the epilogue above): bias, sigma raw, colours through the scaled sigmoid
-                    if (t == 1) tc::mbar_wait(&bar1[nt - 1], ph);               // rows alias the A1 tiles: every layer-1 MMA must have retired
-                    if (t == nt) tc::mbar_wait(&bar2[nt - 1], ph);
+                    if (t == 1) tc::mbar_wait(&bar1[nt - 1], (par >> (nt - 1)) & 1u);               // rows alias the A1 tiles: every layer-1 MMA must have retired
+                    if (t == nt) tc::mbar_wait(&bar2[nt - 1], (par >> (nt - 1)) & 1u);
                     tc::tc_fence_after();
                     uint32_t v[32];
                     tc::tc_ld32(lane_addr + 64 * (t - 1) + 16 * g, v);

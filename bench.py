@@ -200,7 +200,8 @@ def main():
     _capi.check(L.r3dp_device_info(None, None, None))
 
     sr_mode = args.sr_mode or engine.default_sr_mode()
-    eng = engine.FrameEngine(batch=args.batch, sr_mode=sr_mode, device=dev, world=world, rank=rank, dist=dist, use_graph=not args.no_graph)
+    eng = engine.FrameEngine(batch=args.batch, sr_mode=sr_mode, device=dev, world=world, rank=rank, dist=dist, use_graph=not args.no_graph,
+                             hp={'num_samples_fine': 0})
     eng.load_params(syn.make_decoder_params(seed=4), syn.make_sr_params(seed=5))
     B, P = args.batch, max(args.pool, args.batch)
     # resident inputs: every rank owns its own shard of the clip (different seeds per rank)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define R3DP_ABI_VERSION 1
+#define R3DP_ABI_VERSION 2
 
 typedef void* r3dp_stream_t; /* cudaStream_t */
 
@@ -47,6 +47,9 @@ const char* r3dp_last_error(void);
 int r3dp_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Running total of CUDA kernels this library has launched in the process (bench.py's `gpu_launches`). */
 unsigned long long r3dp_launch_count(void);
+/* A/B switches for profiling runs (same meaning as the R3DP_* environment variables, settable at run time):
+ *   "render": 0 = streaming kernel for single-pass renders (default), 1 = CTA-per-ray-tile kernel;  "rs_d": 4 | 8 | 16 samples per ray and tile */
+int r3dp_set_option(const char* key, int value);
 
 /* ---------------------------------------------------------------------------------------------------- rays ---
  * RaySampler.forward (modules/eg3ds/volumetric_rendering/ray_sampler.py:24-63).
@@ -90,13 +93,41 @@ int r3dp_decode(const float* feat, int N, int K, int P, int C, const r3dp_mlp_t*
  * (uint8 0/1).  Batch-global quirks are reproduced per call: invalid rays inherit min/max of the valid ray starts
  * (renderer.py:123-126) and depth is clamped to the call-wide [min,max] sample depth (ray_marcher.py:50).
  * workspace: r3dp_render_workspace_bytes(N, M) bytes of scratch.
- * Decoder arithmetic: the OSGDecoder GEMMs run on tcgen05 with every fp32 operand split into two fp16 halves (three partial products,
- * fp32 accumulation in TMEM) - fp32-grade results (rgb within 2e-6 of the CUDA-core decoder) - whenever the CTA's ray tile fits
- * (single pass: R*S <= 384 samples; two passes: <= 256 samples per pass); other shapes, and R3DP_MLP=const|smem, use the fp32
- * CUDA-core decoder.  The scaled decoder
- * weights are staged in process-wide device storage at the start of every call: calls with DIFFERENT decoders must not overlap on
- * different streams of one process. */
+ * Kernels: single-pass renders (S_imp == 0) run the warp-specialised streaming kernel (render_stream.cu: gather, tcgen05 decoder and
+ * ray march of consecutive 128-sample tiles overlap inside one persistent CTA per SM); importance renders run the CTA-per-ray-tile
+ * kernel (render.cu).  Decoder arithmetic: the OSGDecoder GEMMs run on tcgen05 with every fp32 operand split into two fp16 halves (three
+ * partial products, fp32 accumulation in TMEM) - fp32-grade results (rgb within 2e-6 of the CUDA-core decoder); two-pass shapes whose
+ * tiles do not fit use the fp32 CUDA-core decoder.  The prepared decoder operands live in the caller's `workspace`, so calls with
+ * different decoders may run concurrently on different streams (each with its own workspace).
+ * A/B knobs (read once per process): R3DP_RENDER=tile, R3DP_RS_D=4|8|16, R3DP_MLP=tc|smem|const (const keeps process-wide state). */
 size_t r3dp_render_workspace_bytes(int N, int M);
+
+/* Channels-last plane addressing, strides in floats: the C = 32 features of texel (plane p, row y, col x) of frame n start at
+ *   planes + n*frame_stride + p*plane_stride + y*row_stride + x*texel_stride      (every stride a multiple of 4 floats).
+ *   [N,3,H,W,C] (r3dp_planes_to_channels_last)                      plane = H*W*C, row = W*C,   texel = C
+ *   [N,H,W,3,C] = the producer's [N,3*C,H,W] conv output held in torch.channels_last memory (secc_img2plane.py:73-81,
+ *                 segformer.py:704-733 emit [B,3,C,H,W] views of such a tensor): plane = C, row = W*3*C, texel = 3*C  -> no repack at all
+ *   frame_stride = 0: one plane set shared by every frame of the call (the per-clip canonical planes). */
+typedef struct r3dp_plane_layout {
+    long long frame_stride;
+    int plane_stride, row_stride, texel_stride;
+} r3dp_plane_layout_t;
+
+/* r3dp_render with explicit plane layouts and an optional SECOND plane set sampled at the same points and added to the first
+ * (bilinear sampling is linear): `planes = cano_planes + secc_planes` (secc_img2plane.py:73-81) without the 75 MB/frame add. */
+typedef struct r3dp_render_args {
+    const float* planes;  r3dp_plane_layout_t layout;
+    const float* planes2; r3dp_plane_layout_t layout2;   /* NULL = none; strides (except frame_stride) must equal `layout`'s */
+    int N, C, H, W;
+    const float* ray_o; const float* ray_d; const float* camera; int M, res;
+    int S, S_imp; float box_warp; int white_back;
+    const float* u_coarse; const float* u_fine;
+    const r3dp_mlp_t* mlp;
+    float* rgb; float* depth; float* weights_sum; uint8_t* is_ray_valid;
+    void* workspace; size_t workspace_bytes;
+} r3dp_render_args_t;
+int r3dp_render_ex(const r3dp_render_args_t* args, r3dp_stream_t stream);
+
 int r3dp_render(const float* planes_cl, int N, int C, int H, int W,
                 const float* ray_o, const float* ray_d, const float* camera, int M, int res,
                 int S, int S_imp, float box_warp, int white_back,
@@ -179,6 +210,13 @@ int r3dp_sr_tc_layer_torgb(const void* x_f16, const void* wp_f16, const float* b
 int r3dp_sr_tc_input_nhwc(const float* x_nhwc, int N, int C, int h, int w, int size, void* y_f16, r3dp_stream_t stream);
 int r3dp_sr_tc_last_layer(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
                           const float* img_prev, int N, int Nw, int I, int H, int W, float* img_out, r3dp_stream_t stream);
+/* The same with the caller loop's output conversion fused into the epilogue (inference/real3d_infer.py:515-519):
+ *   clamp != 0       img_out clamped to [-1, 1] (imgs.clamp(-1,1))
+ *   img_out_u8       non-NULL: write uint8 HWC video frames [N,H,W,3] = uint8(int((clamp(x) + 1) / 2 * 255)) INSTEAD of the fp32 image
+ *                    (4x fewer bytes to gather / copy to the host); img_out may then be NULL. */
+int r3dp_sr_tc_last_layer_ex(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
+                             const float* img_prev, int N, int Nw, int I, int H, int W, float* img_out, uint8_t* img_out_u8, int clamp,
+                             r3dp_stream_t stream);
 
 /* Measurement hooks (bench.py): time every tensor-core conv launch with a CUDA-event pair on its launching stream. */
 int r3dp_sr_tc_prof(int enable);
@@ -202,6 +240,9 @@ int r3dp_sr_tc_layer_torgb_noup(const void* x_f16, const void* wp_f16, const flo
                                 r3dp_stream_t stream);
 int r3dp_sr_alpha_cat(const void* xa_f16, int Ca, int stride_a, const void* xb_f16, int Cb, int stride_b, const float* alpha, int N,
                       int H, int W, void* out_f16, r3dp_stream_t stream);
+/* xb_shared != 0: xb holds ONE frame [1,H,W,Cb] read by every frame of the batch (per-clip constant features, e.g. bg_encoder(ref_bg)). */
+int r3dp_sr_alpha_cat_ex(const void* xa_f16, int Ca, int stride_a, const void* xb_f16, int Cb, int stride_b, int xb_shared, const float* alpha,
+                         int N, int H, int W, void* out_f16, r3dp_stream_t stream);
 int r3dp_sr_blend(const float* a, const float* b, const float* alpha, int N, int C, int H, int W, float* out, r3dp_stream_t stream);
 int r3dp_sr_person_occlusion(const float* head_alpha, const float* torso_occlusion, float threshold, int N, int H, int W, float* out,
                              r3dp_stream_t stream);

@@ -23,6 +23,21 @@ class MlpStruct(C.Structure):
                 ('in_features', C.c_int), ('hidden', C.c_int), ('out_dim', C.c_int)]
 
 
+class PlaneLayout(C.Structure):
+    _fields_ = [('frame_stride', C.c_longlong), ('plane_stride', C.c_int), ('row_stride', C.c_int), ('texel_stride', C.c_int)]
+
+
+class RenderArgs(C.Structure):
+    """r3dp_render_args_t (include/r3dp_b200.h)."""
+    _fields_ = [('planes', C.c_void_p), ('layout', PlaneLayout), ('planes2', C.c_void_p), ('layout2', PlaneLayout),
+                ('N', C.c_int), ('C', C.c_int), ('H', C.c_int), ('W', C.c_int),
+                ('ray_o', C.c_void_p), ('ray_d', C.c_void_p), ('camera', C.c_void_p), ('M', C.c_int), ('res', C.c_int),
+                ('S', C.c_int), ('S_imp', C.c_int), ('box_warp', C.c_float), ('white_back', C.c_int),
+                ('u_coarse', C.c_void_p), ('u_fine', C.c_void_p), ('mlp', C.POINTER(MlpStruct)),
+                ('rgb', C.c_void_p), ('depth', C.c_void_p), ('weights_sum', C.c_void_p), ('is_ray_valid', C.c_void_p),
+                ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t)]
+
+
 _P, _I, _F, _Z = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 _M = C.POINTER(MlpStruct)
 #: name -> (restype, argtypes): a typed copy of include/r3dp_b200.h so ctypes rejects mis-ordered / mis-typed calls
@@ -31,6 +46,7 @@ _SIGNATURES = {
     'r3dp_last_error': (C.c_char_p, []),
     'r3dp_device_info': (_I, [C.POINTER(_I)] * 3),
     'r3dp_launch_count': (C.c_ulonglong, []),
+    'r3dp_set_option': (_I, [C.c_char_p, _I]),
     'r3dp_gen_rays': (_I, [_P, _P, _I, _I, _P, _P, _P]),
     'r3dp_planes_to_channels_last': (_I, [_P, _I, _I, _I, _I, _P, _P]),
     'r3dp_triplane_sample': (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _P, _P]),
@@ -38,6 +54,7 @@ _SIGNATURES = {
     'r3dp_decode': (_I, [_P, _I, _I, _I, _I, _M, _P, _P, _P]),
     'r3dp_render_workspace_bytes': (_Z, [_I, _I]),
     'r3dp_render': (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P, _M, _P, _P, _P, _P, _P, _Z, _P]),
+    'r3dp_render_ex': (_I, [C.POINTER(RenderArgs), _P]),
     'r3dp_ray_march': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     'r3dp_sr_styles': (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P]),
     'r3dp_sr_fold_weights': (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
@@ -57,6 +74,7 @@ _SIGNATURES = {
     'r3dp_sr_tc_conv': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'r3dp_sr_tc_layer_torgb_noup': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'r3dp_sr_alpha_cat': (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _P, _P]),
+    'r3dp_sr_alpha_cat_ex': (_I, [_P, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _P, _P]),
     'r3dp_sr_blend': (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     'r3dp_sr_person_occlusion': (_I, [_P, _P, _F, _I, _I, _I, _P, _P]),
     'r3dp_sr_resize_aa_down2': (_I, [_P, _I, _I, _I, _I, _P, _P]),
@@ -64,6 +82,7 @@ _SIGNATURES = {
     'r3dp_sr_tc_debug_buffer': (_I, [_P]),
     'r3dp_sr_tc_prof_read': (_I, [C.POINTER(C.c_float), C.POINTER(_I)]),
     'r3dp_sr_tc_last_layer': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    'r3dp_sr_tc_last_layer_ex': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
 }
 
 
@@ -85,7 +104,7 @@ def lib() -> C.CDLL:
         for name, (restype, argtypes) in _SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError here = header and library out of sync
             fn.restype, fn.argtypes = restype, argtypes
-        if L.r3dp_abi_version() != 1:
+        if L.r3dp_abi_version() != 2:
             raise RuntimeError('libr3dp_b200.so ABI version mismatch')
         _lib = L
     return _lib

@@ -3,9 +3,9 @@
 //   2. render_kernel       depths -> tri-plane gather -> OSG decoder -> ray march [-> importance pass -> merge -> march]
 //   3. depth_clamp_kernel  NaN->inf, clamp depth to the call-wide [min,max] sample depth (ray_marcher.py:49-50)
 // plus gen_rays (RaySampler.forward) and a stand-alone ray marcher.
-#include "render_core.cuh"
-#include "tc_prims.cuh"
+#include "render_shared.cuh"
 #include <stdlib.h>
+#include <string>
 
 namespace r3dp {
 
@@ -20,28 +20,8 @@ __global__ void mlp_to_const_kernel(const r3dp_mlp_t m, MlpConst* dst) {
     for (int i = tid; i < kOut; i += nt) dst->b2[i] = m.b2[i];
 }
 
-// ---- tensor-core decoder (R3DP_MLP=tc, default for single-pass renders) -----------------------------------------------------------
-// The OSG decoder is two GEMMs over the samples: [M x 32] x [32 x 64] -> softplus -> [M x 64] x [64 x 33].  They run on tcgen05 with
-// fp16 operands and fp32 accumulation in TMEM; fp32 accuracy is kept by splitting every operand into two fp16 halves
-// (v = hi + lo exactly to 2^-22 |v|) and summing the three significant partial products hi*hi + lo*hi + hi*lo (lo*lo ~ 2^-22 is dropped).
-// Operand images (K-major, 128-byte swizzle: one 128 B row = 64 fp16, 8-row groups 1024 B apart):
-//   A1 tile  128 samples x [x_hi(32) | x_lo(32)]             written by the gather
-//   W1       64 hidden   x [w_hi(32) | w_lo(32)]             k-steps 0,1 = hi, 2,3 = lo
-//   A2 tile  128 samples x [h_hi(64)] , [h_lo(64)]           two atoms, written by the layer-1 epilogue
-//   W2       48 outputs  x [w_hi(64)] , [w_lo(64)]           two atoms, rows >= 33 are zero (UMMA N must be a multiple of 16)
-struct alignas(16) MlpTcImage {
-    uint8_t w1[kHidden * 128];
-    uint8_t w2hi[48 * 128];
-    uint8_t w2lo[48 * 128];
-    float b1[kHidden];
-    float b2[48];
-};
-static_assert(sizeof(MlpTcImage) == 8192 + 6144 + 6144 + 256 + 192, "MlpTcImage layout");
-__device__ MlpTcImage g_mlp_tc;
 
-__device__ __forceinline__ uint32_t sw128_off(int row, int k) {                // byte offset of fp16 element (row, k) of a swizzled atom
-    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7))) << 4) + (k & 7) * 2);
-}
+
 __global__ void mlp_to_tc_kernel(const r3dp_mlp_t m, MlpTcImage* dst) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
     const float g1 = 0.17677669529663687f, g2 = 0.125f;        // 1/sqrt(32), 1/sqrt(64)  (networks_stylegan2.py:113)
@@ -66,17 +46,6 @@ constexpr int kTcThreads = 256;                          // 8 warps: TMEM lane q
 constexpr int kTcMaxTiles = 3;                           // 128-sample tiles per pass (TMEM: 64 columns each)
 constexpr int kTcA1Bytes = 51200;                        // 3 x 16 KB A1 tiles; later the [R*ST][33] fp32 decoded rows (<= 384 x 132 B)
 constexpr int kTcA2Bytes = 32768;                        // two 16 KB atoms; before the decode: tap descriptors [nsamp][16]; after: march scratch
-constexpr uint32_t kIdescL1 = (1u << 4) | ((uint32_t)(kHidden >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);    // M128 N64, f16 x f16 -> f32
-constexpr uint32_t kIdescL2 = (1u << 4) | ((uint32_t)(48 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);         // M128 N48
-
-struct RenderWs {          // lives at the start of the caller's workspace
-    unsigned t0_min, t0_max;   // ordered-uint encoded floats over valid rays
-    unsigned d_min, d_max;     // over every sample depth of the call
-    unsigned n_valid;
-    unsigned pad[3];
-};
-static_assert(sizeof(RenderWs) == 32, "ws header");
-
 __global__ void init_ws_kernel(RenderWs* ws) {
     ws->t0_min = 0xffffffffu; ws->t0_max = 0u; ws->d_min = 0xffffffffu; ws->d_max = 0u; ws->n_valid = 0u;
 }
@@ -91,16 +60,6 @@ __global__ void gen_rays_kernel(const float* __restrict__ c2w, const float* __re
     Ray r = make_ray(c2w + n * 16, K + n * 9, res, m);
     float* o = ray_o + (size_t)idx * 3; float* d = ray_d + (size_t)idx * 3;
     o[0] = r.ox; o[1] = r.oy; o[2] = r.oz; d[0] = r.dx; d[1] = r.dy; d[2] = r.dz;
-}
-
-__device__ __forceinline__ Ray fetch_ray(const float* __restrict__ ray_o, const float* __restrict__ ray_d,
-                                         const float* __restrict__ camera, int res, int n, int M, int m) {
-    if (ray_o != nullptr) {
-        const float* o = ray_o + ((size_t)n * M + m) * 3; const float* d = ray_d + ((size_t)n * M + m) * 3;
-        Ray r; r.ox = o[0]; r.oy = o[1]; r.oz = o[2]; r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
-        return r;
-    }
-    return make_ray(camera + n * 25, camera + n * 25 + 16, res, m);
 }
 
 __global__ void ray_limits_kernel(const float* __restrict__ ray_o, const float* __restrict__ ray_d,
@@ -139,17 +98,6 @@ __global__ void depth_clamp_kernel(float* __restrict__ depth, int n, const Rende
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-struct RenderArgs {
-    const float* planes; int N, H, W;
-    const float* ray_o; const float* ray_d; const float* camera; int M, res;
-    int S, S_imp; float box_warp; int white_back;
-    const float* u_coarse; const float* u_fine;
-    r3dp_mlp_t mlp;
-    float* rgb; float* depth; float* wsum;
-    const float2* limits; const uint8_t* valid; RenderWs* ws;
-    int tiles_per_frame, tile_cols;     // ray tiling (see ray_of)
-};
-
 constexpr int kRenderThreads = 192;
 
 // R rays per CTA.  If the rays form a res x res image we take them as a COLUMN strip (R rows, 1 col): planes 1 and 2
@@ -198,7 +146,7 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
             b1s = reinterpret_cast<float*>(wimg + 20480); b2s = b1s + kHidden;
             dep = b2s + 48;
             rayf = dep + R * ST;
-            bar1 = reinterpret_cast<uint64_t*>(rayf + R * 8);
+            bar1 = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(a1) + ((reinterpret_cast<uint8_t*>(rayf + R * 8) - a1 + 7) & ~7));
             ord = nullptr;
         } else {
             a2 = a1;
@@ -231,7 +179,7 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
         // decoder weight image (pre-swizzled fp16 hi/lo atoms + biases): 20 928 B from L2
-        const uint4* src = reinterpret_cast<const uint4*>(&g_mlp_tc);
+        const uint4* src = reinterpret_cast<const uint4*>(a.image);
         uint4* dst = reinterpret_cast<uint4*>(wimg);
         for (int i = tid; i < (int)(sizeof(MlpTcImage) / 16); i += kRenderThreads)       // LDGSTS: lands while the rays / depths / taps are computed
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(dst + i)), "l"(src + i) : "memory");
@@ -278,7 +226,10 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
     }
     __syncthreads();
 
-    PlaneView pv; pv.base = a.planes + (size_t)n * 3 * a.H * a.W * kC; pv.H = a.H; pv.W = a.W; pv.scale = 2.0f / a.box_warp;
+    const float* base0 = a.p0.base + (size_t)n * a.p0.frame_stride;
+    const float* base1 = a.p1.base ? a.p1.base + (size_t)n * a.p1.frame_stride : nullptr;     // optional second plane set (same strides)
+    const int rowstep = a.p0.row_stride, texstep = a.p0.texel_stride;
+    const float pscale = 2.0f / a.box_warp;
 
     // One "pass" = gather + decode for samples k in [k0, k0+kn) of every ray.
     auto run_pass = [&](int k0, int kn) {
@@ -292,11 +243,11 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
             const float x = __fadd_rn(rf[0], __fmul_rn(d, rf[3]));
             const float y = __fadd_rn(rf[1], __fmul_rn(d, rf[4]));
             const float z = __fadd_rn(rf[2], __fmul_rn(d, rf[5]));
-            const float gx = pv.scale * x, gy = pv.scale * y, gz = pv.scale * z;
+            const float gx = pscale * x, gy = pscale * y, gz = pscale * z;
             float* row = (TC && !two_pass) ? dsc + q * 16 : rows + (size_t)(r * ST + k) * kRow;
-            tap_desc(gx, gy, pv.H, pv.W, 0, row);                      // plane 0 <- (x, y)   (renderer.py:30-63)
-            tap_desc(gx, gz, pv.H, pv.W, 1, row + 5);                  // plane 1 <- (x, z)
-            tap_desc(gz, gx, pv.H, pv.W, 2, row + 10);                 // plane 2 <- (z, x)
+            tap_desc_s(gx, gy, a.H, a.W, 0, rowstep, texstep, row);                    // plane 0 <- (x, y)   (renderer.py:30-63)
+            tap_desc_s(gx, gz, a.H, a.W, a.p0.plane_stride, rowstep, texstep, row + 5);                // plane 1 <- (x, z)
+            tap_desc_s(gz, gx, a.H, a.W, 2 * a.p0.plane_stride, rowstep, texstep, row + 10);                // plane 2 <- (z, x)
         }
         __syncthreads();
         // (2) gather: each warp takes 4 samples per iteration, 8 lanes x float4 per sample; the row's descriptor is read by all 8
@@ -311,16 +262,27 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
                 float dsc[15];
 #pragma unroll
                 for (int e = 0; e < 15; ++e) dsc[e] = row[e];
-                const int rowstep = pv.W * kC;
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
-                    const float* b = pv.base + __float_as_int(dsc[5 * p]) + cq * 4;
-                    const float4 t00 = ldg_nc_f4(b), t10 = ldg_nc_f4(b + kC), t01 = ldg_nc_f4(b + rowstep), t11 = ldg_nc_f4(b + rowstep + kC);
+                    const float* b = base0 + __float_as_int(dsc[5 * p]) + cq * 4;
+                    const float4 t00 = ldg_nc_f4(b), t10 = ldg_nc_f4(b + texstep), t01 = ldg_nc_f4(b + rowstep), t11 = ldg_nc_f4(b + rowstep + texstep);
                     const float w00 = dsc[5 * p + 1], w10 = dsc[5 * p + 2], w01 = dsc[5 * p + 3], w11 = dsc[5 * p + 4];
                     acc.x += t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
                     acc.y += t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
                     acc.z += t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
                     acc.w += t00.w * w00 + t10.w * w10 + t01.w * w01 + t11.w * w11;
+                }
+                if (base1 != nullptr) {
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        const float* b = base1 + __float_as_int(dsc[5 * p]) + cq * 4;
+                        const float4 t00 = ldg_nc_f4(b), t10 = ldg_nc_f4(b + texstep), t01 = ldg_nc_f4(b + rowstep), t11 = ldg_nc_f4(b + rowstep + texstep);
+                        const float w00 = dsc[5 * p + 1], w10 = dsc[5 * p + 2], w01 = dsc[5 * p + 3], w11 = dsc[5 * p + 4];
+                        acc.x += t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
+                        acc.y += t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
+                        acc.z += t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
+                        acc.w += t00.w * w00 + t10.w * w10 + t01.w * w01 + t11.w * w11;
+                    }
                 }
                 const float third = 1.0f / 3.0f;
                 if (TC) {
@@ -593,9 +555,11 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
         for (int r = warp; r < R; r += kWarps) {
             const float* dd = dep + r * ST; int* od = ord + r * ST;
             for (int i = lane; i < ST; i += 32) {
-                const float di = dd[i];
+                // total order (torch.sort puts NaN last, -0 == +0): every sample gets a distinct rank even for NaN depths (degenerate
+                // cameras), so `ord` never holds an unwritten slot
+                const unsigned ki = sort_key(dd[i]);
                 int rank = 0;
-                for (int j = 0; j < ST; ++j) { const float dj = dd[j]; rank += (dj < di) || (dj == di && j < i); }
+                for (int j = 0; j < ST; ++j) { const unsigned kj = sort_key(dd[j]); rank += (kj < ki) || (kj == ki && j < i); }
                 od[rank] = i;
             }
             __syncwarp();
@@ -661,7 +625,7 @@ static bool mlp_in_const() { return mlp_variant() != 0; }
 
 static size_t render_tc_smem(int R, int S, int S_imp) {
     const int ST = S + S_imp;
-    if (S_imp == 0) return 1024 + kTcA1Bytes + kTcA2Bytes + 20480 + (kHidden + 48) * 4 + (size_t)R * (S + 8) * 4 + 2 * kTcMaxTiles * 8 + 16;
+    if (S_imp == 0) return 1024 + kTcA1Bytes + kTcA2Bytes + 20480 + (kHidden + 48) * 4 + (size_t)R * (S + 8) * 4 + 8 + 2 * kTcMaxTiles * 8 + 16;
     return 1024 + kTcA2Bytes + 20480 + (kHidden + 48) * 4 + (size_t)R * ST * (kRow + 4) * 4 + (size_t)R * 8 * 4 + 8 + 2 * kTcMaxTiles * 8 + 16;
 }
 // the tensor-core decoder needs its CTA tile to fit the A tiles: three 128-sample tiles for single-pass renders (decoded rows overlay
@@ -675,9 +639,7 @@ template <int R>
 static int launch_render_tc(const RenderArgs& a, cudaStream_t st) {
     const size_t smem = render_tc_smem(R, a.S, a.S_imp);
     R3DP_CUDA(cudaFuncSetAttribute(render_kernel<R, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MlpTcImage* dst = nullptr;
-    R3DP_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&dst), g_mlp_tc));
-    mlp_to_tc_kernel<<<4, 256, 0, st>>>(a.mlp, dst);
+    mlp_to_tc_kernel<<<4, 256, 0, st>>>(a.mlp, const_cast<MlpTcImage*>(a.image));
     count_launches(1);
     dim3 grid(a.tiles_per_frame, a.N);
     render_kernel<R, true, false, true><<<grid, kTcThreads, smem, st>>>(a);
@@ -702,10 +664,18 @@ static int launch_render_v(const RenderArgs& a, cudaStream_t st) {
 }
 template <int R>
 static int launch_render(const RenderArgs& a, cudaStream_t st) {
-    if (!mlp_in_const()) return launch_render_v<R, false, false>(a, st);
+    // default: tcgen05 decoder when the tile fits, else the smem-weights CUDA-core decoder (both keep the decoder in per-call storage);
+    // the constant-bank variants hold process-wide state and are reachable only through R3DP_MLP=const (A/B runs)
     if (mlp_variant() == 2 && render_tc_fits(R, a.S, a.S_imp)) return launch_render_tc<R>(a, st);
+    if (mlp_variant() != 1) return launch_render_v<R, false, false>(a, st);
     const int per_pass = R * (a.S_imp > 0 && a.S_imp < a.S ? a.S_imp : a.S);          // the smaller pass decides
     return per_pass >= 2 * kRenderThreads ? launch_render_v<R, true, true>(a, st) : launch_render_v<R, true, false>(a, st);
+}
+
+int g_render_variant = -1;                         // R3DP_RENDER = stream (default for single-pass renders) | tile: A/B knob
+static int render_variant() {
+    if (g_render_variant < 0) { const char* e = getenv("R3DP_RENDER"); g_render_variant = (e && e[0] == 't') ? 1 : 0; }
+    return g_render_variant;
 }
 
 }  // namespace r3dp
@@ -723,8 +693,17 @@ extern "C" int r3dp_gen_rays(const float* cam2world, const float* intrinsics, in
     return 0;
 }
 
+extern "C" int r3dp_set_option(const char* key, int value) {
+    R3DP_REQUIRE(key != nullptr, "set_option: null key");
+    const std::string k(key);
+    if (k == "render") { R3DP_REQUIRE(value == 0 || value == 1, "set_option: render = 0 (stream) | 1 (tile)"); g_render_variant = value; return 0; }
+    if (k == "rs_d") { R3DP_REQUIRE(value == 4 || value == 8 || value == 16, "set_option: rs_d = 4 | 8 | 16"); g_rs_chunk_log2 = value == 4 ? 2 : (value == 16 ? 4 : 3); return 0; }
+    R3DP_REQUIRE(false, "set_option: unknown key '%s'", key);
+    return 1;
+}
+
 extern "C" size_t r3dp_render_workspace_bytes(int N, int M) {
-    return sizeof(RenderWs) + (size_t)N * M * sizeof(float2);
+    return kWsLimitsOff + (size_t)N * M * sizeof(float2);
 }
 
 static int check_mlp(const r3dp_mlp_t* mlp, int C) {
@@ -735,44 +714,88 @@ static int check_mlp(const r3dp_mlp_t* mlp, int C) {
     return 0;
 }
 
+static int check_layout(const r3dp_plane_layout_t& l, int H, int W, const char* what) {
+    R3DP_REQUIRE(l.plane_stride > 0 && l.row_stride > 0 && l.texel_stride >= kC && l.frame_stride >= 0, "render: bad %s plane strides", what);
+    R3DP_REQUIRE((l.plane_stride % 4) == 0 && (l.row_stride % 4) == 0 && (l.texel_stride % 4) == 0 && (l.frame_stride % 4) == 0,
+                 "render: %s plane strides must keep texels 16-byte aligned", what);
+    const long long span = 2ll * l.plane_stride + (long long)(H - 1) * l.row_stride + (long long)(W - 1) * l.texel_stride + kC;
+    R3DP_REQUIRE(span < (1ll << 31), "render: %s planes of %dx%d exceed the 32-bit texel offsets of the tap descriptors", what, H, W);
+    return 0;
+}
+
+extern "C" int r3dp_render_ex(const r3dp_render_args_t* g, r3dp_stream_t stream) {
+    R3DP_REQUIRE(g != nullptr, "render: null argument block");
+    if (check_mlp(g->mlp, g->C)) return 1;
+    const int N = g->N, M = g->M, H = g->H, W = g->W, S = g->S, S_imp = g->S_imp, res = g->res;
+    R3DP_REQUIRE(g->planes && g->u_coarse && g->rgb && g->depth && g->weights_sum && g->is_ray_valid && g->workspace, "render: null pointer");
+    R3DP_REQUIRE(N > 0 && M > 0 && H >= 2 && W >= 2, "render: bad shape N=%d M=%d H=%d W=%d (planes must be at least 2x2)", N, M, H, W);
+    R3DP_REQUIRE(S >= 4, "render: depth_resolution must be >= 4 (got %d)", S);
+    R3DP_REQUIRE(S_imp >= 0 && (S_imp == 0 || g->u_fine), "render: depth_resolution_importance=%d needs u_fine", S_imp);
+    R3DP_REQUIRE(g->box_warp > 0.f, "render: box_warp must be positive");
+    R3DP_REQUIRE((g->ray_o && g->ray_d) || (g->camera && res > 0 && res * res == M), "render: need rays, or camera with M == res*res");
+    R3DP_REQUIRE(g->workspace_bytes >= r3dp_render_workspace_bytes(N, M), "render: workspace too small");
+    R3DP_REQUIRE((reinterpret_cast<uintptr_t>(g->workspace) & 15) == 0 && (reinterpret_cast<uintptr_t>(g->planes) & 15) == 0, "render: workspace and planes must be 16-byte aligned");
+    const int ST = S + S_imp;
+    R3DP_REQUIRE(ST <= 384, "render: at most 384 samples per ray are supported (got %d)", ST);
+    if (check_layout(g->layout, H, W, "first")) return 1;
+    if (g->planes2) {
+        if (check_layout(g->layout2, H, W, "second")) return 1;
+        R3DP_REQUIRE(g->layout2.plane_stride == g->layout.plane_stride && g->layout2.row_stride == g->layout.row_stride &&
+                     g->layout2.texel_stride == g->layout.texel_stride && (reinterpret_cast<uintptr_t>(g->planes2) & 15) == 0,
+                     "render: the second plane set must use the strides of the first (only its frame stride may differ)");
+    }
+    cudaStream_t st = as_stream(stream);
+
+    char* wsb = reinterpret_cast<char*>(g->workspace);
+    RenderWs* ws = reinterpret_cast<RenderWs*>(wsb);
+    float2* limits = reinterpret_cast<float2*>(wsb + kWsLimitsOff);
+    init_ws_kernel<<<1, 1, 0, st>>>(ws);
+    const int total = N * M;
+    ray_limits_kernel<<<(total + 255) / 256, 256, 0, st>>>(g->ray_o, g->ray_d, g->camera, res, N, M, g->box_warp, limits, g->is_ray_valid, ws);
+    R3DP_LAUNCH_CHECK();
+
+    RenderArgs a = {};
+    a.p0.base = g->planes; a.p0.frame_stride = g->layout.frame_stride; a.p0.plane_stride = g->layout.plane_stride;
+    a.p0.row_stride = g->layout.row_stride; a.p0.texel_stride = g->layout.texel_stride;
+    if (g->planes2) {
+        a.p1.base = g->planes2; a.p1.frame_stride = g->layout2.frame_stride; a.p1.plane_stride = g->layout2.plane_stride;
+        a.p1.row_stride = g->layout2.row_stride; a.p1.texel_stride = g->layout2.texel_stride;
+    }
+    a.N = N; a.H = H; a.W = W; a.ray_o = g->ray_o; a.ray_d = g->ray_d; a.camera = g->camera; a.M = M; a.res = res;
+    a.S = S; a.S_imp = S_imp; a.box_warp = g->box_warp; a.white_back = g->white_back; a.u_coarse = g->u_coarse; a.u_fine = g->u_fine;
+    a.mlp = *g->mlp; a.image = reinterpret_cast<const MlpTcImage*>(wsb + kWsImageOff);
+    a.rgb = g->rgb; a.depth = g->depth; a.wsum = g->weights_sum; a.limits = limits; a.valid = g->is_ray_valid; a.ws = ws;
+    int rc;
+    if (render_variant() == 0 && mlp_variant() == 2 && render_stream_fits(a)) {
+        mlp_to_tc_kernel<<<4, 256, 0, st>>>(a.mlp, const_cast<MlpTcImage*>(a.image));
+        count_launches(1);
+        rc = launch_render_stream(a, st);
+    } else {
+        const int R = ST <= 48 ? 8 : ST <= 96 ? 4 : ST <= 192 ? 2 : 1;
+        const bool image = res > 0 && res * res == M && (res % R) == 0;
+        a.tile_cols = image ? res : 0;
+        a.tiles_per_frame = (M + R - 1) / R;
+        rc = R == 8 ? launch_render<8>(a, st) : R == 4 ? launch_render<4>(a, st) : R == 2 ? launch_render<2>(a, st) : launch_render<1>(a, st);
+    }
+    if (rc) return rc;
+    count_launches(4);
+    depth_clamp_kernel<<<(total + 255) / 256, 256, 0, st>>>(g->depth, total, ws);
+    R3DP_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int r3dp_render(const float* planes_cl, int N, int C, int H, int W, const float* ray_o, const float* ray_d,
                            const float* camera, int M, int res, int S, int S_imp, float box_warp, int white_back,
                            const float* u_coarse, const float* u_fine, const r3dp_mlp_t* mlp, float* rgb, float* depth,
                            float* weights_sum, uint8_t* is_ray_valid, void* workspace, size_t workspace_bytes,
                            r3dp_stream_t stream) {
-    if (check_mlp(mlp, C)) return 1;
-    R3DP_REQUIRE(planes_cl && u_coarse && rgb && depth && weights_sum && is_ray_valid && workspace, "render: null pointer");
-    R3DP_REQUIRE(N > 0 && M > 0 && H >= 2 && W >= 2, "render: bad shape N=%d M=%d H=%d W=%d (planes must be at least 2x2)", N, M, H, W);
-    R3DP_REQUIRE(S >= 4, "render: depth_resolution must be >= 4 (got %d)", S);
-    R3DP_REQUIRE(S_imp >= 0 && (S_imp == 0 || u_fine), "render: depth_resolution_importance=%d needs u_fine", S_imp);
-    R3DP_REQUIRE(box_warp > 0.f, "render: box_warp must be positive");
-    R3DP_REQUIRE((ray_o && ray_d) || (camera && res > 0 && res * res == M), "render: need rays, or camera with M == res*res");
-    R3DP_REQUIRE(workspace_bytes >= r3dp_render_workspace_bytes(N, M), "render: workspace too small");
-    const int ST = S + S_imp;
-    R3DP_REQUIRE(ST <= 384, "render: at most 384 samples per ray are supported (got %d)", ST);
-    cudaStream_t st = as_stream(stream);
-
-    RenderWs* ws = reinterpret_cast<RenderWs*>(workspace);
-    float2* limits = reinterpret_cast<float2*>(reinterpret_cast<char*>(workspace) + sizeof(RenderWs));
-    init_ws_kernel<<<1, 1, 0, st>>>(ws);
-    const int total = N * M;
-    ray_limits_kernel<<<(total + 255) / 256, 256, 0, st>>>(ray_o, ray_d, camera, res, N, M, box_warp, limits, is_ray_valid, ws);
-    R3DP_LAUNCH_CHECK();
-
-    RenderArgs a;
-    a.planes = planes_cl; a.N = N; a.H = H; a.W = W; a.ray_o = ray_o; a.ray_d = ray_d; a.camera = camera; a.M = M; a.res = res;
-    a.S = S; a.S_imp = S_imp; a.box_warp = box_warp; a.white_back = white_back; a.u_coarse = u_coarse; a.u_fine = u_fine;
-    a.mlp = *mlp; a.rgb = rgb; a.depth = depth; a.wsum = weights_sum; a.limits = limits; a.valid = is_ray_valid; a.ws = ws;
-    const int R = ST <= 48 ? 8 : ST <= 96 ? 4 : ST <= 192 ? 2 : 1;
-    const bool image = res > 0 && res * res == M && (res % R) == 0;
-    a.tile_cols = image ? res : 0;
-    a.tiles_per_frame = (M + R - 1) / R;
-    int rc = R == 8 ? launch_render<8>(a, st) : R == 4 ? launch_render<4>(a, st) : R == 2 ? launch_render<2>(a, st) : launch_render<1>(a, st);
-    if (rc) return rc;
-    count_launches(4);
-    depth_clamp_kernel<<<(total + 255) / 256, 256, 0, st>>>(depth, total, ws);
-    R3DP_LAUNCH_CHECK();
-    return 0;
+    r3dp_render_args_t g = {};
+    g.planes = planes_cl; g.N = N; g.C = C; g.H = H; g.W = W;
+    g.layout.frame_stride = 3ll * H * W * C; g.layout.plane_stride = H * W * C; g.layout.row_stride = W * C; g.layout.texel_stride = C;
+    g.ray_o = ray_o; g.ray_d = ray_d; g.camera = camera; g.M = M; g.res = res; g.S = S; g.S_imp = S_imp; g.box_warp = box_warp;
+    g.white_back = white_back; g.u_coarse = u_coarse; g.u_fine = u_fine; g.mlp = mlp; g.rgb = rgb; g.depth = depth;
+    g.weights_sum = weights_sum; g.is_ray_valid = is_ray_valid; g.workspace = workspace; g.workspace_bytes = workspace_bytes;
+    return r3dp_render_ex(&g, stream);
 }
 
 extern "C" int r3dp_ray_march(const float* colors, const float* sigmas, const float* depths, int N, int M, int S, int C,

@@ -1,0 +1,445 @@
+// Streaming fused renderer for single-pass renders (ImportanceRenderer.forward with depth_resolution_importance == 0,
+// renderer.py:118-167): one PERSISTENT, warp-specialised CTA per SM in which the tri-plane gather, the OSG decoder on tcgen05 and the
+// ray march of consecutive sample tiles overlap instead of alternating.
+//
+// Work item   = a group of G rays of one frame (G rows of one image column when the rays form an image: planes 1 and 2 are indexed by
+//               (x,z)/(z,x) only, so these rays walk the same texels), streamed front to back in depth chunks of D = 128/G samples per ray.
+// Tile        = the G x D = 128 samples of one chunk = one UMMA M-tile; row = ray_local * D + k_local.
+// Roles (17 warps, mbarrier hand-offs, every ring is filled and drained in tile order):
+//   gather  x8  sample depths (renderer.py:223-226) -> positions -> bilinear tap descriptors -> 12 x LDG.128 per lane group -> mean feature as
+//               fp16 hi|lo halves straight into the swizzled A1 stage (3-stage ring); depths into a small ring for the marcher
+//   mma     x1  layer 1: A1 x W1 (3 partial products x 2 k-steps, M128 N64 K16) -> TMEM; layer 2: A2 x W2 (3 x 4, M128 N48) -> TMEM
+//   decode  x4  TMEM -> +bias, softplus -> re-split into the A2 atoms; TMEM -> +bias, scaled sigmoid -> fp32 rows (2-deep ring)
+//   march   x4  MipRayMarcher2 (ray_marcher.py:26-57) incrementally: per-ray transmittance / colour / depth accumulators live in registers
+//               across the tiles of an item (lane = colour channel); nothing but the final [32] features, weight sum and depth leaves the SM
+// Decoder arithmetic is the split-fp16 scheme of render_shared.cuh (fp32-grade results).
+#include "render_shared.cuh"
+#include <stdlib.h>
+
+namespace r3dp {
+int g_rs_chunk_log2 = -1;
+namespace rs {
+
+constexpr int kGatherWarps = 8;
+constexpr int kMmaWarp = 8;                                     // warps 0-3 decode (TMEM lane quadrant = warp), 4-7 march, 8 MMA, 9-16 gather
+constexpr int kFirstGather = 9;
+constexpr int kThreads = (kFirstGather + kGatherWarps) * 32;    // 544
+constexpr int NS = 3;                                           // A1 stages
+constexpr int NR = 2;                                           // decoded-row buffers
+constexpr int ND = 8;                                           // depth ring slots
+constexpr int kRowF = 33;                                       // floats per decoded row (odd: conflict-free thread-per-row stores)
+constexpr int kSPW = 128 / kGatherWarps;                        // samples per gather warp and tile
+
+constexpr int kOffA2 = NS * 16384;
+constexpr int kOffW = kOffA2 + 32768;
+constexpr int kOffRows = kOffW + 21504;                         // MlpTcImage (20 928 B) padded
+constexpr int kOffDep = kOffRows + NR * 128 * kRowF * 4;
+constexpr int kOffDsc = kOffDep + ND * 128 * 4;
+constexpr int kOffRay = kOffDsc + kGatherWarps * kSPW * 16 * 4;
+constexpr int kOffBar = kOffRay + kGatherWarps * 8 * 8 * 4;
+constexpr int kSmem = kOffBar + 512 + 1024;                     // + alignment slack
+
+struct Bars {
+    uint64_t a1_full[NS], a1_empty[NS];
+    uint64_t l1_done[2], l2_done[2], acc2_empty[2];
+    uint64_t a2_full;
+    uint64_t rows_full[NR], rows_empty[NR];
+    uint64_t dep_empty[ND];
+    uint32_t tmem_slot;
+};
+static_assert(sizeof(Bars) <= 512, "barrier block");
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int LOG2D>
+__device__ __forceinline__ int ray_index(const RenderArgs& a, int grp, int r) {
+    constexpr int G = 128 >> LOG2D;
+    if (a.tile_cols > 0) {
+        const int col = grp % a.tile_cols, band = grp / a.tile_cols;
+        return (band * G + r) * a.res + col;
+    }
+    return grp * G + r;
+}
+
+template <int LOG2D>
+__global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const RenderArgs a, int items_per_frame, int total_items) {
+    constexpr int D = 1 << LOG2D, G = 128 >> LOG2D;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = tc::align_smem_1024(smem_raw);
+    uint8_t* a1 = smem;
+    uint8_t* a2 = smem + kOffA2;
+    uint8_t* wimg = smem + kOffW;
+    float* rows = reinterpret_cast<float*>(smem + kOffRows);
+    float* dep = reinterpret_cast<float*>(smem + kOffDep);
+    float* dsc_all = reinterpret_cast<float*>(smem + kOffDsc);
+    float* ray_all = reinterpret_cast<float*>(smem + kOffRay);
+    Bars& B = *reinterpret_cast<Bars*>(smem + kOffBar);
+    const float* b1s = reinterpret_cast<const float*>(wimg + 20480);
+    const float* b2s = b1s + kHidden;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NT = (a.S + D - 1) >> LOG2D;                                     // tiles per item
+    const int my_items = (int)blockIdx.x < total_items ? (total_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const uint32_t total_tiles = (uint32_t)(my_items * NT);
+
+    if (tid == 0) {
+        for (int i = 0; i < NS; ++i) { tc::mbar_init(&B.a1_full[i], kGatherWarps); tc::mbar_init(&B.a1_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&B.l1_done[i], 1); tc::mbar_init(&B.l2_done[i], 1); tc::mbar_init(&B.acc2_empty[i], 4); }
+        tc::mbar_init(&B.a2_full, 4);
+        for (int i = 0; i < NR; ++i) { tc::mbar_init(&B.rows_full[i], 4); tc::mbar_init(&B.rows_empty[i], 4); }
+        for (int i = 0; i < ND; ++i) tc::mbar_init(&B.dep_empty[i], 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&B.tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   // decoder operand image (pre-swizzled fp16 hi/lo atoms + biases) from the call's workspace
+        const uint4* src = reinterpret_cast<const uint4*>(a.image);
+        uint4* dst = reinterpret_cast<uint4*>(wimg);
+        for (int i = tid; i < (int)(sizeof(MlpTcImage) / 16); i += kThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(dst + i)), "l"(src + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = B.tmem_slot;
+
+    if (warp >= kFirstGather) {
+        // ===================================================== gather ===========================================================
+        constexpr int RPW = kSPW >> LOG2D;                                      // rays per gather warp
+        static_assert(RPW >= 1, "D must not exceed the samples of one gather warp");
+        const int gw = warp - kFirstGather, sub = lane >> 3, cq = lane & 7;
+        float* dsc = dsc_all + gw * kSPW * 16;
+        float* rayw = ray_all + gw * 64;
+        const float scale = 2.0f / a.box_warp;
+        const int rs = a.p0.row_stride, ts = a.p0.texel_stride;
+        float dmin = __int_as_float(0x7f800000), dmax = __int_as_float(0xff800000);
+        uint32_t q = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            const int n = item / items_per_frame, grp = item - n * items_per_frame;
+            __syncwarp();
+            if (lane < RPW) {
+                const int m = ray_index<LOG2D>(a, grp, gw * RPW + lane);
+                float* rf = rayw + lane * 8;
+                if (m < a.M) {
+                    Ray r = fetch_ray(a.ray_o, a.ray_d, a.camera, a.res, n, a.M, m);
+                    float2 lim = a.limits[(size_t)n * a.M + m];
+                    if (!a.valid[(size_t)n * a.M + m] && a.ws->n_valid > 0) {      // renderer.py:125-126 (far end from ray_START, sic)
+                        lim.x = ord2f(a.ws->t0_min); lim.y = ord2f(a.ws->t0_max);
+                    }
+                    rf[0] = r.ox; rf[1] = r.oy; rf[2] = r.oz; rf[3] = r.dx; rf[4] = r.dy; rf[5] = r.dz; rf[6] = lim.x; rf[7] = lim.y;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) rf[e] = 0.f;
+                }
+            }
+            __syncwarp();
+            const float* base0 = a.p0.base + (size_t)n * a.p0.frame_stride;
+            const float* base1 = a.p1.base ? a.p1.base + (size_t)n * a.p1.frame_stride : nullptr;
+            // this lane's sample of the descriptor phase (lanes 0..kSPW-1): ray rl of the warp, depth index k0 + j
+            const int s_rl = (lane & (kSPW - 1)) >> LOG2D, s_j = lane & (D - 1);
+            const int s_m = ray_index<LOG2D>(a, grp, gw * RPW + s_rl);
+            const float* up = a.u_coarse + ((size_t)n * a.M + (s_m < a.M ? s_m : 0)) * a.S;
+            float u_next = (lane < kSPW && s_m < a.M && s_j < a.S) ? __ldg(up + s_j) : 0.f;
+            for (int t = 0; t < NT; ++t, ++q) {
+                const int k0 = t << LOG2D, stage = q % NS, dslot = q % ND;
+                const float u = u_next;
+                {
+                    const int kn = k0 + D + s_j;
+                    u_next = (t + 1 < NT && lane < kSPW && s_m < a.M && kn < a.S) ? __ldg(up + kn) : 0.f;
+                }
+                tc::mbar_wait(&B.dep_empty[dslot], ((q / ND) & 1) ^ 1);
+                if (lane < kSPW) {
+                    const int k = k0 + s_j;
+                    float* row = dsc + lane * 16;
+                    float d = 0.f;
+                    if (s_m < a.M && k < a.S) {
+                        const float* rf = rayw + s_rl * 8;
+                        const float t0 = rf[6], t1 = rf[7];
+                        const float step = __fdiv_rn((float)k, (float)(a.S - 1));                  // renderer.py:223-226, math_utils.py:101-118
+                        d = __fadd_rn(t0, __fmul_rn(step, __fsub_rn(t1, t0)));
+                        d = __fadd_rn(d, __fmul_rn(u, __fdiv_rn(__fsub_rn(t1, t0), (float)(a.S - 1))));
+                        dmin = fminf(dmin, d); dmax = fmaxf(dmax, d);
+                        const float x = __fadd_rn(rf[0], __fmul_rn(d, rf[3]));
+                        const float y = __fadd_rn(rf[1], __fmul_rn(d, rf[4]));
+                        const float z = __fadd_rn(rf[2], __fmul_rn(d, rf[5]));
+                        const float gx = scale * x, gy = scale * y, gz = scale * z;
+                        tap_desc_s(gx, gy, a.H, a.W, 0, rs, ts, row);                              // plane 0 <- (x, y)   (renderer.py:30-63)
+                        tap_desc_s(gx, gz, a.H, a.W, a.p0.plane_stride, rs, ts, row + 5);          // plane 1 <- (x, z)
+                        tap_desc_s(gz, gx, a.H, a.W, 2 * a.p0.plane_stride, rs, ts, row + 10);     // plane 2 <- (z, x)
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 15; ++e) row[e] = 0.f;                                 // offset 0, weights 0: a harmless tap
+                    }
+                    dep[dslot * 128 + gw * kSPW + lane] = d;
+                }
+                __syncwarp();
+                tc::mbar_wait(&B.a1_empty[stage], ((q / NS) & 1) ^ 1);
+                uint8_t* a1s = a1 + stage * 16384;
+#pragma unroll 1
+                for (int it = 0; it < kSPW / 4; ++it) {
+                    const int s = it * 4 + sub;
+                    const float4* rw = reinterpret_cast<const float4*>(dsc + s * 16);
+                    const float4 q0 = rw[0], q1 = rw[1], q2 = rw[2], q3 = rw[3];
+                    const float dscv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        const float* b = base0 + __float_as_int(dscv[5 * p]) + cq * 4;
+                        const float4 t00 = ldg_nc_f4(b), t10 = ldg_nc_f4(b + ts), t01 = ldg_nc_f4(b + rs), t11 = ldg_nc_f4(b + rs + ts);
+                        const float w00 = dscv[5 * p + 1], w10 = dscv[5 * p + 2], w01 = dscv[5 * p + 3], w11 = dscv[5 * p + 4];
+                        acc.x += t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
+                        acc.y += t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
+                        acc.z += t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
+                        acc.w += t00.w * w00 + t10.w * w10 + t01.w * w01 + t11.w * w11;
+                    }
+                    if (base1 != nullptr) {                                      // second plane set, same points (bilinear sampling is linear)
+#pragma unroll
+                        for (int p = 0; p < 3; ++p) {
+                            const float* b = base1 + __float_as_int(dscv[5 * p]) + cq * 4;
+                            const float4 t00 = ldg_nc_f4(b), t10 = ldg_nc_f4(b + ts), t01 = ldg_nc_f4(b + rs), t11 = ldg_nc_f4(b + rs + ts);
+                            const float w00 = dscv[5 * p + 1], w10 = dscv[5 * p + 2], w01 = dscv[5 * p + 3], w11 = dscv[5 * p + 4];
+                            acc.x += t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
+                            acc.y += t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
+                            acc.z += t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
+                            acc.w += t00.w * w00 + t10.w * w10 + t01.w * w01 + t11.w * w11;
+                        }
+                    }
+                    // mean over the planes as fp16 hi + lo halves into the swizzled A1 stage: lane cq owns K = [4cq, 4cq+4) of both halves
+                    const float third = 1.0f / 3.0f;
+                    const float f0 = acc.x * third, f1 = acc.y * third, f2 = acc.z * third, f3 = acc.w * third;
+                    const __half2 h01 = __floats2half2_rn(f0, f1), h23 = __floats2half2_rn(f2, f3);
+                    const float2 g01 = __half22float2(h01), g23 = __half22float2(h23);
+                    const __half2 l01 = __floats2half2_rn(f0 - g01.x, f1 - g01.y), l23 = __floats2half2_rn(f2 - g23.x, f3 - g23.y);
+                    const int trow = gw * kSPW + s;
+                    uint8_t* rp = a1s + (trow >> 3) * 1024 + (trow & 7) * 128 + (cq & 1) * 8;
+                    uint2 hv, lv;
+                    hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                    lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                    *reinterpret_cast<uint2*>(rp + (((cq >> 1) ^ (trow & 7)) << 4)) = hv;
+                    *reinterpret_cast<uint2*>(rp + (((4 + (cq >> 1)) ^ (trow & 7)) << 4)) = lv;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy A1 stores -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&B.a1_full[stage]);
+            }
+        }
+        // call-wide min/max of the sample depths (ray_marcher.py:50)
+        dmin = warp_min(dmin); dmax = warp_max(dmax);
+        if (lane == 0 && dmin <= dmax) { atomicMin(&a.ws->d_min, f2ord(dmin)); atomicMax(&a.ws->d_max, f2ord(dmax)); }
+    } else if (warp == kMmaWarp) {
+        // ======================================================= MMA ============================================================
+        const uint32_t a2_s = tc::smem_u32(a2), w_s = tc::smem_u32(wimg);
+        auto issue_l2 = [&](uint32_t p) {                                      // h_hi w_hi + h_lo w_hi + h_hi w_lo, 4 k-steps each
+            tc::mbar_wait(&B.a2_full, p & 1u);
+            tc::mbar_wait(&B.acc2_empty[p & 1u], ((p >> 1) & 1u) ^ 1u);
+            tc::tc_fence_after();
+            const uint32_t acc = tmem_base + 128u * (p & 1u) + 64u;
+            if (tc::elect_one()) {
+                uint32_t accum = 0;
+#pragma unroll
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t ao = term == 1 ? 16384u : 0u, bo = term == 2 ? (8192u + 6144u) : 8192u;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        tc::tc_mma_f16(acc, tc::umma_desc_sw128(a2_s + ao + ks * 32), tc::umma_desc_sw128(w_s + bo + ks * 32), kIdescL2, accum);
+                        accum = 1;
+                    }
+                }
+                tc::tc_commit(&B.l2_done[p & 1u]);
+            }
+            __syncwarp();
+        };
+        for (uint32_t q = 0; q < total_tiles; ++q) {
+            if (q >= 1) issue_l2(q - 1);
+            const uint32_t stage = q % NS;
+            tc::mbar_wait(&B.a1_full[stage], (q / NS) & 1u);
+            tc::tc_fence_after();
+            const uint32_t a1_s = tc::smem_u32(a1) + stage * 16384u;
+            const uint32_t acc = tmem_base + 128u * (q & 1u);
+            if (tc::elect_one()) {                                            // x_hi w_hi + x_lo w_hi + x_hi w_lo, 2 k-steps each
+                uint32_t accum = 0;
+#pragma unroll
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t ao = term == 1 ? 64u : 0u, bo = term == 2 ? 64u : 0u;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        tc::tc_mma_f16(acc, tc::umma_desc_sw128(a1_s + ao + ks * 32), tc::umma_desc_sw128(w_s + bo + ks * 32), kIdescL1, accum);
+                        accum = 1;
+                    }
+                }
+                tc::tc_commit(&B.l1_done[q & 1u]);
+                tc::tc_commit(&B.a1_empty[stage]);
+            }
+            __syncwarp();
+        }
+        if (total_tiles) issue_l2(total_tiles - 1);
+    } else if (warp < 4) {
+        // ====================================================== decode ==========================================================
+        const int qd = warp, trow = qd * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
+        auto epi2 = [&](uint32_t p) {                                          // outputs of tile p: sigma raw, colours through the scaled sigmoid
+            tc::mbar_wait(&B.l2_done[p & 1u], (p >> 1) & 1u);
+            tc::tc_fence_after();
+            uint32_t v[32], v2[16];
+            tc::tc_ld32(lane_addr + 128u * (p & 1u) + 64u, v);
+            tc_ld16(lane_addr + 128u * (p & 1u) + 96u, v2);
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&B.acc2_empty[p & 1u]);
+            const uint32_t rb = p % NR;
+            tc::mbar_wait(&B.rows_empty[rb], ((p / NR) & 1u) ^ 1u);
+            float* out = rows + (rb * 128 + trow) * kRowF;
+            out[0] = __uint_as_float(v[0]) + b2s[0];
+#pragma unroll
+            for (int o = 1; o < 32; ++o) out[o] = sigmoid_fast(__uint_as_float(v[o]) + b2s[o]) * 1.002f - 0.001f;
+            out[32] = sigmoid_fast(__uint_as_float(v2[0]) + b2s[32]) * 1.002f - 0.001f;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&B.rows_full[rb]);
+        };
+        for (uint32_t q = 0; q < total_tiles; ++q) {
+            tc::mbar_wait(&B.l1_done[q & 1u], (q >> 1) & 1u);
+            tc::tc_fence_after();
+            uint8_t* rp = a2 + (trow >> 3) * 1024 + (trow & 7) * 128;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v[32];
+                tc::tc_ld32(lane_addr + 128u * (q & 1u) + 32u * h, v);           // hidden units [32h, 32h+32) of this sample, pre-activation
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float h0 = softplus_fast(__uint_as_float(v[2 * i]) + b1s[32 * h + 2 * i]);
+                    const float h1 = softplus_fast(__uint_as_float(v[2 * i + 1]) + b1s[32 * h + 2 * i + 1]);
+                    const __half2 hh = __floats2half2_rn(h0, h1);
+                    const float2 hf = __half22float2(hh);
+                    const __half2 ll = __floats2half2_rn(h0 - hf.x, h1 - hf.y);
+                    hi[i] = *reinterpret_cast<const uint32_t*>(&hh); lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
+                }
+                if (h == 0 && q >= 1) tc::mbar_wait(&B.l2_done[(q - 1) & 1u], ((q - 1) >> 1) & 1u);     // layer 2 of the previous tile has read A2
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int off = ((4 * h + c) ^ (trow & 7)) << 4;
+                    *reinterpret_cast<uint4*>(rp + off) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                    *reinterpret_cast<uint4*>(rp + 16384 + off) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&B.a2_full);
+            if (q >= 1) epi2(q - 1);
+        }
+        if (total_tiles) epi2(total_tiles - 1);
+    } else {
+        // ====================================================== march ===========================================================
+        // ray_marcher.py:26-57, front to back over the tiles of an item; warp mw owns RM rays, lane = colour channel.
+        constexpr int RM = G / 4;
+        const int mw = warp - 4;
+        uint32_t q = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            const int n = item / items_per_frame, grp = item - n * items_per_frame;
+            float T[RM], acc[RM], wsum[RM], dsum[RM], ps[RM], pc[RM], pd[RM];
+#pragma unroll
+            for (int i = 0; i < RM; ++i) { T[i] = 1.f; acc[i] = 0.f; wsum[i] = 0.f; dsum[i] = 0.f; ps[i] = 0.f; pc[i] = 0.f; pd[i] = 0.f; }
+            for (int t = 0; t < NT; ++t, ++q) {
+                const uint32_t rb = q % NR, dslot = q % ND;
+                tc::mbar_wait(&B.rows_full[rb], (q / NR) & 1u);
+                const float* rbuf = rows + rb * 128 * kRowF;
+                const float* dd = dep + dslot * 128;
+                const int k0 = t << LOG2D;
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const int k = k0 + j;
+                    if (k < a.S) {
+#pragma unroll
+                        for (int i = 0; i < RM; ++i) {
+                            const int row = ((mw * RM + i) << LOG2D) + j;
+                            const float s = rbuf[row * kRowF], c = rbuf[row * kRowF + 1 + lane], d = dd[row];
+                            if (k > 0) {
+                                const float delta = d - pd[i];
+                                const float smid = softplus_fast((ps[i] + s) * 0.5f - 1.0f);          // ray_marcher.py:33
+                                const float alpha = 1.0f - __expf(-(smid * delta));
+                                const float w = alpha * T[i];
+                                T[i] *= (1.0f - alpha + 1e-10f);
+                                acc[i] = fmaf(w, 0.5f * (pc[i] + c), acc[i]);
+                                wsum[i] += w;
+                                dsum[i] = fmaf(w, 0.5f * (pd[i] + d), dsum[i]);
+                            }
+                            ps[i] = s; pc[i] = c; pd[i] = d;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&B.rows_empty[rb]); mbar_arrive(&B.dep_empty[dslot]); }
+            }
+#pragma unroll
+            for (int i = 0; i < RM; ++i) {
+                const int m = ray_index<LOG2D>(a, grp, mw * RM + i);
+                if (m < a.M) {
+                    const size_t o = (size_t)n * a.M + m;
+                    float v = acc[i];
+                    if (a.white_back) v = v + 1.0f - wsum[i];
+                    a.rgb[o * (kOut - 1) + lane] = v * 2.0f - 1.0f;
+                    if (lane == 0) { a.wsum[o] = wsum[i]; a.depth[o] = dsum[i] / wsum[i]; }      // 0/0 -> NaN, fixed by depth_clamp_kernel
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc::tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    }
+}
+
+static int chunk_log2() {                          // R3DP_RS_D = 4 | 8 | 16: depth samples per ray and tile (rays per item = 128 / D); A/B knob
+    if (g_rs_chunk_log2 < 0) { const char* e = getenv("R3DP_RS_D"); const int d = e ? atoi(e) : 8; g_rs_chunk_log2 = d == 4 ? 2 : (d == 16 ? 4 : 3); }
+    return g_rs_chunk_log2;
+}
+
+template <int LOG2D>
+static int launch(RenderArgs a, cudaStream_t st) {
+    constexpr int G = 128 >> LOG2D;
+    const bool image = a.res > 0 && a.res * a.res == a.M && (a.res % G) == 0;
+    a.tile_cols = image ? a.res : 0;
+    const int items_per_frame = (a.M + G - 1) / G;
+    const int total = a.N * items_per_frame;
+    R3DP_CUDA(cudaFuncSetAttribute(render_stream_kernel<LOG2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    const int grid = total < sm_count() ? total : sm_count();
+    render_stream_kernel<LOG2D><<<grid, kThreads, kSmem, st>>>(a, items_per_frame, total);
+    R3DP_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace rs
+
+bool render_stream_fits(const RenderArgs& a) {
+    if (a.S_imp != 0 || a.S < 2) return false;
+    if (a.p1.base && (a.p1.plane_stride != a.p0.plane_stride || a.p1.row_stride != a.p0.row_stride || a.p1.texel_stride != a.p0.texel_stride)) return false;
+    return true;
+}
+
+int launch_render_stream(const RenderArgs& a, cudaStream_t st) {
+    switch (rs::chunk_log2()) {
+        case 2: return rs::launch<2>(a, st);
+        case 4: return rs::launch<4>(a, st);
+        default: return rs::launch<3>(a, st);
+    }
+}
+
+}  // namespace r3dp

@@ -5,12 +5,10 @@
 //   weights      per-sample folded (modulated+demodulated) fp16, packed [n][tap][Cout][Cin_pad]  (K-major B operand)
 //   accumulate   fp32 in TMEM; epilogue in fp32 (bias, lrelu*sqrt2, ToRGB + skip) then fp16 / fp32 stores
 //
-// Three generations of the conv kernel live here (selected by R3DP_TC_KERNEL, default 3):
-//   v3 conv_tc3_kernel  persistent CTA PAIRS (cta_group::2): M256 x N128 x K16 MMAs, half weight tile per CTA, A row strips reused by the
-//                       horizontal taps through row-shifted descriptors, double-buffered TMEM accumulators, 8 epilogue warps    <- DEFAULT
-//   v2 conv_tc2_kernel  the same persistent design on single CTAs (4 epilogue warps)
-//   v1 conv_tc_kernel   one 128x128 tile per CTA, 3-stage ring, 2 CTAs/SM (first working version; kept for A/B runs)
-// In all of them the im2col is done by TMA itself: every (tap, 64-channel chunk) of the K loop is a box load at the tap's shifted
+// The conv kernel (conv_tc3_kernel): persistent CTA PAIRS (cta_group::2): M256 x N128 x K16 MMAs, half weight tile per CTA, A row strips
+// reused by the horizontal taps through row-shifted descriptors, double-buffered TMEM accumulators, 8 epilogue warps.  (Its two
+// predecessors - one tile per CTA, and the same persistent design on single CTAs - were removed in round 2; see git history.)
+// The im2col is done by TMA itself: every (tap, 64-channel chunk) of the K loop is a box load at the tap's shifted
 // coordinates, zero-filled outside the image (= the conv's zero padding); one elected lane issues the MMAs.
 //
 // The stride-2 transposed convolution of the up layers (conv2d_resample.py:116-133) keeps the reference's operation order for large Cin:
@@ -28,10 +26,7 @@
 namespace r3dp {
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3, UMMA_K = 16;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int kThreads = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers, bias, rgb weights*/ + 2048;
+constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16;
 
 // kind::f16 instruction descriptor: D=f32 (bit 4), A=B=f16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -55,182 +50,14 @@ struct ConvArgs {
     const float* brgb;       // [3]
     const float* img_prev;
     float* img_out;
+    int out_clamp; uint8_t* img_out_u8;
 };
 
-__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = align_smem_1024(smem_raw);
-    uint8_t* stage_base = smem;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    float* s_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 128);       // [128]
-    float* s_wrgb = s_bias + 128;                                                       // [3][128]
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x / a.tiles_x, col0 = (blockIdx.x % a.tiles_x) * BM;
-    const int nblk = blockIdx.y, n = blockIdx.z;
-    const int wn = a.w_shared ? 0 : n;
-    const int num_kb = a.taps.n * a.k_chunks;
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (warp >= 2) {
-        const int t = threadIdx.x - 64;
-        if (a.bias) s_bias[t] = a.bias[nblk * BN + t];
-        if (a.mode == kToRgbFinal) { for (int e = t; e < 3 * BN; e += 128) s_wrgb[e] = a.wrgb[(size_t)wn * 3 * BN + e]; }
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                const int t = kb / a.k_chunks, kc = kb - t * a.k_chunks;
-                uint8_t* sa = stage_base + s * STAGE_BYTES;
-                mbar_expect_tx(&full[s], STAGE_BYTES);
-                tma_load_4d(sa, &tmA, &full[s], kc * BK, col0 + a.taps.dx[t], row + a.taps.dy[t], n);
-                tma_load_4d(sa + A_BYTES, &tmB, &full[s], kc * BK, nblk * BN, a.taps.widx[t], wn);
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-            mbar_wait(&full[s], ph);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t sa = smem_u32(stage_base + s * STAGE_BYTES);
-                const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + A_BYTES);
-#pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    // advancing K by 16 fp16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr>>4) field
-                    tc_mma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kb | k) != 0);
-                }
-                tc_commit(&empty[s]);                       // frees the smem stage when these MMAs retire
-                if (kb == num_kb - 1) tc_commit(tmem_full);  // accumulator complete
-            }
-            __syncwarp();
-        }
-    } else {
-        // ===== epilogue: warps 2..5 own TMEM lanes [32*(warp%4), +32) =====
-        const int q = warp & 3;
-        const int m = q * 32 + lane;                         // row of the tile = grid column col0 + m
-        const int gcol = col0 + m;
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        float rgb[3] = {0.f, 0.f, 0.f};
-        const int Y = row * a.oy_mul + a.oy_off, X = gcol * a.ox_mul + a.ox_off;
-        const bool in_img = (Y < a.out_H) && (X < a.out_W);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tc_ld32(taddr + c0, r);
-            if (a.mode == kStoreRaw) {
-                if (in_img) {
-                    uint4* dst = reinterpret_cast<uint4*>(a.out + (((size_t)n * a.out_H + Y) * a.out_W + X) * a.out_C + nblk * BN + c0);
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        __half2 h0 = __floats2half2_rn(__uint_as_float(r[8 * v + 0]), __uint_as_float(r[8 * v + 1]));
-                        __half2 h1 = __floats2half2_rn(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3]));
-                        __half2 h2 = __floats2half2_rn(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5]));
-                        __half2 h3 = __floats2half2_rn(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7]));
-                        uint4 pk;
-                        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                        dst[v] = pk;
-                    }
-                }
-            } else {
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float v = __uint_as_float(r[j]) + s_bias[c0 + j];
-                    f[j] = (v < 0.f ? v * 0.2f : v) * 1.4142135623730951f;        // bias_act lrelu, gain sqrt(2)
-                }
-                if (a.mode == kStoreAct) {
-                    if (in_img) {
-                        uint4* dst = reinterpret_cast<uint4*>(a.out + (((size_t)n * a.out_H + Y) * a.out_W + X) * a.out_C + nblk * BN + c0);
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            __half2 h0 = __floats2half2_rn(f[8 * v + 0], f[8 * v + 1]), h1 = __floats2half2_rn(f[8 * v + 2], f[8 * v + 3]);
-                            __half2 h2 = __floats2half2_rn(f[8 * v + 4], f[8 * v + 5]), h3 = __floats2half2_rn(f[8 * v + 6], f[8 * v + 7]);
-                            uint4 pk;
-                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                            dst[v] = pk;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float4* w4 = reinterpret_cast<const float4*>(s_wrgb + c * BN + c0);
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 w = w4[j4];
-                            rgb[c] = fmaf(f[4 * j4 + 0], w.x, rgb[c]); rgb[c] = fmaf(f[4 * j4 + 1], w.y, rgb[c]);
-                            rgb[c] = fmaf(f[4 * j4 + 2], w.z, rgb[c]); rgb[c] = fmaf(f[4 * j4 + 3], w.w, rgb[c]);
-                        }
-                    }
-                }
-            }
-        }
-        if (a.mode == kToRgbFinal && in_img) {
-            const int h = a.out_H / 2, w = a.out_W / 2;
-            const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float acc = 0.f;
-                if (a.img_prev) {
-                    const float* ip = a.img_prev + ((size_t)n * 3 + c) * h * w;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int zy = Y + u - 2;
-                        if (zy < 0 || (zy & 1) || (zy >> 1) >= h) continue;
-                        float rowv = 0.f;
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            const int zx = X + v - 2;
-                            if (zx < 0 || (zx & 1) || (zx >> 1) >= w) continue;
-                            rowv = fmaf(k4[v], __ldg(ip + (size_t)(zy >> 1) * w + (zx >> 1)), rowv);
-                        }
-                        acc = fmaf(k4[u], rowv, acc);
-                    }
-                }
-                a.img_out[(((size_t)n * 3 + c) * a.out_H + Y) * a.out_W + X] = rgb[c] + a.brgb[c] + acc;
-            }
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
-    }
-}
-
 // =====================================================================================================================
-// conv_tc2_kernel<R>: persistent implicit-GEMM conv, R output rows (R x 128 pixels) x 128 couts per tile.
+// Persistent implicit-GEMM conv design (shared by conv_tc3_kernel<R>): R output rows (R x 128 pixels) x 128 couts per tile.
 //
-// Why: ncu on the v1 kernel showed 58 % tensor-pipe activity on the largest layer, L2 at 65 % / 92 % hits: not L2-bound, but
-// with 128x128 tiles the two smem operands cost 128 B/clk of shared-memory reads per MMA, the same port TMA fills.  v2 cuts the
+// Why: ncu on the first one-tile-per-CTA kernel showed 58 % tensor-pipe activity on the largest layer, L2 at 65 % / 92 % hits: not L2-bound, but
+// with 128x128 tiles the two smem operands cost 128 B/clk of shared-memory reads per MMA, the same port TMA fills.  This design cuts the
 // fill traffic and the per-tile overheads:
 //   * an input ROW STRIP {64 ch, 130 px} is loaded once per 64-channel chunk and serves all horizontal taps (the UMMA smem
 //     descriptor starts 128 B x shift later; the 128-byte swizzle is a function of the ABSOLUTE smem address, so the descriptor's
@@ -262,16 +89,11 @@ struct Conv2Args {
     const float* bias; const float* wrgb; const float* brgb; const float* img_prev; float* img_out; int img_H, img_W;
     float act_slope, act_gain;      // epilogue activation: v < 0 ? v*slope : v, then * gain  (0.2, sqrt2 = bias_act lrelu; 0.01, 1 = nn.LeakyReLU; 1, 1 = linear)
     int skip_same_res;              // ToRGB skip image has the output resolution (SynthesisBlockNoUp) instead of half (FIR-upsampled)
+    int out_clamp;                  // final image clamped to [-1, 1] (the caller-side imgs.clamp(-1,1), inference/real3d_infer.py:515)
+    uint8_t* img_out_u8;            // non-null: final image as uint8 HWC frames [N][H][W][3] = int((clamp(x)+1)/2*255) (real3d_infer.py:519) instead of fp32 NCHW
     unsigned long long* debug;      // R3DP_TC_DEBUG_TIMING builds: [acc wait, strip wait, tap wait, issue, total, #CTAs] clock sums of the MMA warp
 };
 
-template <int R> struct Cfg2 {
-    static constexpr int NA = (R >= 4) ? 8 : (R == 2 ? 5 : 4);
-    static constexpr int NB = (R >= 4) ? 5 : 8;
-    static constexpr int NACC = (R * BN * 2 <= 512) ? 2 : 1;
-    static constexpr int TMEM_COLS = (R * BN * NACC <= 128) ? 128 : (R * BN * NACC <= 256 ? 256 : 512);
-    static constexpr int SMEM = NA * A2_SLOT + NB * B_BYTES + 1024 + 5120;
-};
 
 // FIR-upsampled skip image (upsample2d, upfirdn2d.py:317-354) at output pixel (Y,X): zero-insert x2, pad (2,1,2,1), [1,3,3,1]^2/64 * 4
 __device__ __forceinline__ float upsampled_skip(const float* __restrict__ ip, int h, int w, int Y, int X) {
@@ -355,226 +177,6 @@ __device__ __forceinline__ void store_half32(__half* dst, const float* f) {
         pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
         pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
         d4[v] = pk;
-    }
-}
-
-template <int R>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                               const __grid_constant__ CUtensorMap tmB, const Conv2Args a) {
-    using C = Cfg2<R>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = align_smem_1024(smem_raw);
-    uint8_t* a_ring = smem;
-    uint8_t* b_ring = smem + C::NA * A2_SLOT;
-    uint8_t* tail = b_ring + C::NB * B_BYTES;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
-    uint64_t* a_empty = a_full + C::NA;
-    uint64_t* b_full = a_empty + C::NA;
-    uint64_t* b_empty = b_full + C::NB;
-    uint64_t* acc_full = b_empty + C::NB;
-    uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    float* s_bias = reinterpret_cast<float*>(tail + 512);                    // [256]
-    float* s_wrgb = s_bias + 256;                                            // [3][n_blocks*128]
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int units_per_image = a.n_phases * a.row_groups * a.tiles_x;
-
-    if (warp == 0 && lane == 0) {
-        for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < C::NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (warp >= 2) {
-        const int t = threadIdx.x - 64;
-        for (int e = t; e < a.n_blocks * BN && e < 256; e += 128) s_bias[e] = a.bias ? a.bias[e] : 0.f;
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    // unit index -> (image n, phase, row group, x block); x fastest so neighbouring CTAs share strips in L2
-    auto decode = [&](int unit, int& n, int& ph, int& row0, int& col0) {
-        n = unit / units_per_image; int r = unit - n * units_per_image;
-        const int xb = r % a.tiles_x; r /= a.tiles_x;
-        const int rg = r % a.row_groups; ph = r / a.row_groups;
-        row0 = rg * R; col0 = xb * BM;
-    };
-
-    if (warp == 0) {
-        // ===== TMA producer (one lane): strips and taps in consumption order =====
-        if (lane == 0) {
-            uint32_t aq = 0, bq = 0;                                         // running strip / tap sequence numbers
-            for (int unit = blockIdx.x; unit < a.total_units; unit += gridDim.x) {
-                int n, ph, row0, col0; decode(unit, n, ph, row0, col0);
-                const Taps2& tp = a.ph[ph].taps;
-                const int DY = tp.ngroups;
-                const int wn = a.w_shared ? 0 : n;
-                for (int nblk = 0; nblk < a.n_blocks; ++nblk)
-                    for (int kc = 0; kc < a.k_chunks; ++kc)
-                        for (int d = 0; d < DY; ++d) {
-                            const int s_lo = d == 0 ? 0 : R - 1 + d, s_hi = R - 1 + d;
-                            for (int s = s_lo; s <= s_hi; ++s, ++aq) {
-                                const int slot = aq % C::NA;
-                                mbar_wait(&a_empty[slot], ((aq / C::NA) & 1) ^ 1);
-                                mbar_expect_tx(&a_full[slot], A2_BYTES);
-                                tma_load_4d(a_ring + slot * A2_SLOT, &tmA, &a_full[slot], kc * BK, col0 - 1, row0 + tp.dy_min + s, n);
-                            }
-                            for (int t = tp.gstart[d]; t < tp.gstart[d + 1]; ++t, ++bq) {
-                                const int slot = bq % C::NB;
-                                mbar_wait(&b_empty[slot], ((bq / C::NB) & 1) ^ 1);
-                                mbar_expect_tx(&b_full[slot], B_BYTES);
-                                tma_load_4d(b_ring + slot * B_BYTES, &tmB, &b_full[slot], kc * BK, nblk * BN, tp.widx[t], wn);
-                            }
-                        }
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        uint32_t aq = 0, bq = 0, it = 0;
-        for (int unit = blockIdx.x; unit < a.total_units; unit += gridDim.x) {
-            int n, ph, row0, col0; decode(unit, n, ph, row0, col0);
-            const Taps2& tp = a.ph[ph].taps;
-            const int DY = tp.ngroups, NS = R + DY - 1;
-            for (int nblk = 0; nblk < a.n_blocks; ++nblk, ++it) {
-                const int buf = it % C::NACC;
-                mbar_wait(&acc_empty[buf], (((it / C::NACC) & 1) ^ 1));
-                tc_fence_after();
-                const uint32_t acc0 = tmem_base + buf * (R * BN);
-                for (int kc = 0; kc < a.k_chunks; ++kc) {
-                    const uint32_t a_base = aq;                               // sequence number of strip 0 of this chunk
-                    for (int d = 0; d < DY; ++d) {
-                        const int s_lo = d == 0 ? 0 : R - 1 + d, s_hi = R - 1 + d;
-                        for (int s = s_lo; s <= s_hi; ++s, ++aq) mbar_wait(&a_full[aq % C::NA], (aq / C::NA) & 1);
-                        for (int t = tp.gstart[d]; t < tp.gstart[d + 1]; ++t, ++bq) {
-                            const int bslot = bq % C::NB;
-                            mbar_wait(&b_full[bslot], (bq / C::NB) & 1);
-                            tc_fence_after();
-                            {
-                                const uint64_t db = umma_desc_sw128(smem_u32(b_ring + bslot * B_BYTES));
-                                const int sh = tp.shift[t];
-                                const uint32_t first = (uint32_t)(kc | t);
-#pragma unroll
-                                for (int j = 0; j < R; ++j) {
-                                    const uint32_t sq = a_base + j + d;
-                                    const uint64_t da = umma_desc_sw128(smem_u32(a_ring + (sq % C::NA) * A2_SLOT) + 128 * sh);
-                                    if (elect_one()) {
-#pragma unroll
-                                        for (int k = 0; k < BK / UMMA_K; ++k)
-                                            tc_mma_f16(acc0 + j * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, first | (uint32_t)k);
-                                    }
-                                }
-                                if (elect_one()) tc_commit(&b_empty[bslot]);
-                            }
-                            __syncwarp();
-                        }
-                        // strips no later group needs: strip d after group d; everything left after the last group
-                        if (d < DY - 1) {
-                            if (elect_one()) tc_commit(&a_empty[(a_base + d) % C::NA]);
-                        } else {
-                            for (int s = DY - 1; s < NS; ++s) { if (elect_one()) tc_commit(&a_empty[(a_base + s) % C::NA]); }
-                        }
-                        __syncwarp();
-                    }
-                }
-                if (elect_one()) tc_commit(&acc_full[buf]);
-                __syncwarp();
-            }
-        }
-    } else {
-        // ===== epilogue: warps 2..5 own TMEM lanes [32*(warp%4), +32) =====
-        const int q = warp & 3, m = q * 32 + lane;
-        const bool want_rgb = (a.mode == kToRgbFinal) || (a.mode == kActRgb);
-        const int CW = a.n_blocks * BN;                                      // channels ToRGB sums over
-        uint32_t it = 0;
-        int n_loaded = -1;
-        for (int unit = blockIdx.x; unit < a.total_units; unit += gridDim.x) {
-            int n, ph, row0, col0; decode(unit, n, ph, row0, col0);
-            const Phase2& P = a.ph[ph];
-            const int wn = a.w_shared ? 0 : n;
-            if (want_rgb && wn != n_loaded) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");               // all four epilogue warps are done with the old weights
-                for (int e = threadIdx.x - 64; e < 3 * CW; e += 128) s_wrgb[e] = a.wrgb[(size_t)wn * 3 * CW + e];
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                n_loaded = wn;
-            }
-            const int gcol = col0 + m, X = gcol * a.ox_mul + P.ox_off;
-            float rgb[R][3];
-#pragma unroll
-            for (int j = 0; j < R; ++j) { rgb[j][0] = 0.f; rgb[j][1] = 0.f; rgb[j][2] = 0.f; }
-            for (int nblk = 0; nblk < a.n_blocks; ++nblk, ++it) {
-                const int buf = it % C::NACC;
-                mbar_wait(&acc_full[buf], (it / C::NACC) & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const int row = row0 + j;
-                    const int Y = row * a.oy_mul + P.oy_off;
-                    const bool in_img = (row < P.rows) && (Y < a.out_H) && (X < a.out_W);
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (R * BN) + j * BN;
-                    __half* dst = a.out + (((size_t)n * a.out_H + Y) * a.out_W + X) * a.out_C + nblk * BN;
-#pragma unroll 1
-                    for (int c0 = 0; c0 < BN; c0 += 32) {
-                        uint32_t r[32];
-                        tc_ld32(taddr + c0, r);
-                        float f[32];
-                        if (a.mode == kStoreRaw) {
-#pragma unroll
-                            for (int jj = 0; jj < 32; ++jj) f[jj] = __uint_as_float(r[jj]);
-                        } else {
-#pragma unroll
-                            for (int jj = 0; jj < 32; ++jj) {
-                                const float v = __uint_as_float(r[jj]) + s_bias[nblk * BN + c0 + jj];
-                                f[jj] = (v < 0.f ? v * a.act_slope : v) * a.act_gain;        // bias_act lrelu*sqrt2 | nn.LeakyReLU | linear
-                            }
-                        }
-                        if (a.mode != kToRgbFinal && in_img) store_half32(dst + c0, f);
-                        if (want_rgb) {
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                const float4* w4 = reinterpret_cast<const float4*>(s_wrgb + c * CW + nblk * BN + c0);
-                                float acc = rgb[j][c];
-#pragma unroll
-                                for (int j4 = 0; j4 < 8; ++j4) {
-                                    const float4 w = w4[j4];
-                                    acc = fmaf(f[4 * j4 + 0], w.x, acc); acc = fmaf(f[4 * j4 + 1], w.y, acc);
-                                    acc = fmaf(f[4 * j4 + 2], w.z, acc); acc = fmaf(f[4 * j4 + 3], w.w, acc);
-                                }
-                                rgb[j][c] = acc;
-                            }
-                        }
-                    }
-                    if (want_rgb && nblk == a.n_blocks - 1 && in_img) {
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            float skip = 0.f;
-                            if (a.img_prev) skip = a.skip_same_res ? __ldg(a.img_prev + (((size_t)n * 3 + c) * a.img_H + Y) * a.img_W + X)
-                                                                   : upsampled_skip(a.img_prev + ((size_t)n * 3 + c) * (a.img_H / 2) * (a.img_W / 2),
-                                                                                    a.img_H / 2, a.img_W / 2, Y, X);
-                            a.img_out[(((size_t)n * 3 + c) * a.img_H + Y) * a.img_W + X] = rgb[j][c] + a.brgb[c] + skip;
-                        }
-                    }
-                }
-                // this warp is done reading the accumulator buffer
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
     }
 }
 
@@ -949,8 +551,15 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                     ET_BEGIN();
                     if (want_rgb && nblk == a.n_blocks - 1 && in_img && cg == 0) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c)
-                            a.img_out[(((size_t)n * 3 + c) * a.img_H + Y) * a.img_W + X] = rgb2[j][c].x + brgb[c];
+                        for (int c = 0; c < 3; ++c) {
+                            float v = rgb2[j][c].x + brgb[c];
+                            if (a.out_clamp) v = fminf(fmaxf(v, -1.0f), 1.0f);
+                            if (a.img_out_u8)          // torch: ((x + 1) / 2 * 255.).int() -> uint8, every step rounded in fp32, truncation
+                                a.img_out_u8[(((size_t)n * a.img_H + Y) * a.img_W + X) * 3 + c] =
+                                    (uint8_t)(int)__fmul_rn(__fmul_rn(__fadd_rn(v, 1.0f), 0.5f), 255.0f);
+                            else
+                                a.img_out[(((size_t)n * 3 + c) * a.img_H + Y) * a.img_W + X] = v;
+                        }
                     }
                     ET_END(e_fin);
                 }
@@ -1267,26 +876,9 @@ static int make_map_fir(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d
 
 static int launch_conv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, const ConvArgs& a1, cudaStream_t st);
 static int launch_upconv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, __half* yb, const float* bias, cudaStream_t st);
-static int tc_version();
 static int launch_conv(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, ConvArgs a, cudaStream_t st) {
-    if (tc_version() >= 2) return launch_conv2(x, N, H, W, Cp, wp, Nw, O, a, st);
-    CUtensorMap tmA, tmB;
-    if (make_map_4d(&tmA, x, (uint64_t)Cp, (uint64_t)W, (uint64_t)H, (uint64_t)N, BM)) return 1;
-    if (make_map_4d(&tmB, wp, (uint64_t)Cp, (uint64_t)O, 9, (uint64_t)Nw, BN)) return 1;
-    a.k_chunks = Cp / BK;
-    a.w_shared = (Nw == 1);
-    static bool attr_set = false;
-    if (!attr_set) {
-        R3DP_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
-    dim3 grid(a.tiles_x * a.rows, O / BN, N);
-    conv_tc_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(tmA, tmB, a);
-    R3DP_LAUNCH_CHECK();
-    count_launches(1);
-    return 0;
+    return launch_conv2(x, N, H, W, Cp, wp, Nw, O, a, st);
 }
-
 
 // ---- optional in-library timing of the conv launches (bench.py's roofline): CUDA events on the launching stream around each launch --------
 struct ConvProf { bool on = false; std::vector<cudaEvent_t> ev; size_t used = 0; };
@@ -1299,12 +891,6 @@ static void prof_mark(cudaStream_t st) {
 
 static unsigned long long* g_debug_buf = nullptr;
 static int g_debug_launch = 0;
-static int tc_version() {                      // R3DP_TC_KERNEL=1: simple v1 kernel; 2: single-CTA persistent v2; 3 (default): CTA pairs
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("R3DP_TC_KERNEL"); v = (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 3); }
-    return v;
-}
-static bool tc_pairs() { return tc_version() == 3; }
 static int tc_rows() {                         // R3DP_TC_ROWS = 1 | 2 | 4 output rows per tile (default 2: double-buffered accumulators)
     static int v = -1;
     if (v < 0) { const char* e = getenv("R3DP_TC_ROWS"); v = e ? atoi(e) : 2; if (v != 1 && v != 2 && v != 4) v = 2; }
@@ -1314,11 +900,7 @@ static int tc_rows() {                         // R3DP_TC_ROWS = 1 | 2 | 4 outpu
 template <int R>
 static int launch_conv3_r(const CUtensorMap& tmA, const CUtensorMap& tmB, Conv2Args a, int max_rows, cudaStream_t st) {
     using C = Cfg3<R>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        R3DP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr_set = true;
-    }
+            R3DP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     a.debug = g_debug_buf ? g_debug_buf + 24 * (g_debug_launch++ % 32) : nullptr;
     a.row_groups = (max_rows + R - 1) / R;
     if ((a.row_groups * a.tiles_x) & 1) a.row_groups += 1;       // the two CTAs of a pair must work on units of the same (image, phase)
@@ -1334,25 +916,6 @@ static int launch_conv3_r(const CUtensorMap& tmA, const CUtensorMap& tmB, Conv2A
     prof_mark(st);
     R3DP_CUDA(cudaLaunchKernelEx(&cfg, conv_tc3_kernel<R>, tmA, tmB, a));
     prof_mark(st);
-    count_launches(1);
-    return 0;
-}
-
-template <int R>
-static int launch_conv2_r(const CUtensorMap& tmA, const CUtensorMap& tmB, Conv2Args a, int max_rows, cudaStream_t st) {
-    using C = Cfg2<R>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        R3DP_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr_set = true;
-    }
-    a.row_groups = (max_rows + R - 1) / R;
-    a.total_units = a.n_images * a.n_phases * a.row_groups * a.tiles_x;
-    const int grid = a.total_units < sm_count() ? a.total_units : sm_count();
-    prof_mark(st);
-    conv_tc2_kernel<R><<<grid, kThreads, C::SMEM, st>>>(tmA, tmB, a);
-    prof_mark(st);
-    R3DP_LAUNCH_CHECK();
     count_launches(1);
     return 0;
 }
@@ -1381,16 +944,11 @@ static void fill_taps2(Taps2& t2, const Taps& t) {
 static int run_conv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, Conv2Args& a, int max_rows, cudaStream_t st, int n_taps = 9) {
     CUtensorMap tmA, tmB;
     if (make_map_4d_box(&tmA, x, (uint64_t)Cp, (uint64_t)W, (uint64_t)H, (uint64_t)N, A2_ROWS)) return 1;
-    if (make_map_4d_box(&tmB, wp, (uint64_t)Cp, (uint64_t)O, (uint64_t)n_taps, (uint64_t)Nw, tc_pairs() ? BN / 2 : BN)) return 1;
+    if (make_map_4d_box(&tmB, wp, (uint64_t)Cp, (uint64_t)O, (uint64_t)n_taps, (uint64_t)Nw, BN / 2)) return 1;
     a.k_chunks = Cp / BK; a.tiles_x = W / BM; a.n_blocks = O / BN; a.n_images = N; a.w_shared = (Nw == 1);
     if (a.act_gain == 0.f) { a.act_slope = 0.2f; a.act_gain = 1.4142135623730951f; }      // default: bias_act lrelu
-    R3DP_REQUIRE(a.n_blocks >= 1 && a.n_blocks <= 2, "conv_tc2: 128 or 256 output channels");
-    if (tc_pairs()) return tc_rows() == 1 ? launch_conv3_r<1>(tmA, tmB, a, max_rows, st) : (tc_rows() == 4 ? launch_conv3_r<4>(tmA, tmB, a, max_rows, st) : launch_conv3_r<2>(tmA, tmB, a, max_rows, st));
-    switch (tc_rows()) {
-        case 1: return launch_conv2_r<1>(tmA, tmB, a, max_rows, st);
-        case 4: return launch_conv2_r<4>(tmA, tmB, a, max_rows, st);
-        default: return launch_conv2_r<2>(tmA, tmB, a, max_rows, st);
-    }
+    R3DP_REQUIRE(a.n_blocks >= 1 && a.n_blocks <= 2, "conv_tc3: 128 or 256 output channels");
+    return tc_rows() == 1 ? launch_conv3_r<1>(tmA, tmB, a, max_rows, st) : (tc_rows() == 4 ? launch_conv3_r<4>(tmA, tmB, a, max_rows, st) : launch_conv3_r<2>(tmA, tmB, a, max_rows, st));
 }
 
 // v1-style single-phase description -> v2 launch
@@ -1401,6 +959,7 @@ static int launch_conv2(const void* x, int N, int H, int W, int Cp, const void* 
     a.ph[0].rows = a1.rows; a.ph[0].oy_off = a1.oy_off; a.ph[0].ox_off = a1.ox_off;
     a.mode = a1.mode; a.out = a1.out; a.out_H = a1.out_H; a.out_W = a1.out_W; a.out_C = a1.out_C; a.oy_mul = a1.oy_mul; a.ox_mul = a1.ox_mul;
     a.bias = a1.bias; a.wrgb = a1.wrgb; a.brgb = a1.brgb; a.img_prev = a1.img_prev; a.img_out = a1.img_out; a.img_H = a1.out_H; a.img_W = a1.out_W;
+    a.out_clamp = a1.out_clamp; a.img_out_u8 = a1.img_out_u8;
     return run_conv2(x, N, H, W, Cp, wp, Nw, O, a, a1.rows, st);
 }
 
@@ -1472,29 +1031,12 @@ extern "C" int r3dp_sr_tc_layer(const void* x_f16, const void* wp_f16, const flo
     }
     R3DP_REQUIRE(scratch, "sr_tc_layer: up=2 needs scratch");
     __half* yb = reinterpret_cast<__half*>(scratch);
-    if (tc_version() >= 2) {
-        if (launch_upconv2(x_f16, N, H, W, Ip, wp_f16, Nw, O, yb, bias, st)) return 1;
-    } else {
-        a.mode = kStoreRaw; a.out = yb; a.out_H = 2 * H + 1; a.out_W = 2 * W + 1; a.out_C = O; a.oy_mul = a.ox_mul = 2;
-        a.tiles_x = W / BM;
-        for (int pa = 0; pa < 2; ++pa)
-            for (int pb = 0; pb < 2; ++pb) {
-                a.oy_off = pa; a.ox_off = pb; a.rows = pa ? H : H + 1;
-                a.taps.n = 0;
-                for (int ky = pa; ky < 3; ky += 2)
-                    for (int kx = pb; kx < 3; kx += 2) {
-                        const int t = a.taps.n++;
-                        a.taps.dy[t] = -(ky >> 1); a.taps.dx[t] = -(kx >> 1); a.taps.widx[t] = ky * 3 + kx;
-                    }
-                if (launch_conv(x_f16, N, H, W, Ip, wp_f16, Nw, O, a, st)) return 1;
-            }
-    }
+    if (launch_upconv2(x_f16, N, H, W, Ip, wp_f16, Nw, O, yb, bias, st)) return 1;
     {
         R3DP_REQUIRE(Ip <= 256, "sr_tc_layer: up=2 supports at most 256 input channels");
         dim3 grid((2 * H + 1 + kEdgeRows - 1) / kEdgeRows, (O + kEdgeCo - 1) / kEdgeCo, N);
         const size_t esmem = ((size_t)(kEdgeRows / 2 + 2) * Ip + 3 * (size_t)kEdgeCo * (Ip + 8)) * sizeof(__half);
-        static bool eattr = false;
-        if (!eattr) { R3DP_CUDA(cudaFuncSetAttribute(upconv_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); eattr = true; }
+        R3DP_CUDA(cudaFuncSetAttribute(upconv_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         upconv_edge_kernel<<<grid, 256, esmem, st>>>(reinterpret_cast<const __half*>(x_f16), reinterpret_cast<const __half*>(wp_f16), H, W, Ip, O,
                                                  Nw == 1, yb);
     }
@@ -1502,11 +1044,7 @@ extern "C" int r3dp_sr_tc_layer(const void* x_f16, const void* wp_f16, const flo
         R3DP_REQUIRE((2 * W) % FIR_TW == 0 && O % 64 == 0, "sr_tc_layer: FIR needs 2W %% 32 == 0 and Cout %% 64 == 0");
         CUtensorMap tmY;
         if (make_map_fir(&tmY, yb, (uint64_t)O, (uint64_t)(2 * W + 1), (uint64_t)(2 * H + 1), (uint64_t)N)) return 1;
-        static bool attr_set = false;
-        if (!attr_set) {
-            R3DP_CUDA(cudaFuncSetAttribute(fir_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIR_SMEM));
-            attr_set = true;
-        }
+                    R3DP_CUDA(cudaFuncSetAttribute(fir_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIR_SMEM));
         const int total = N * (O / 64) * ((2 * H + FIR_TH - 1) / FIR_TH) * (2 * W / FIR_TW);
         const int grid = total < 2 * sm_count() ? total : 2 * sm_count();
         fir_tma_kernel<<<grid, 256, FIR_SMEM, st>>>(tmY, bias, N, 2 * H, 2 * W, O, reinterpret_cast<__half*>(y_f16));
@@ -1518,17 +1056,22 @@ extern "C" int r3dp_sr_tc_layer(const void* x_f16, const void* wp_f16, const flo
 
 // Last layer fused with ToRGB: conv3x3 (I -> 128) + bias + lrelu, then img_out = upsample2d(img_prev) + torgb + brgb; the 128-channel
 // activation itself is never written (SynthesisBlock is_last: only the image leaves the block).
-extern "C" int r3dp_sr_tc_last_layer(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
-                                     const float* img_prev, int N, int Nw, int I, int H, int W, float* img_out, r3dp_stream_t stream) {
-    R3DP_REQUIRE(x_f16 && wp_f16 && bias && wrgb && brgb && img_out, "sr_tc_last_layer: null pointer");
+extern "C" int r3dp_sr_tc_last_layer_ex(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
+                                        const float* img_prev, int N, int Nw, int I, int H, int W, float* img_out, uint8_t* img_out_u8, int clamp,
+                                        r3dp_stream_t stream) {
+    R3DP_REQUIRE(x_f16 && wp_f16 && bias && wrgb && brgb && (img_out || img_out_u8), "sr_tc_last_layer: null pointer");
     R3DP_REQUIRE(N > 0 && (Nw == N || Nw == 1) && W % BM == 0 && H % 2 == 0, "sr_tc_last_layer: bad shape");
     const int Ip = (I + 63) / 64 * 64;
     ConvArgs a = {};
-    a.bias = bias; a.wrgb = wrgb; a.brgb = brgb; a.img_prev = img_prev; a.img_out = img_out;
+    a.bias = bias; a.wrgb = wrgb; a.brgb = brgb; a.img_prev = img_prev; a.img_out = img_out; a.img_out_u8 = img_out_u8; a.out_clamp = clamp || img_out_u8;
     a.taps.n = 9;
     for (int t = 0; t < 9; ++t) { a.taps.dy[t] = t / 3 - 1; a.taps.dx[t] = t % 3 - 1; a.taps.widx[t] = t; }
     a.tiles_x = W / BM; a.rows = H; a.mode = kToRgbFinal; a.out_H = H; a.out_W = W; a.out_C = BN; a.oy_mul = a.ox_mul = 1;
     return launch_conv(x_f16, N, H, W, Ip, wp_f16, Nw, BN, a, as_stream(stream));
+}
+extern "C" int r3dp_sr_tc_last_layer(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
+                                     const float* img_prev, int N, int Nw, int I, int H, int W, float* img_out, r3dp_stream_t stream) {
+    return r3dp_sr_tc_last_layer_ex(x_f16, wp_f16, bias, wrgb, brgb, img_prev, N, Nw, I, H, W, img_out, nullptr, 0, stream);
 }
 
 // ToRGB of a non-final block: x NHWC fp16 [N][H][W][C] -> img_out NCHW fp32 [N][3][H][W] (+ upsample2d(img_prev) + bias).
@@ -1658,7 +1201,6 @@ extern "C" int r3dp_sr_tc_layer_up_composed(const void* x_f16, const void* wpc_f
                                             int W, void* y_f16, r3dp_stream_t stream) {
     R3DP_REQUIRE(x_f16 && wpc_f16 && bias && y_f16, "sr_tc_layer_up_composed: null pointer");
     R3DP_REQUIRE(N > 0 && (Nw == N || Nw == 1) && W % BM == 0 && O % BN == 0 && O <= 256, "sr_tc_layer_up_composed: bad shape");
-    R3DP_REQUIRE(tc_version() >= 2, "sr_tc_layer_up_composed needs the persistent conv kernels");
     const int Ip = (I + 63) / 64 * 64;
     Conv2Args a = {};
     a.n_phases = 4;
@@ -1683,7 +1225,6 @@ extern "C" int r3dp_sr_tc_conv(const void* x_f16, const void* wp_f16, const floa
     R3DP_REQUIRE(x_f16 && wp_f16 && bias && y_f16, "sr_tc_conv: null pointer");
     R3DP_REQUIRE(N > 0 && (Nw == N || Nw == 1) && W % BM == 0 && O % BN == 0 && O <= 256 && (ksize == 1 || ksize == 3) && act >= 0 && act <= 2,
                  "sr_tc_conv: bad shape / options");
-    R3DP_REQUIRE(tc_version() >= 2, "sr_tc_conv needs the persistent conv kernels");
     const int Ip = (I + 63) / 64 * 64;
     Conv2Args a = {};
     Taps t = {};
@@ -1720,14 +1261,15 @@ extern "C" int r3dp_sr_tc_layer_torgb_noup(const void* x_f16, const void* wp_f16
 
 // out[n,y,x,:] = [ xa[n,y,x,0:Ca] * alpha[n,y,x] , xb[n,y,x,0:Cb] * (1 - alpha[n,y,x]) ]   (sr_with_ref.py:111,122: alpha-cat fusion), fp16 NHWC
 __global__ void alpha_cat_kernel(const __half* __restrict__ xa, int Ca, int sa, const __half* __restrict__ xb, int Cb, int sb,
-                                 const float* __restrict__ alpha, long long npix, __half* __restrict__ out) {
+                                 long long hw_b, const float* __restrict__ alpha, long long npix, __half* __restrict__ out) {
     const int cv = (Ca + Cb) / 8;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= npix * cv) return;
     const long long pix = idx / cv; const int c8 = (int)(idx - pix * cv);
     const float al = alpha[pix];
     const bool first = c8 * 8 < Ca;
-    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(first ? xa + pix * sa + c8 * 8 : xb + pix * sb + (c8 * 8 - Ca)));
+    const long long pb = hw_b > 0 ? pix % hw_b : pix;                    // xb holds one frame shared by the batch
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(first ? xa + pix * sa + c8 * 8 : xb + pb * sb + (c8 * 8 - Ca)));
     const float m = first ? al : 1.0f - al;
     const __half2* h = reinterpret_cast<const __half2*>(&raw);
     uint4 pk; __half2* ph = reinterpret_cast<__half2*>(&pk);
@@ -1735,17 +1277,21 @@ __global__ void alpha_cat_kernel(const __half* __restrict__ xa, int Ca, int sa, 
     for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); ph[j] = __floats2half2_rn(f.x * m, f.y * m); }
     *reinterpret_cast<uint4*>(out + idx * 8) = pk;
 }
-extern "C" int r3dp_sr_alpha_cat(const void* xa_f16, int Ca, int stride_a, const void* xb_f16, int Cb, int stride_b, const float* alpha, int N,
-                                 int H, int W, void* out_f16, r3dp_stream_t stream) {
+extern "C" int r3dp_sr_alpha_cat_ex(const void* xa_f16, int Ca, int stride_a, const void* xb_f16, int Cb, int stride_b, int xb_shared,
+                                    const float* alpha, int N, int H, int W, void* out_f16, r3dp_stream_t stream) {
     R3DP_REQUIRE(xa_f16 && xb_f16 && alpha && out_f16, "sr_alpha_cat: null pointer");
     R3DP_REQUIRE(N > 0 && H > 0 && W > 0 && Ca % 8 == 0 && Cb % 8 == 0 && stride_a >= Ca && stride_b >= Cb && stride_a % 8 == 0 && stride_b % 8 == 0,
                  "sr_alpha_cat: bad shape");
     const long long npix = (long long)N * H * W, total = npix * ((Ca + Cb) / 8);
     alpha_cat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(xa_f16), Ca, stride_a,
-        reinterpret_cast<const __half*>(xb_f16), Cb, stride_b, alpha, npix, reinterpret_cast<__half*>(out_f16));
+        reinterpret_cast<const __half*>(xb_f16), Cb, stride_b, xb_shared ? (long long)H * W : 0ll, alpha, npix, reinterpret_cast<__half*>(out_f16));
     R3DP_LAUNCH_CHECK();
     count_launches(1);
     return 0;
+}
+extern "C" int r3dp_sr_alpha_cat(const void* xa_f16, int Ca, int stride_a, const void* xb_f16, int Cb, int stride_b, const float* alpha, int N,
+                                 int H, int W, void* out_f16, r3dp_stream_t stream) {
+    return r3dp_sr_alpha_cat_ex(xa_f16, Ca, stride_a, xb_f16, Cb, stride_b, 0, alpha, N, H, W, out_f16, stream);
 }
 
 // out = a * alpha + b * (1 - alpha), fp32 NCHW [N,C,H,W] with alpha [N,1,H,W]  (sr_with_ref.py:110,132)
@@ -1820,7 +1366,7 @@ extern "C" int r3dp_sr_resize_aa_down2(const float* x, int N, int C, int h_out, 
     return 0;
 }
 
-// Timing of the tensor-core conv launches: r3dp_sr_tc_prof(1) starts recording a CUDA-event pair around every conv_tc2/3 launch,
+// Timing of the tensor-core conv launches: r3dp_sr_tc_prof(1) starts recording a CUDA-event pair around every conv_tc3 launch,
 // r3dp_sr_tc_prof(0) stops; r3dp_sr_tc_prof_read synchronises the recorded events and returns their summed duration and count.
 extern "C" int r3dp_sr_tc_prof(int enable) { g_prof.on = enable != 0; if (enable) g_prof.used = 0; return 0; }
 extern "C" int r3dp_sr_tc_prof_read(float* total_ms, int* launches) {

@@ -26,20 +26,38 @@ def generate_planes() -> torch.Tensor:
 
 
 class PlanesCL:
-    """Tri-planes already in the gather layout [N,3,H,W,C] (one texel = one 128-byte line)."""
+    """Tri-planes in a channels-last gather layout (one texel's C features = one contiguous 128-byte line).
 
-    def __init__(self, data: torch.Tensor):
+    layout 'phwc': data [N,3,H,W,C]  (what r3dp_planes_to_channels_last writes)
+    layout 'hwpc': data [N,H,W,3,C]  = the plane producer's [N,3*C,H,W] conv output held in torch.channels_last memory
+                   (modules/real3d/secc_img2plane.py:73-81 views exactly such a tensor as [B,3,C,H,W]): zero-copy, no repack at all.
+    A set with N == 1 may be shared by every frame of a call (frame stride 0): the per-clip canonical planes."""
+
+    def __init__(self, data: torch.Tensor, layout: str = 'phwc'):
+        assert layout in ('phwc', 'hwpc'), layout
         assert data.ndim == 5 and data.is_cuda and data.dtype == torch.float32 and data.is_contiguous()
-        self.data = data
+        self.data, self.layout = data, layout
 
     @property
     def dims(self):
-        N, _, H, W, Cc = self.data.shape
+        if self.layout == 'phwc':
+            N, _, H, W, Cc = self.data.shape
+        else:
+            N, H, W, _, Cc = self.data.shape
         return N, Cc, H, W
+
+    def c_layout(self, n_frames: int) -> capi.PlaneLayout:
+        N, Cc, H, W = self.dims
+        if N != n_frames and N != 1:
+            raise ValueError(f'plane set holds {N} frames, the call renders {n_frames}')
+        frame = 0 if (N == 1 and n_frames > 1) else 3 * H * W * Cc
+        if self.layout == 'phwc':
+            return capi.PlaneLayout(frame, H * W * Cc, W * Cc, Cc)
+        return capi.PlaneLayout(frame, Cc, W * 3 * Cc, 3 * Cc)
 
 
 def planes_to_channels_last(planes: torch.Tensor, out: Optional[torch.Tensor] = None) -> PlanesCL:
-    """[N,3,C,H,W] (reference layout, secc_img2plane.py:105-110) -> PlanesCL."""
+    """[N,3,C,H,W] (reference layout, secc_img2plane.py:105-110) -> PlanesCL ('phwc')."""
     planes = capi.f32(planes)
     assert planes.ndim == 5 and planes.shape[1] == 3, planes.shape
     N, _, Cc, H, W = planes.shape
@@ -50,8 +68,49 @@ def planes_to_channels_last(planes: torch.Tensor, out: Optional[torch.Tensor] = 
     return PlanesCL(out)
 
 
+def producer_view(planes: torch.Tensor) -> Optional[PlanesCL]:
+    """If `planes` [N,3,C,H,W] (or [N,3*C,H,W]) is a VIEW of a channels_last conv output - memory order [N,H,W,3,C] - wrap it without
+    copying; otherwise None.  (`x.to(memory_format=torch.channels_last)` on the producer's last conv makes its output such a tensor.)"""
+    t = planes.detach()
+    if t.dtype != torch.float32 or not t.is_cuda:
+        return None
+    if t.ndim == 4 and t.shape[1] % 3 == 0:
+        t = t.view(t.shape[0], 3, t.shape[1] // 3, t.shape[2], t.shape[3]) if t.is_contiguous(memory_format=torch.channels_last) else None
+        if t is None:
+            return None
+    if t.ndim != 5 or t.shape[1] != 3:
+        return None
+    N, _, Cc, H, W = t.shape
+    if tuple(t.stride()) != (H * W * 3 * Cc, Cc, 1, W * 3 * Cc, 3 * Cc):
+        return None
+    return PlanesCL(t.permute(0, 3, 4, 1, 2), 'hwpc')          # [N,H,W,3,C], contiguous by construction
+
+
 def _as_cl(planes: Union[torch.Tensor, PlanesCL]) -> PlanesCL:
-    return planes if isinstance(planes, PlanesCL) else planes_to_channels_last(planes)
+    if isinstance(planes, PlanesCL):
+        return planes
+    pv = producer_view(planes)
+    return pv if pv is not None else planes_to_channels_last(planes)
+
+
+def _plane_sets(planes):
+    """planes | PlanesCL | (a, b) pair of either -> (first, second-or-None); a pair is sampled set by set and summed in-kernel
+    (`cano_planes + secc_planes`, secc_img2plane.py:73-81, without materialising the sum)."""
+    if isinstance(planes, (tuple, list)):
+        assert len(planes) == 2, 'at most two plane sets'
+        a, b = _as_cl(planes[0]), _as_cl(planes[1])
+        if a.layout != b.layout or a.dims[1:] != b.dims[1:]:
+            raise ValueError('the two plane sets must share layout and shape')
+        return a, b
+    return _as_cl(planes), None
+
+
+def _as_phwc(planes) -> PlanesCL:
+    """The stand-alone sampler / run_model kernels read the 'phwc' layout only."""
+    pcl = _as_cl(planes)
+    if pcl.layout != 'phwc':
+        pcl = PlanesCL(pcl.data.permute(0, 3, 1, 2, 4).contiguous(), 'phwc')
+    return pcl
 
 
 def sample_from_planes(plane_axes, plane_features, coordinates, mode='bilinear', padding_mode='zeros', box_warp=None):
@@ -59,7 +118,7 @@ def sample_from_planes(plane_axes, plane_features, coordinates, mode='bilinear',
     assert padding_mode == 'zeros' and mode == 'bilinear'
     if plane_axes is not None and not torch.equal(plane_axes.detach().cpu().float(), generate_planes()):
         raise NotImplementedError('only the reference plane axes (generate_planes()) are built')
-    pcl = _as_cl(plane_features)
+    pcl = _as_phwc(plane_features)
     N, Cc, H, W = pcl.dims
     coords = capi.f32(coordinates)
     P = coords.shape[1]
@@ -95,10 +154,10 @@ class ImportanceRenderer(torch.nn.Module):
             raise NotImplementedError('training-time density noise / plane rescaling are outside the inference path')
         if not isinstance(decoder, OSGDecoder):
             raise TypeError('the fused renderer needs an OSGDecoder (its four parameter tensors are read by the kernel)')
-        pcl = _as_cl(planes)
-        N, Cc, H, W = pcl.dims
+        pcl, pcl2 = _plane_sets(planes)
+        _, Cc, H, W = pcl.dims
         ray_o, ray_d = capi.f32(ray_origins), capi.f32(ray_directions)
-        M = ray_o.shape[1]
+        N, M = ray_o.shape[0], ray_o.shape[1]
         S, S_imp = int(opt['depth_resolution']), int(opt.get('depth_resolution_importance', 0) or 0)
         dev = ray_o.device
         u_c = opt.get('u_coarse')
@@ -117,18 +176,25 @@ class ImportanceRenderer(torch.nn.Module):
         ws_bytes = L.r3dp_render_workspace_bytes(N, M)
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         m = decoder.mlp_struct()
+        g = capi.RenderArgs()
+        g.planes, g.layout = capi.ptr(pcl.data).value, pcl.c_layout(N)
+        if pcl2 is not None:
+            g.planes2, g.layout2 = capi.ptr(pcl2.data).value, pcl2.c_layout(N)
+        g.N, g.C, g.H, g.W, g.M, g.res, g.S, g.S_imp = N, Cc, H, W, M, res, S, S_imp
+        g.ray_o, g.ray_d, g.camera = capi.ptr(ray_o).value, capi.ptr(ray_d).value, None
+        g.box_warp, g.white_back = float(opt['box_warp']), int(bool(opt.get('white_back', False)))
+        g.u_coarse, g.u_fine, g.mlp = capi.ptr(u_c).value, capi.ptr(u_f).value, C.pointer(m)
+        g.rgb, g.depth, g.weights_sum = capi.ptr(rgb).value, capi.ptr(depth).value, capi.ptr(wsum).value
+        g.is_ray_valid, g.workspace, g.workspace_bytes = capi.ptr(valid, torch.bool).value, capi.ptr(ws, torch.uint8).value, ws_bytes
         with capi.region('render'):
-            capi.check(L.r3dp_render(capi.ptr(pcl.data), N, Cc, H, W, capi.ptr(ray_o), capi.ptr(ray_d), None, M, res, S, S_imp,
-                                     float(opt['box_warp']), int(bool(opt.get('white_back', False))),
-                                     capi.ptr(u_c), capi.ptr(u_f), C.byref(m), capi.ptr(rgb), capi.ptr(depth), capi.ptr(wsum),
-                                     capi.ptr(valid, torch.bool), capi.ptr(ws, torch.uint8), ws_bytes, capi.stream()))
+            capi.check(L.r3dp_render_ex(C.byref(g), capi.stream()))
         return rgb, depth, wsum, valid
 
     def run_model(self, planes, decoder, sample_coordinates, sample_directions, options):
         """renderer.py:169-188: planes, coords [N,P,3] -> {'rgb': [N,P,C], 'sigma': [N,P,1]}."""
         if options.get('density_noise', 0) > 0:
             raise NotImplementedError('density_noise is a training-time option')
-        pcl = _as_cl(planes)
+        pcl = _as_phwc(planes)
         N, Cc, H, W = pcl.dims
         coords = capi.f32(sample_coordinates)
         P = coords.shape[1]

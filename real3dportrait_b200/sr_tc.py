@@ -86,9 +86,11 @@ class Prepared:
 
 
 def forward(sr, rgb: torch.Tensor, x: torch.Tensor, ws3: torch.Tensor, shared_styles: Optional[bool] = None,
-            x_nhwc: Optional[torch.Tensor] = None) -> torch.Tensor:
+            x_nhwc: Optional[torch.Tensor] = None, out_clamp: bool = False, out_uint8: bool = False) -> torch.Tensor:
     """rgb [N,3,h,w], x [N,C,h,w] (fp32 NCHW, h <= 128), ws3 [N,3,512] -> [N,3,512,512] fp32.
     x_nhwc: the same features channels-last [N,h,w,C] (the renderer's native output) - skips a layout round trip.
+    out_clamp: the image leaves the last epilogue clamped to [-1,1]; out_uint8: it leaves as uint8 HWC frames [N,512,512,3]
+    (the caller loop's conversion, inference/real3d_infer.py:515-519, fused).
     If `sr.static_prepared` is set (caller guarantees constant styles, e.g. Real3D's ws == 1) the weight preparation
     (styles -> fold -> demod -> fp16 pack) is skipped."""
     from .superresolution import SuperresolutionHybrid8XDC
@@ -117,9 +119,10 @@ def forward(sr, rgb: torch.Tensor, x: torch.Tensor, ws3: torch.Tensor, shared_st
                                             capi.ptr(prep.wrgb0), capi.ptr(capi.f32(b0.torgb.bias)), capi.ptr(rgb0), N, Nw, 256, 256, 256, 256,
                                             capi.ptr(a1, torch.float16), capi.ptr(img1), capi.stream()))
     a2 = layer(a1, b1.conv0, wp[2], 2)
-    out = torch.empty(N, 3, 512, 512, device=x.device)
+    out = torch.empty(N, 512, 512, 3, device=x.device, dtype=torch.uint8) if out_uint8 else torch.empty(N, 3, 512, 512, device=x.device)
     with capi.region('sr_conv'):                               # block1.conv1 + block1.torgb: the 128-channel activation is never written
-        capi.check(L.r3dp_sr_tc_last_layer(capi.ptr(a2, torch.float16), capi.ptr(wp[3], torch.float16), capi.ptr(capi.f32(b1.conv1.bias)),
-                                           capi.ptr(prep.wrgb1), capi.ptr(capi.f32(b1.torgb.bias)), capi.ptr(img1), N, Nw, 128, 512, 512,
-                                           capi.ptr(out), capi.stream()))
+        capi.check(L.r3dp_sr_tc_last_layer_ex(capi.ptr(a2, torch.float16), capi.ptr(wp[3], torch.float16), capi.ptr(capi.f32(b1.conv1.bias)),
+                                              capi.ptr(prep.wrgb1), capi.ptr(capi.f32(b1.torgb.bias)), capi.ptr(img1), N, Nw, 128, 512, 512,
+                                              None if out_uint8 else capi.ptr(out), capi.ptr(out, torch.uint8) if out_uint8 else None,
+                                              int(out_clamp or out_uint8), capi.stream()))
     return out

@@ -81,6 +81,8 @@ class SuperresolutionHybrid8XDC_Warp(SuperresolutionHybrid8XDC):
         self.fuse_fg_bg_convs = nn.Sequential(nn.Conv2d(512, 64, 1, 1, padding=0), nn.LeakyReLU(), nn.Conv2d(64, 256, 3, 1, padding=1),
                                               nn.LeakyReLU(), nn.Conv2d(256, 256, 3, 1, padding=1))
         self._plain_cache = None
+        self._clip_cache = None
+        self.static_prepared_warp = None
 
     # ---- weight preparation ------------------------------------------------------------------------------------------------
     def _plain(self) -> Dict[str, tuple]:
@@ -93,9 +95,13 @@ class SuperresolutionHybrid8XDC_Warp(SuperresolutionHybrid8XDC):
             }
         return self._plain_cache
 
-    def load_state_dict(self, *a, **k):
+    def _load_from_state_dict(self, *a, **k):
+        # runs for THIS module whenever it or any parent (RenderHead, FrameEngine.load_params) loads a state_dict: every cache that was
+        # derived from the parameters is dropped (packed fp16 conv weights, per-clip constants, prepared styles)
         self._plain_cache = None
-        return super().load_state_dict(*a, **k)
+        self._clip_cache = None
+        self.static_prepared_warp = None
+        return super()._load_from_state_dict(*a, **k)
 
     @staticmethod
     def _conv(x16: torch.Tensor, packed, act: int) -> torch.Tensor:
@@ -110,11 +116,27 @@ class SuperresolutionHybrid8XDC_Warp(SuperresolutionHybrid8XDC):
 
     @staticmethod
     def _alpha_cat(xa16, Ca, xb16, Cb, alpha) -> torch.Tensor:
+        """cat[xa*alpha, xb*(1-alpha)]; xb may hold ONE frame shared by the whole batch (per-clip constant features)."""
         N, H, W, _ = xa16.shape
         out = torch.empty(N, H, W, Ca + Cb, device=xa16.device, dtype=torch.float16)
-        capi.check(capi.lib().r3dp_sr_alpha_cat(capi.ptr(xa16, torch.float16), Ca, xa16.shape[-1], capi.ptr(xb16, torch.float16), Cb, xb16.shape[-1],
-                                                capi.ptr(alpha), N, H, W, capi.ptr(out, torch.float16), capi.stream()))
+        capi.check(capi.lib().r3dp_sr_alpha_cat_ex(capi.ptr(xa16, torch.float16), Ca, xa16.shape[-1], capi.ptr(xb16, torch.float16), Cb, xb16.shape[-1],
+                                                   int(xb16.shape[0] == 1 and N > 1), capi.ptr(alpha), N, H, W, capi.ptr(out, torch.float16), capi.stream()))
         return out
+
+    # ---- per-clip constants (SURVEY.md §8f #2) -------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def begin_clip(self, ref_torso_rgb: torch.Tensor, ref_bg_rgb: torch.Tensor) -> None:
+        """Hoist what the reference recomputes for every frame although it only depends on the clip's reference images
+        (sr_with_ref.py:77-90): the two antialiased 512->256 resizes and bg_encoder(ref_bg) (96.9 GFLOP/frame).  ref_* [1,3,512,512].
+        Until end_clip(), forward() ignores its ref_torso_rgb / ref_bg_rgb arguments and uses these."""
+        assert ref_torso_rgb.shape[0] == 1 and ref_bg_rgb.shape[0] == 1, 'one reference image per clip'
+        plain = self._plain()
+        t256, b256 = self._aa_down2(ref_torso_rgb), self._aa_down2(ref_bg_rgb)
+        x_bg = self._conv(self._conv(self._conv(sr_tc.to_nhwc_f16(b256, 256), plain['bg0'], 2), plain['bg2'], 2), plain['bg4'], 0)
+        self._clip_cache = {'ref_torso_256': t256, 'ref_bg_256': b256, 'x_bg': x_bg}
+
+    def end_clip(self) -> None:
+        self._clip_cache = None
 
     @staticmethod
     def _blend(a, b, alpha) -> torch.Tensor:
@@ -159,7 +181,11 @@ class SuperresolutionHybrid8XDC_Warp(SuperresolutionHybrid8XDC):
             rgb0 = self._resize(rgb, self.input_resolution) if rgb.shape[-1] != self.input_resolution else capi.f32(rgb)
             rgb_256 = self._resize(rgb0, 256)
             weights_256 = self._resize(weights_img.detach(), 256)
-            ref_torso_256, ref_bg_256 = self._aa_down2(ref_torso_rgb), self._aa_down2(ref_bg_rgb)
+            cc = self._clip_cache
+            if cc is None:
+                ref_torso_256, ref_bg_256 = self._aa_down2(ref_torso_rgb), self._aa_down2(ref_bg_rgb)
+            else:                                                        # per-clip constants, one frame broadcast over the batch (0.8 MB copies)
+                ref_torso_256, ref_bg_256 = cc['ref_torso_256'].expand(N, -1, -1, -1).contiguous(), cc['ref_bg_256'].expand(N, -1, -1, -1).contiguous()
         main, Nw = prep['main'], prep['main'].Nw
         b0, b1, hb = self.block0, self.block1, self.head_torso_block
         # block0: 128^2 -> 256^2 head features + head rgb
@@ -175,7 +201,10 @@ class SuperresolutionHybrid8XDC_Warp(SuperresolutionHybrid8XDC):
             rgb_torso, facev2v_ret = self.torso_model(ref_torso_256, segmap, kp_s, kp_d, rgb_256.detach(), weights_256.detach(), cal_loss=True,
                                                       target_torso_mask=target_torso_mask)
         x_torso = self._conv(sr_tc.to_nhwc_f16(facev2v_ret['deformed_torso_hid'], 256), plain['te'], 0)               # 1x1, 64 -> 256
-        x_bg = self._conv(self._conv(self._conv(sr_tc.to_nhwc_f16(ref_bg_256, 256), plain['bg0'], 2), plain['bg2'], 2), plain['bg4'], 0)
+        if cc is None:
+            x_bg = self._conv(self._conv(self._conv(sr_tc.to_nhwc_f16(ref_bg_256, 256), plain['bg0'], 2), plain['bg2'], 2), plain['bg4'], 0)
+        else:
+            x_bg = cc['x_bg']                                            # [1,256,256,256] fp16, read by every frame of the batch
         # head/torso fusion (v2: alpha-cat), sr_with_ref.py:106-113
         alpha = weights_256
         rgb_p = self._blend(rgb_h, rgb_torso, alpha)

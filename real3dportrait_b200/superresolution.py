@@ -155,6 +155,11 @@ class SuperresolutionHybrid8XDC(torch.nn.Module):
                                      conv_clamp=None, **block_kwargs)
         self.block1 = SynthesisBlock(256, 128, w_dim=512, resolution=512, img_channels=3, is_last=True, use_fp16=False,
                                      conv_clamp=None, **block_kwargs)
+        self.static_prepared = None
+
+    def _load_from_state_dict(self, *a, **k):
+        self.static_prepared = None          # prepared (folded + packed) weights belong to the parameters being replaced
+        return super()._load_from_state_dict(*a, **k)
 
     @staticmethod
     def _resize(x: torch.Tensor, size: int) -> torch.Tensor:
@@ -167,13 +172,16 @@ class SuperresolutionHybrid8XDC(torch.nn.Module):
     def forward(self, rgb, x, ws, **block_kwargs):
         """rgb [N,3,h,w], x [N,channels,h,w], ws [N,>=1,512] -> [N,3,512,512]   (superresolution.py:348-359)."""
         x_nhwc = block_kwargs.pop('x_nhwc', None)          # optional: the same features channels-last (tensor-core path only)
+        out_clamp, out_uint8 = bool(block_kwargs.pop('out_clamp', False)), bool(block_kwargs.pop('out_uint8', False))
+        if (out_clamp or out_uint8) and self.sr_mode != 'tc':
+            raise NotImplementedError('fused clamp / uint8 output is an option of the tensor-core SR path')
         block_kwargs = {k: v for k, v in block_kwargs.items() if k != 'sr_mode'}
         ws = ws[:, -1:, :].repeat(1, 3, 1)
         if x.shape[-1] > self.input_resolution:
             raise NotImplementedError('down-scaling inputs (antialiased) is not on the Real3D path')
         if self.sr_mode == 'tc':
             from . import sr_tc
-            return sr_tc.forward(self, rgb, x, ws, x_nhwc=x_nhwc)
+            return sr_tc.forward(self, rgb, x, ws, x_nhwc=x_nhwc, out_clamp=out_clamp, out_uint8=out_uint8)
         if x.shape[-1] != self.input_resolution:
             x = self._resize(x, self.input_resolution)
             rgb = self._resize(rgb, self.input_resolution)

@@ -13,9 +13,11 @@ from .renderer import ImportanceRenderer
 from .superresolution import SuperresolutionHybrid8XDC
 from .sr_with_ref import SuperresolutionHybrid8XDC_Warp
 
+# defaults follow the reference configs (egs/egs_bases/eg3d/base.yaml:39-40: 48 coarse + 48 importance samples); BASELINE.json's
+# configs 1-4 are quoted at 48 samples/ray, so bench.py / the fixtures pass num_samples_fine=0 explicitly
 DEFAULT_HPARAMS = {
     'neural_rendering_resolution': 64, 'w_dim': 512, 'final_resolution': 512, 'triplane_hid_dim': 32,
-    'num_samples_coarse': 48, 'num_samples_fine': 0, 'box_warp': 1.0, 'base_channel': 32768, 'max_channel': 512,
+    'num_samples_coarse': 48, 'num_samples_fine': 48, 'box_warp': 1.0, 'base_channel': 32768, 'max_channel': 512,
     'enable_rescale_plane_regulation': False, 'triplane_feature_type': 'triplane', 'mask_invalid_rays': False,
 }
 
@@ -60,6 +62,7 @@ class RenderHead(torch.nn.Module):
         ray_o, ray_d = self.ray_sampler(cam2world, intrinsics, res)
         N = ray_o.shape[0]
         lean = bool(render_overrides.pop('lean', False))
+        out_uint8 = bool(render_overrides.pop('out_uint8', False))
         opts = dict(self.rendering_kwargs, **render_overrides)
         feat, depth, wsum, valid = self.renderer(planes, self.decoder, ray_o, ray_d, opts)
         if lean and not self.torso and self.superresolution.sr_mode == 'tc' and not self.hparams.get('mask_invalid_rays', False):
@@ -68,10 +71,13 @@ class RenderHead(torch.nn.Module):
             x_nhwc = feat.view(N, res, res, feat.shape[-1])
             if getattr(self, '_ones_ws', None) is None or self._ones_ws.shape[0] != N or self._ones_ws.device != feat.device:
                 self._ones_ws = torch.ones(N, 14, self.hparams['w_dim'], device=feat.device)
+            # the clamp (and, if asked, the uint8 HWC conversion of real3d_infer.py:519) happen in the last SR epilogue
             sr_image = self.superresolution(x_nhwc[..., :3].permute(0, 3, 1, 2), x_nhwc.permute(0, 3, 1, 2), self._ones_ws, noise_mode='none',
-                                            x_nhwc=x_nhwc)
-            ret.update({'image': sr_image.clamp_(-1, 1), 'is_ray_valid': valid})
+                                            x_nhwc=x_nhwc, out_clamp=True, out_uint8=out_uint8)
+            ret.update({'image': sr_image, 'is_ray_valid': valid})
             return ret
+        if out_uint8:
+            raise NotImplementedError('uint8 frames come from the lean tensor-core path (FrameEngine); the full ret dict is fp32 like the reference')
         feature_image = feat.permute(0, 2, 1).reshape(N, feat.shape[-1], res, res).contiguous()
         weights_image = wsum.permute(0, 2, 1).reshape(N, 1, res, res).contiguous()
         depth_image = depth.permute(0, 2, 1).reshape(N, 1, res, res)

@@ -64,6 +64,17 @@ int r3dp_gen_rays(const float* cam2world, const float* intrinsics, int N, int re
 int r3dp_planes_to_channels_last(const float* planes_nchw, int N, int C, int H, int W, float* planes_cl,
                                  r3dp_stream_t stream);
 
+/* Tri-grids (`triplane_feature_type: trigrid | trigrid_v2`): grids_nchw [N,3,C*D,H,W] with channel index c*D + d (the reference views
+ * it as [N*3,C,D,H,W], renderer.py:83) -> grids_cl [N,3,D,H,W,C]: every depth slice a channels-last plane.  D = 1 is the call above. */
+int r3dp_grids_to_channels_last(const float* grids_nchw, int N, int C, int D, int H, int W, float* grids_cl, r3dp_stream_t stream);
+/* sample_from_trigrids (renderer.py:78-89): grids_cl [N,3,D,H,W,C], coords [N,P,3] -> out [N,3,P,C]; trilinear, zero padding,
+ * align_corners=False; plane p is sampled at (x,y,z), (x,z,y), (z,x,y) x 2/box_warp.  D >= 2. */
+int r3dp_trigrid_sample(const float* grids_cl, int N, int C, int D, int H, int W, const float* coords, int P, float box_warp,
+                        float* out, r3dp_stream_t stream);
+/* r3dp_run_model for tri-grids [N,3,D,H,W,C] (D = 1: tri-planes). */
+int r3dp_run_model_grid(const float* planes_cl, int N, int C, int D, int H, int W, const float* coords, int P, float box_warp,
+                        const r3dp_mlp_t* mlp, float* rgb, float* sigma, r3dp_stream_t stream);
+
 /* sample_from_planes (renderer.py:65-75): planes_cl [N,3,H,W,C], coords [N,P,3] -> out [N,3,P,C]
  * (bilinear, zero padding, align_corners=False, coords scaled by 2/box_warp; plane axes of generate_planes()). */
 int r3dp_triplane_sample(const float* planes_cl, int N, int C, int H, int W, const float* coords, int P,
@@ -111,6 +122,10 @@ size_t r3dp_render_workspace_bytes(int N, int M);
 typedef struct r3dp_plane_layout {
     long long frame_stride;
     int plane_stride, row_stride, texel_stride;
+    /* tri-grids (`triplane_feature_type: trigrid | trigrid_v2`, sample_from_trigrids, renderer.py:78-89; egs/os_avatar/img2plane.yaml:65-66):
+     * every plane is a stack of `depth` >= 2 slices `slice_stride` floats apart, sampled trilinearly with the third projected coordinate
+     * (z, y, y for planes 0, 1, 2); depth <= 1: plain tri-planes.  [N,3,D,H,W,C] (r3dp_grids_to_channels_last): slice = H*W*C. */
+    int depth, slice_stride;
 } r3dp_plane_layout_t;
 
 /* r3dp_render with explicit plane layouts and an optional SECOND plane set sampled at the same points and added to the first

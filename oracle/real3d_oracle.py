@@ -148,6 +148,50 @@ def sample_planes_lib(planes: Tensor, coords: Tensor, box_warp: float) -> Tensor
     return o.permute(0, 3, 2, 1).reshape(N, n_planes, P, C)
 
 
+#: third projected coordinate of each plane (the tri-grid depth axis): coords @ inv(plane_axes) = (x,y,z), (x,z,y), (z,x,y)
+PLANE_W = (2, 1, 1)
+
+
+def sample_trigrids(planes: Tensor, coords: Tensor, box_warp: float, depth: int) -> Tensor:
+    """sample_from_trigrids (renderer.py:78-89; `triplane_feature_type: trigrid_v2`, egs/os_avatar/img2plane.yaml:65-66):
+    planes[N,3,C*D,H,W] viewed as [N*3,C,D,H,W] (channel index = c*D + d), trilinear, zero padding, align_corners=False -> [N,3,P,C]."""
+    N, n_planes, CD, H, W = planes.shape
+    C, D = CD // depth, depth
+    P = coords.shape[1]
+    g = (2.0 / box_warp) * coords
+    grid = planes.reshape(N, n_planes, C, D, H * W)
+    out = torch.empty(N, n_planes, P, C, dtype=planes.dtype)
+    for p, ((au, av), aw) in enumerate(zip(PLANE_UV, PLANE_W)):
+        px = ((g[..., au] + 1) * W - 1) / 2
+        py = ((g[..., av] + 1) * H - 1) / 2
+        pz = ((g[..., aw] + 1) * D - 1) / 2
+        x0, y0, z0 = torch.floor(px), torch.floor(py), torch.floor(pz)
+        wx, wy, wz = (((x0 + 1) - px, px - x0), ((y0 + 1) - py, py - y0), ((z0 + 1) - pz, pz - z0))
+        acc = torch.zeros(N, C, P, dtype=planes.dtype)
+        gp = grid[:, p].reshape(N, C, D * H * W)
+        for dz in (0, 1):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    xi, yi, zi = (x0 + dx).long(), (y0 + dy).long(), (z0 + dz).long()
+                    inb = (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H) & (zi >= 0) & (zi < D)
+                    lin = (zi.clamp(0, D - 1) * H + yi.clamp(0, H - 1)) * W + xi.clamp(0, W - 1)       # [N,P]
+                    tex = torch.gather(gp, 2, lin[:, None, :].expand(-1, C, -1))                      # [N,C,P]
+                    acc = acc + tex * (wx[dx] * wy[dy] * wz[dz] * inb)[:, None, :]
+        out[:, p] = acc.permute(0, 2, 1)
+    return out
+
+
+def sample_trigrids_lib(planes: Tensor, coords: Tensor, box_warp: float, depth: int) -> Tensor:
+    """Same through F.grid_sample (5-D), as the reference calls it."""
+    N, n_planes, CD, H, W = planes.shape
+    C, D = CD // depth, depth
+    P = coords.shape[1]
+    g = (2.0 / box_warp) * coords
+    grids = torch.stack([g[..., [au, av, aw]] for (au, av), aw in zip(PLANE_UV, PLANE_W)], dim=1).reshape(N * n_planes, 1, 1, P, 3)
+    o = F.grid_sample(planes.reshape(N * n_planes, C, D, H, W), grids, mode='bilinear', padding_mode='zeros', align_corners=False)
+    return o.permute(0, 4, 3, 2, 1).reshape(N, n_planes, P, C)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # A.5  OSG decoder                         modules/img2plane/triplane.py:122-146, networks_stylegan2.py:99-131
 # ----------------------------------------------------------------------------------------------------------------------
@@ -167,9 +211,12 @@ def decode(feat3: Tensor, mlp: Dict[str, Tensor]) -> Tuple[Tensor, Tensor]:
     return torch.sigmoid(y[..., 1:]) * 1.002 - 0.001, y[..., 0:1]
 
 
-def run_model(planes: Tensor, mlp: Dict[str, Tensor], coords: Tensor, box_warp: float, lib: bool = False):
-    """renderer.py:169-188 (inference branch: no plane rescale, no density noise)."""
-    f = (sample_planes_lib if lib else sample_planes)(planes, coords, box_warp)
+def run_model(planes: Tensor, mlp: Dict[str, Tensor], coords: Tensor, box_warp: float, lib: bool = False, depth: int = 0):
+    """renderer.py:169-188 (inference branch: no plane rescale, no density noise).  depth > 0: tri-grids (trigrid / trigrid_v2)."""
+    if depth > 0:
+        f = (sample_trigrids_lib if lib else sample_trigrids)(planes, coords, box_warp, depth)
+    else:
+        f = (sample_planes_lib if lib else sample_planes)(planes, coords, box_warp)
     return decode(f, mlp)
 
 
@@ -234,20 +281,20 @@ def unify(d1, c1, s1, d2, c2, s2):
 
 def render(planes: Tensor, mlp: Dict[str, Tensor], ray_o: Tensor, ray_d: Tensor, *, S: int, S_imp: int = 0,
            box_warp: float = 1.0, white_back: bool = False, u_coarse: Tensor, u_fine: Optional[Tensor] = None,
-           lib: bool = False):
+           lib: bool = False, trigrid_depth: int = 0):
     """ImportanceRenderer.forward with 'auto' limits (renderer.py:118-167); jitter supplied by the caller.
     Returns rgb[N,M,C], depth[N,M,1], weights_sum[N,M,1], is_ray_valid[N,M,1]."""
     N, M, _ = ray_o.shape
     t0, t1, valid = auto_limits(ray_o, ray_d, box_warp)
     d_c = stratified_depths(t0, t1, S, u_coarse)
     xyz = (ray_o.unsqueeze(-2) + d_c * ray_d.unsqueeze(-2)).reshape(N, -1, 3)
-    col, sig = run_model(planes, mlp, xyz, box_warp, lib)
+    col, sig = run_model(planes, mlp, xyz, box_warp, lib, trigrid_depth)
     col, sig = col.reshape(N, M, S, -1), sig.reshape(N, M, S, 1)
     if S_imp > 0:
         _, _, w = ray_march(col, sig, d_c, white_back)
         d_f = importance_depths(d_c, w, u_fine)
         xyz = (ray_o.unsqueeze(-2) + d_f * ray_d.unsqueeze(-2)).reshape(N, -1, 3)
-        col_f, sig_f = run_model(planes, mlp, xyz, box_warp, lib)
+        col_f, sig_f = run_model(planes, mlp, xyz, box_warp, lib, trigrid_depth)
         d_a, c_a, s_a = unify(d_c, col, sig, d_f, col_f.reshape(N, M, S_imp, -1), sig_f.reshape(N, M, S_imp, 1))
         rgb, depth, w = ray_march(c_a, s_a, d_a, white_back)
     else:

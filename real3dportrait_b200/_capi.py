@@ -24,7 +24,8 @@ class MlpStruct(C.Structure):
 
 
 class PlaneLayout(C.Structure):
-    _fields_ = [('frame_stride', C.c_longlong), ('plane_stride', C.c_int), ('row_stride', C.c_int), ('texel_stride', C.c_int)]
+    _fields_ = [('frame_stride', C.c_longlong), ('plane_stride', C.c_int), ('row_stride', C.c_int), ('texel_stride', C.c_int),
+                ('depth', C.c_int), ('slice_stride', C.c_int)]
 
 
 class RenderArgs(C.Structure):
@@ -49,6 +50,9 @@ _SIGNATURES = {
     'r3dp_set_option': (_I, [C.c_char_p, _I]),
     'r3dp_gen_rays': (_I, [_P, _P, _I, _I, _P, _P, _P]),
     'r3dp_planes_to_channels_last': (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    'r3dp_grids_to_channels_last': (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    'r3dp_trigrid_sample': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _F, _P, _P]),
+    'r3dp_run_model_grid': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _F, _M, _P, _P, _P]),
     'r3dp_triplane_sample': (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _P, _P]),
     'r3dp_run_model': (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _M, _P, _P, _P]),
     'r3dp_decode': (_I, [_P, _I, _I, _I, _I, _M, _P, _P, _P]),

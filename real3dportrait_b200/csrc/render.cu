@@ -243,11 +243,8 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
             const float x = __fadd_rn(rf[0], __fmul_rn(d, rf[3]));
             const float y = __fadd_rn(rf[1], __fmul_rn(d, rf[4]));
             const float z = __fadd_rn(rf[2], __fmul_rn(d, rf[5]));
-            const float gx = pscale * x, gy = pscale * y, gz = pscale * z;
             float* row = (TC && !two_pass) ? dsc + q * 16 : rows + (size_t)(r * ST + k) * kRow;
-            tap_desc_s(gx, gy, a.H, a.W, 0, rowstep, texstep, row);                    // plane 0 <- (x, y)   (renderer.py:30-63)
-            tap_desc_s(gx, gz, a.H, a.W, a.p0.plane_stride, rowstep, texstep, row + 5);                // plane 1 <- (x, z)
-            tap_desc_s(gz, gx, a.H, a.W, 2 * a.p0.plane_stride, rowstep, texstep, row + 10);                // plane 2 <- (z, x)
+            sample_desc(a.p0, a.H, a.W, pscale * x, pscale * y, pscale * z, row);       // 15 floats (tri-planes) | 27 (tri-grids: rows only)
         }
         __syncthreads();
         // (2) gather: each warp takes 4 samples per iteration, 8 lanes x float4 per sample; the row's descriptor is read by all 8
@@ -259,30 +256,18 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
                 const int r = q / kn, k = k0 + (q - r * kn);
                 float* row = (TC && !two_pass) ? dsc + q * 16 : rows + (size_t)(r * ST + k) * kRow;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                float dsc[15];
+                if (a.p0.depth > 1) {                                    // tri-grids (never with the [nsamp][16] descriptor layout: see r3dp_render_ex)
+                    float dg[27];
 #pragma unroll
-                for (int e = 0; e < 15; ++e) dsc[e] = row[e];
+                    for (int e = 0; e < 27; ++e) dg[e] = row[e];
+                    gather_desc<true>(base0, dg, rowstep, texstep, a.p0.slice_stride, cq, acc);
+                    if (base1 != nullptr) gather_desc<true>(base1, dg, rowstep, texstep, a.p0.slice_stride, cq, acc);
+                } else {
+                    float dp[15];
 #pragma unroll
-                for (int p = 0; p < 3; ++p) {
-                    const float* b = base0 + __float_as_int(dsc[5 * p]) + cq * 4;
-                    const float4 t00 = ldg_nc_f4(b), t10 = ldg_nc_f4(b + texstep), t01 = ldg_nc_f4(b + rowstep), t11 = ldg_nc_f4(b + rowstep + texstep);
-                    const float w00 = dsc[5 * p + 1], w10 = dsc[5 * p + 2], w01 = dsc[5 * p + 3], w11 = dsc[5 * p + 4];
-                    acc.x += t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
-                    acc.y += t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
-                    acc.z += t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
-                    acc.w += t00.w * w00 + t10.w * w10 + t01.w * w01 + t11.w * w11;
-                }
-                if (base1 != nullptr) {
-#pragma unroll
-                    for (int p = 0; p < 3; ++p) {
-                        const float* b = base1 + __float_as_int(dsc[5 * p]) + cq * 4;
-                        const float4 t00 = ldg_nc_f4(b), t10 = ldg_nc_f4(b + texstep), t01 = ldg_nc_f4(b + rowstep), t11 = ldg_nc_f4(b + rowstep + texstep);
-                        const float w00 = dsc[5 * p + 1], w10 = dsc[5 * p + 2], w01 = dsc[5 * p + 3], w11 = dsc[5 * p + 4];
-                        acc.x += t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
-                        acc.y += t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
-                        acc.z += t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
-                        acc.w += t00.w * w00 + t10.w * w10 + t01.w * w01 + t11.w * w11;
-                    }
+                    for (int e = 0; e < 15; ++e) dp[e] = row[e];
+                    gather_desc<false>(base0, dp, rowstep, texstep, 0, cq, acc);
+                    if (base1 != nullptr) gather_desc<false>(base1, dp, rowstep, texstep, 0, cq, acc);
                 }
                 const float third = 1.0f / 3.0f;
                 if (TC) {
@@ -666,7 +651,8 @@ template <int R>
 static int launch_render(const RenderArgs& a, cudaStream_t st) {
     // default: tcgen05 decoder when the tile fits, else the smem-weights CUDA-core decoder (both keep the decoder in per-call storage);
     // the constant-bank variants hold process-wide state and are reachable only through R3DP_MLP=const (A/B runs)
-    if (mlp_variant() == 2 && render_tc_fits(R, a.S, a.S_imp)) return launch_render_tc<R>(a, st);
+    const bool grid_single = a.p0.depth > 1 && a.S_imp == 0;      // tri-grid descriptors (27 floats) do not fit the single-pass [nsamp][16] layout
+    if (mlp_variant() == 2 && !grid_single && render_tc_fits(R, a.S, a.S_imp)) return launch_render_tc<R>(a, st);
     if (mlp_variant() != 1) return launch_render_v<R, false, false>(a, st);
     const int per_pass = R * (a.S_imp > 0 && a.S_imp < a.S ? a.S_imp : a.S);          // the smaller pass decides
     return per_pass >= 2 * kRenderThreads ? launch_render_v<R, true, true>(a, st) : launch_render_v<R, true, false>(a, st);
@@ -716,9 +702,11 @@ static int check_mlp(const r3dp_mlp_t* mlp, int C) {
 
 static int check_layout(const r3dp_plane_layout_t& l, int H, int W, const char* what) {
     R3DP_REQUIRE(l.plane_stride > 0 && l.row_stride > 0 && l.texel_stride >= kC && l.frame_stride >= 0, "render: bad %s plane strides", what);
-    R3DP_REQUIRE((l.plane_stride % 4) == 0 && (l.row_stride % 4) == 0 && (l.texel_stride % 4) == 0 && (l.frame_stride % 4) == 0,
+    R3DP_REQUIRE((l.plane_stride % 4) == 0 && (l.row_stride % 4) == 0 && (l.texel_stride % 4) == 0 && (l.frame_stride % 4) == 0 && (l.slice_stride % 4) == 0,
                  "render: %s plane strides must keep texels 16-byte aligned", what);
-    const long long span = 2ll * l.plane_stride + (long long)(H - 1) * l.row_stride + (long long)(W - 1) * l.texel_stride + kC;
+    R3DP_REQUIRE(l.depth <= 1 || (l.depth <= 64 && l.slice_stride > 0), "render: tri-grids need 2 <= depth <= 64 slices and a slice stride (%s set)", what);
+    const long long span = 2ll * l.plane_stride + (long long)(l.depth > 1 ? l.depth - 1 : 0) * l.slice_stride + (long long)(H - 1) * l.row_stride +
+                           (long long)(W - 1) * l.texel_stride + kC;
     R3DP_REQUIRE(span < (1ll << 31), "render: %s planes of %dx%d exceed the 32-bit texel offsets of the tap descriptors", what, H, W);
     return 0;
 }
@@ -741,7 +729,8 @@ extern "C" int r3dp_render_ex(const r3dp_render_args_t* g, r3dp_stream_t stream)
     if (g->planes2) {
         if (check_layout(g->layout2, H, W, "second")) return 1;
         R3DP_REQUIRE(g->layout2.plane_stride == g->layout.plane_stride && g->layout2.row_stride == g->layout.row_stride &&
-                     g->layout2.texel_stride == g->layout.texel_stride && (reinterpret_cast<uintptr_t>(g->planes2) & 15) == 0,
+                     g->layout2.texel_stride == g->layout.texel_stride && g->layout2.depth == g->layout.depth &&
+                     g->layout2.slice_stride == g->layout.slice_stride && (reinterpret_cast<uintptr_t>(g->planes2) & 15) == 0,
                      "render: the second plane set must use the strides of the first (only its frame stride may differ)");
     }
     cudaStream_t st = as_stream(stream);
@@ -756,10 +745,10 @@ extern "C" int r3dp_render_ex(const r3dp_render_args_t* g, r3dp_stream_t stream)
 
     RenderArgs a = {};
     a.p0.base = g->planes; a.p0.frame_stride = g->layout.frame_stride; a.p0.plane_stride = g->layout.plane_stride;
-    a.p0.row_stride = g->layout.row_stride; a.p0.texel_stride = g->layout.texel_stride;
+    a.p0.row_stride = g->layout.row_stride; a.p0.texel_stride = g->layout.texel_stride; a.p0.depth = g->layout.depth; a.p0.slice_stride = g->layout.slice_stride;
     if (g->planes2) {
         a.p1.base = g->planes2; a.p1.frame_stride = g->layout2.frame_stride; a.p1.plane_stride = g->layout2.plane_stride;
-        a.p1.row_stride = g->layout2.row_stride; a.p1.texel_stride = g->layout2.texel_stride;
+        a.p1.row_stride = g->layout2.row_stride; a.p1.texel_stride = g->layout2.texel_stride; a.p1.depth = g->layout2.depth; a.p1.slice_stride = g->layout2.slice_stride;
     }
     a.N = N; a.H = H; a.W = W; a.ray_o = g->ray_o; a.ray_d = g->ray_d; a.camera = g->camera; a.M = M; a.res = res;
     a.S = S; a.S_imp = S_imp; a.box_warp = g->box_warp; a.white_back = g->white_back; a.u_coarse = g->u_coarse; a.u_fine = g->u_fine;

@@ -48,10 +48,13 @@ constexpr size_t kWsLimitsOff = kWsImageOff + ((sizeof(MlpTcImage) + 255) / 256)
 // channels-last plane addressing, strides in floats: texel (plane p, row y, col x) of frame n starts at
 //   base + n*frame_stride + p*plane_stride + y*row_stride + x*texel_stride    and holds kC contiguous floats.
 // [N,3,H,W,C]: plane = H*W*C, row = W*C, texel = C.   [N,H,W,3,C] (= torch channels_last of the producer's [N,3*C,H,W]): plane = C, row = W*3*C, texel = 3*C.
+// Tri-grids (`triplane_feature_type: trigrid / trigrid_v2`, renderer.py:78-89): each plane is a stack of `depth` slices, slice d of plane p
+// starts slice_stride floats further; depth <= 1 = plain tri-planes.
 struct PlaneSet {
     const float* base;
     long long frame_stride;
     int plane_stride, row_stride, texel_stride;
+    int depth, slice_stride;
 };
 
 struct RenderArgs {
@@ -87,6 +90,63 @@ __device__ __forceinline__ void tap_desc_s(float gu, float gv, int H, int W, int
     axis_taps(py, H, by, wya, wyb);
     out[0] = __int_as_float(plane_off + by * row_stride + bx * texel_stride);
     out[1] = wxa * wya; out[2] = wxb * wya; out[3] = wxa * wyb; out[4] = wxb * wyb;
+}
+
+// Tri-grid descriptor (sample_from_trigrids, renderer.py:78-89: 3-D grid_sample, zero padding, align_corners=False): out[0] = offset of the
+// 2x2x2 texel block (shifted inside the grid), out[1..4] = weights of the four taps in slice z, out[5..8] = in slice z+1.  D >= 2.
+__device__ __forceinline__ void tap_desc_grid(float gu, float gv, float gw, int H, int W, int D, int plane_off, int slice_stride, int row_stride,
+                                              int texel_stride, float* out) {
+    const float px = ((gu + 1.0f) * (float)W - 1.0f) * 0.5f;
+    const float py = ((gv + 1.0f) * (float)H - 1.0f) * 0.5f;
+    const float pz = ((gw + 1.0f) * (float)D - 1.0f) * 0.5f;
+    int bx, by, bz; float wxa, wxb, wya, wyb, wza, wzb;
+    axis_taps(px, W, bx, wxa, wxb);
+    axis_taps(py, H, by, wya, wyb);
+    axis_taps(pz, D, bz, wza, wzb);
+    out[0] = __int_as_float(plane_off + bz * slice_stride + by * row_stride + bx * texel_stride);
+    const float w00 = wxa * wya, w10 = wxb * wya, w01 = wxa * wyb, w11 = wxb * wyb;
+    out[1] = w00 * wza; out[2] = w10 * wza; out[3] = w01 * wza; out[4] = w11 * wza;
+    out[5] = w00 * wzb; out[6] = w10 * wzb; out[7] = w01 * wzb; out[8] = w11 * wzb;
+}
+
+// the three descriptors of one sample position: plane 0 <- (x, y | z), plane 1 <- (x, z | y), plane 2 <- (z, x | y)
+// (generate_planes + project_onto_planes, renderer.py:30-63); 15 floats for tri-planes, 27 for tri-grids
+__device__ __forceinline__ void sample_desc(const PlaneSet& ps, int H, int W, float gx, float gy, float gz, float* row) {
+    if (ps.depth > 1) {
+        tap_desc_grid(gx, gy, gz, H, W, ps.depth, 0, ps.slice_stride, ps.row_stride, ps.texel_stride, row);
+        tap_desc_grid(gx, gz, gy, H, W, ps.depth, ps.plane_stride, ps.slice_stride, ps.row_stride, ps.texel_stride, row + 9);
+        tap_desc_grid(gz, gx, gy, H, W, ps.depth, 2 * ps.plane_stride, ps.slice_stride, ps.row_stride, ps.texel_stride, row + 18);
+    } else {
+        tap_desc_s(gx, gy, H, W, 0, ps.row_stride, ps.texel_stride, row);
+        tap_desc_s(gx, gz, H, W, ps.plane_stride, ps.row_stride, ps.texel_stride, row + 5);
+        tap_desc_s(gz, gx, H, W, 2 * ps.plane_stride, ps.row_stride, ps.texel_stride, row + 10);
+    }
+}
+
+// gather of one sample by an 8-lane group (lane cq owns channels 4cq..4cq+3): SUM over the three planes of the (bi|tri)linear taps
+// described by `d` (15 or 27 floats, already in registers), read from `base`.  GRID is a compile-time flag.
+template <bool GRID>
+__device__ __forceinline__ void gather_desc(const float* __restrict__ base, const float* d, int rs, int ts, int ss, int cq, float4& acc) {
+    constexpr int kStep = GRID ? 9 : 5;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const float* b = base + __float_as_int(d[kStep * p]) + cq * 4;
+        const float4 t00 = ldg_nc_f4(b), t10 = ldg_nc_f4(b + ts), t01 = ldg_nc_f4(b + rs), t11 = ldg_nc_f4(b + rs + ts);
+        const float w00 = d[kStep * p + 1], w10 = d[kStep * p + 2], w01 = d[kStep * p + 3], w11 = d[kStep * p + 4];
+        acc.x += t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
+        acc.y += t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
+        acc.z += t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
+        acc.w += t00.w * w00 + t10.w * w10 + t01.w * w01 + t11.w * w11;
+        if (GRID) {
+            const float* c = b + ss;
+            const float4 u00 = ldg_nc_f4(c), u10 = ldg_nc_f4(c + ts), u01 = ldg_nc_f4(c + rs), u11 = ldg_nc_f4(c + rs + ts);
+            const float v00 = d[kStep * p + 5], v10 = d[kStep * p + 6], v01 = d[kStep * p + 7], v11 = d[kStep * p + 8];
+            acc.x += u00.x * v00 + u10.x * v10 + u01.x * v01 + u11.x * v11;
+            acc.y += u00.y * v00 + u10.y * v10 + u01.y * v01 + u11.y * v11;
+            acc.z += u00.z * v00 + u10.z * v10 + u01.z * v01 + u11.z * v11;
+            acc.w += u00.w * v00 + u10.w * v10 + u01.w * v01 + u11.w * v11;
+        }
+    }
 }
 
 // order-preserving key of a depth for the merge sort: NaN last (as torch.sort), -0 == +0

@@ -35,7 +35,8 @@ constexpr int kOffW = kOffA2 + 32768;
 constexpr int kOffRows = kOffW + 21504;                         // MlpTcImage (20 928 B) padded
 constexpr int kOffDep = kOffRows + NR * 128 * kRowF * 4;
 constexpr int kOffDsc = kOffDep + ND * 128 * 4;
-constexpr int kOffRay = kOffDsc + kGatherWarps * kSPW * 16 * 4;
+constexpr int kDscF = 32;                                       // floats per sample descriptor row (15 used by tri-planes, 27 by tri-grids)
+constexpr int kOffRay = kOffDsc + kGatherWarps * kSPW * kDscF * 4;
 constexpr int kOffBar = kOffRay + kGatherWarps * 8 * 8 * 4;
 constexpr int kSmem = kOffBar + 512 + 1024;                     // + alignment slack
 
@@ -71,7 +72,7 @@ __device__ __forceinline__ int ray_index(const RenderArgs& a, int grp, int r) {
     return grp * G + r;
 }
 
-template <int LOG2D>
+template <int LOG2D, bool GRID>
 __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const RenderArgs a, int items_per_frame, int total_items) {
     constexpr int D = 1 << LOG2D, G = 128 >> LOG2D;
     extern __shared__ uint8_t smem_raw[];
@@ -123,10 +124,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
         constexpr int RPW = kSPW >> LOG2D;                                      // rays per gather warp
         static_assert(RPW >= 1, "D must not exceed the samples of one gather warp");
         const int gw = warp - kFirstGather, sub = lane >> 3, cq = lane & 7;
-        float* dsc = dsc_all + gw * kSPW * 16;
+        float* dsc = dsc_all + gw * kSPW * kDscF;
         float* rayw = ray_all + gw * 64;
         const float scale = 2.0f / a.box_warp;
-        const int rs = a.p0.row_stride, ts = a.p0.texel_stride;
+        const int rs = a.p0.row_stride, ts = a.p0.texel_stride, ss = a.p0.slice_stride;
         float dmin = __int_as_float(0x7f800000), dmax = __int_as_float(0xff800000);
         uint32_t q = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
                 tc::mbar_wait(&B.dep_empty[dslot], ((q / ND) & 1) ^ 1);
                 if (lane < kSPW) {
                     const int k = k0 + s_j;
-                    float* row = dsc + lane * 16;
+                    float* row = dsc + lane * kDscF;
                     float d = 0.f;
                     if (s_m < a.M && k < a.S) {
                         const float* rf = rayw + s_rl * 8;
@@ -177,13 +178,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
                         const float x = __fadd_rn(rf[0], __fmul_rn(d, rf[3]));
                         const float y = __fadd_rn(rf[1], __fmul_rn(d, rf[4]));
                         const float z = __fadd_rn(rf[2], __fmul_rn(d, rf[5]));
-                        const float gx = scale * x, gy = scale * y, gz = scale * z;
-                        tap_desc_s(gx, gy, a.H, a.W, 0, rs, ts, row);                              // plane 0 <- (x, y)   (renderer.py:30-63)
-                        tap_desc_s(gx, gz, a.H, a.W, a.p0.plane_stride, rs, ts, row + 5);          // plane 1 <- (x, z)
-                        tap_desc_s(gz, gx, a.H, a.W, 2 * a.p0.plane_stride, rs, ts, row + 10);     // plane 2 <- (z, x)
+                        sample_desc(a.p0, a.H, a.W, scale * x, scale * y, scale * z, row);
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 15; ++e) row[e] = 0.f;                                 // offset 0, weights 0: a harmless tap
+                        for (int e = 0; e < (GRID ? 27 : 15); ++e) row[e] = 0.f;                   // offset 0, weights 0: a harmless tap
                     }
                     dep[dslot * 128 + gw * kSPW + lane] = d;
                 }
@@ -193,32 +191,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
 #pragma unroll 1
                 for (int it = 0; it < kSPW / 4; ++it) {
                     const int s = it * 4 + sub;
-                    const float4* rw = reinterpret_cast<const float4*>(dsc + s * 16);
-                    const float4 q0 = rw[0], q1 = rw[1], q2 = rw[2], q3 = rw[3];
-                    const float dscv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+                    const float4* rw = reinterpret_cast<const float4*>(dsc + s * kDscF);
+                    float dscv[GRID ? 28 : 16];
+#pragma unroll
+                    for (int e = 0; e < (GRID ? 7 : 4); ++e) { const float4 qv = rw[e]; dscv[4 * e] = qv.x; dscv[4 * e + 1] = qv.y; dscv[4 * e + 2] = qv.z; dscv[4 * e + 3] = qv.w; }
                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int p = 0; p < 3; ++p) {
-                        const float* b = base0 + __float_as_int(dscv[5 * p]) + cq * 4;
-                        const float4 t00 = ldg_nc_f4(b), t10 = ldg_nc_f4(b + ts), t01 = ldg_nc_f4(b + rs), t11 = ldg_nc_f4(b + rs + ts);
-                        const float w00 = dscv[5 * p + 1], w10 = dscv[5 * p + 2], w01 = dscv[5 * p + 3], w11 = dscv[5 * p + 4];
-                        acc.x += t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
-                        acc.y += t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
-                        acc.z += t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
-                        acc.w += t00.w * w00 + t10.w * w10 + t01.w * w01 + t11.w * w11;
-                    }
-                    if (base1 != nullptr) {                                      // second plane set, same points (bilinear sampling is linear)
-#pragma unroll
-                        for (int p = 0; p < 3; ++p) {
-                            const float* b = base1 + __float_as_int(dscv[5 * p]) + cq * 4;
-                            const float4 t00 = ldg_nc_f4(b), t10 = ldg_nc_f4(b + ts), t01 = ldg_nc_f4(b + rs), t11 = ldg_nc_f4(b + rs + ts);
-                            const float w00 = dscv[5 * p + 1], w10 = dscv[5 * p + 2], w01 = dscv[5 * p + 3], w11 = dscv[5 * p + 4];
-                            acc.x += t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
-                            acc.y += t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
-                            acc.z += t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
-                            acc.w += t00.w * w00 + t10.w * w10 + t01.w * w01 + t11.w * w11;
-                        }
-                    }
+                    gather_desc<GRID>(base0, dscv, rs, ts, ss, cq, acc);
+                    if (base1 != nullptr) gather_desc<GRID>(base1, dscv, rs, ts, ss, cq, acc);     // second plane set, same points (sampling is linear)
                     // mean over the planes as fp16 hi + lo halves into the swizzled A1 stage: lane cq owns K = [4cq, 4cq+4) of both halves
                     const float third = 1.0f / 3.0f;
                     const float f0 = acc.x * third, f1 = acc.y * third, f2 = acc.z * third, f3 = acc.w * third;
@@ -412,16 +391,16 @@ static int chunk_log2() {                          // R3DP_RS_D = 4 | 8 | 16: de
     return g_rs_chunk_log2;
 }
 
-template <int LOG2D>
+template <int LOG2D, bool GRID>
 static int launch(RenderArgs a, cudaStream_t st) {
     constexpr int G = 128 >> LOG2D;
     const bool image = a.res > 0 && a.res * a.res == a.M && (a.res % G) == 0;
     a.tile_cols = image ? a.res : 0;
     const int items_per_frame = (a.M + G - 1) / G;
     const int total = a.N * items_per_frame;
-    R3DP_CUDA(cudaFuncSetAttribute(render_stream_kernel<LOG2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    R3DP_CUDA(cudaFuncSetAttribute(render_stream_kernel<LOG2D, GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     const int grid = total < sm_count() ? total : sm_count();
-    render_stream_kernel<LOG2D><<<grid, kThreads, kSmem, st>>>(a, items_per_frame, total);
+    render_stream_kernel<LOG2D, GRID><<<grid, kThreads, kSmem, st>>>(a, items_per_frame, total);
     R3DP_LAUNCH_CHECK();
     return 0;
 }
@@ -430,15 +409,17 @@ static int launch(RenderArgs a, cudaStream_t st) {
 
 bool render_stream_fits(const RenderArgs& a) {
     if (a.S_imp != 0 || a.S < 2) return false;
-    if (a.p1.base && (a.p1.plane_stride != a.p0.plane_stride || a.p1.row_stride != a.p0.row_stride || a.p1.texel_stride != a.p0.texel_stride)) return false;
+    if (a.p1.base && (a.p1.plane_stride != a.p0.plane_stride || a.p1.row_stride != a.p0.row_stride || a.p1.texel_stride != a.p0.texel_stride ||
+                      a.p1.depth != a.p0.depth || a.p1.slice_stride != a.p0.slice_stride)) return false;
     return true;
 }
 
 int launch_render_stream(const RenderArgs& a, cudaStream_t st) {
+    if (a.p0.depth > 1) return rs::launch<3, true>(a, st);                      // tri-grids: D = 8 chunks only
     switch (rs::chunk_log2()) {
-        case 2: return rs::launch<2>(a, st);
-        case 4: return rs::launch<4>(a, st);
-        default: return rs::launch<3>(a, st);
+        case 2: return rs::launch<2, false>(a, st);
+        case 4: return rs::launch<4, false>(a, st);
+        default: return rs::launch<3, false>(a, st);
     }
 }
 

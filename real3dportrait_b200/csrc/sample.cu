@@ -2,7 +2,7 @@
 //   planes_to_channels_last   [N,3,C,H,W] -> [N,3,H,W,C]        (HBM-bound transposition)
 //   triplane_sample           sample_from_planes (renderer.py:65-75): the HBM-roofline gather, write-dominated
 //   run_model                 ImportanceRenderer.run_model (renderer.py:169-188): gather + OSG decoder
-#include "render_core.cuh"
+#include "render_shared.cuh"
 #include <stdlib.h>
 
 namespace r3dp {
@@ -11,12 +11,15 @@ namespace r3dp {
 // One CTA moves a [32 ch][128 px] tile through shared memory: reads are 512 B contiguous per channel row (float4 per
 // lane), writes are 128 B contiguous per pixel (float4 per lane, 8 lanes per pixel).
 constexpr int kTilePx = 128;
-__global__ void __launch_bounds__(256) planes_to_cl_kernel(const float* __restrict__ src, float* __restrict__ dst, int HW) {
+// D = depth slices per plane (1: tri-planes).  Source channel index = c*D + d (the reference views [N,3,C*D,H,W] as [N*3,C,D,H,W],
+// renderer.py:83); destination [N,3,D,H,W,C]: every slice is a channels-last plane.
+__global__ void __launch_bounds__(256) planes_to_cl_kernel(const float* __restrict__ src, float* __restrict__ dst, int HW, int D) {
     __shared__ float tile[kC][kTilePx + 1];
-    const int plane = blockIdx.y;                         // n*3 + p
+    const int plane = blockIdx.y / D, dsl = blockIdx.y - plane * D;        // plane = n*3 + p
     const int px0 = blockIdx.x * kTilePx;
-    const float* s = src + (size_t)plane * kC * HW;
-    float* d = dst + (size_t)plane * HW * kC;
+    const float* s = src + ((size_t)plane * kC * D + dsl) * HW;
+    float* d = dst + ((size_t)plane * D + dsl) * HW * kC;
+    const size_t cstride = (size_t)D * HW;
     const int tid = threadIdx.x;
     const bool full = (px0 + kTilePx <= HW) && ((HW & 3) == 0);
     if (full) {
@@ -24,13 +27,13 @@ __global__ void __launch_bounds__(256) planes_to_cl_kernel(const float* __restri
         for (int it = 0; it < (kC * kTilePx / 4) / 256; ++it) {       // 4 iterations
             const int v = it * 256 + tid;                              // float4 index in tile
             const int c = v / (kTilePx / 4), p4 = v % (kTilePx / 4);
-            const float4 f = ldg_nc_f4(s + (size_t)c * HW + px0 + p4 * 4);
+            const float4 f = ldg_nc_f4(s + (size_t)c * cstride + px0 + p4 * 4);
             tile[c][p4 * 4 + 0] = f.x; tile[c][p4 * 4 + 1] = f.y; tile[c][p4 * 4 + 2] = f.z; tile[c][p4 * 4 + 3] = f.w;
         }
     } else {
         for (int v = tid; v < kC * kTilePx; v += 256) {
             const int c = v / kTilePx, p = v % kTilePx;
-            tile[c][p] = (px0 + p < HW) ? s[(size_t)c * HW + px0 + p] : 0.f;
+            tile[c][p] = (px0 + p < HW) ? s[(size_t)c * cstride + px0 + p] : 0.f;
         }
     }
     __syncthreads();
@@ -41,6 +44,39 @@ __global__ void __launch_bounds__(256) planes_to_cl_kernel(const float* __restri
         if (px0 + p < HW) {
             float4 f = make_float4(tile[c4 * 4 + 0][p], tile[c4 * 4 + 1][p], tile[c4 * 4 + 2][p], tile[c4 * 4 + 3][p]);
             *reinterpret_cast<float4*>(d + (size_t)(px0 + p) * kC + c4 * 4) = f;
+        }
+    }
+}
+
+// ---- sample_from_trigrids (renderer.py:78-89) on [N,3,D,H,W,C] -----------------------------------------------------------------------
+// warp = 4 points x 8 lanes x float4; per plane one descriptor (8 trilinear taps), results per plane as the reference returns them.
+__global__ void __launch_bounds__(256, 3) trigrid_sample_kernel(const float* __restrict__ grids, int N, int D, int H, int W,
+                                                                const float* __restrict__ coords, int P, float scale, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31, sub = lane >> 3, cq = lane & 7;
+    const long long total4 = ((long long)N * P + 3) / 4;
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    const int ts = kC, rs = W * kC, ss = H * W * kC, ps = D * ss;
+    for (long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < total4; g += wstride) {
+        const long long pt = g * 4 + sub;
+        if (pt >= (long long)N * P) continue;
+        const int n = (int)(pt / P); const int s = (int)(pt - (long long)n * P);
+        const float* c = coords + pt * 3;
+        const float gx = scale * __ldg(c), gy = scale * __ldg(c + 1), gz = scale * __ldg(c + 2);
+        const float* base = grids + (size_t)n * 3 * ps;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            float d[9];
+            const float gu = p == 2 ? gz : gx, gv = p == 0 ? gy : (p == 1 ? gz : gx), gw = p == 0 ? gz : gy;
+            tap_desc_grid(gu, gv, gw, H, W, D, p * ps, ss, rs, ts, d);
+            const float* b = base + __float_as_int(d[0]) + cq * 4;
+            const float4 t0 = ldg_nc_f4(b), t1 = ldg_nc_f4(b + ts), t2 = ldg_nc_f4(b + rs), t3 = ldg_nc_f4(b + rs + ts);
+            const float4 u0 = ldg_nc_f4(b + ss), u1 = ldg_nc_f4(b + ss + ts), u2 = ldg_nc_f4(b + ss + rs), u3 = ldg_nc_f4(b + ss + rs + ts);
+            float4 r;
+            r.x = t0.x * d[1] + t1.x * d[2] + t2.x * d[3] + t3.x * d[4] + u0.x * d[5] + u1.x * d[6] + u2.x * d[7] + u3.x * d[8];
+            r.y = t0.y * d[1] + t1.y * d[2] + t2.y * d[3] + t3.y * d[4] + u0.y * d[5] + u1.y * d[6] + u2.y * d[7] + u3.y * d[8];
+            r.z = t0.z * d[1] + t1.z * d[2] + t2.z * d[3] + t3.z * d[4] + u0.z * d[5] + u1.z * d[6] + u2.z * d[7] + u3.z * d[8];
+            r.w = t0.w * d[1] + t1.w * d[2] + t2.w * d[3] + t3.w * d[4] + u0.w * d[5] + u1.w * d[6] + u2.w * d[7] + u3.w * d[8];
+            stg_cs_f4(out + (((size_t)n * 3 + p) * P + s) * kC + cq * 4, r);
         }
     }
 }
@@ -74,7 +110,7 @@ __global__ void __launch_bounds__(256, MINB) triplane_sample_kernel(const float*
 
 // ---- run_model ----------------------------------------------------------------------------------------------------
 constexpr int kRmThreads = 192, kRmPoints = 384;
-__global__ void __launch_bounds__(kRmThreads, 2) run_model_kernel(const float* __restrict__ planes, int N, int H, int W,
+__global__ void __launch_bounds__(kRmThreads, 2) run_model_kernel(const PlaneSet ps, int N, int H, int W,
                                                                  const float* __restrict__ coords, int P, float scale,
                                                                  const r3dp_mlp_t m, float* __restrict__ rgb,
                                                                  float* __restrict__ sigma) {
@@ -85,17 +121,20 @@ __global__ void __launch_bounds__(kRmThreads, 2) run_model_kernel(const float* _
     const int n = blockIdx.y, p0 = blockIdx.x * kRmPoints;
     const int cnt = min(kRmPoints, P - p0);
     load_mlp_smem(mlp, m, tid, kRmThreads);
-    PlaneView pv; pv.base = planes + (size_t)n * 3 * H * W * kC; pv.H = H; pv.W = W; pv.scale = scale;
+    const float* base = ps.base + (size_t)n * ps.frame_stride;
     for (int q4 = warp * 4; q4 < cnt; q4 += (kRmThreads / 32) * 4) {
         const int q = q4 + sub;
         if (q < cnt) {
             const float* c = coords + ((size_t)n * P + p0 + q) * 3;
-            float4 f0, f1, f2;
-            gather3(pv, __ldg(c), __ldg(c + 1), __ldg(c + 2), cq, f0, f1, f2);
+            const float gx = scale * __ldg(c), gy = scale * __ldg(c + 1), gz = scale * __ldg(c + 2);
+            float d[27];
+            sample_desc(ps, H, W, gx, gy, gz, d);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ps.depth > 1) gather_desc<true>(base, d, ps.row_stride, ps.texel_stride, ps.slice_stride, cq, acc);
+            else gather_desc<false>(base, d, ps.row_stride, ps.texel_stride, 0, cq, acc);
             float* row = rows + (size_t)q * kRow + cq * 4;
             const float third = 1.0f / 3.0f;
-            row[0] = (f0.x + f1.x + f2.x) * third; row[1] = (f0.y + f1.y + f2.y) * third;
-            row[2] = (f0.z + f1.z + f2.z) * third; row[3] = (f0.w + f1.w + f2.w) * third;
+            row[0] = acc.x * third; row[1] = acc.y * third; row[2] = acc.z * third; row[3] = acc.w * third;
         }
     }
     __syncthreads();
@@ -147,14 +186,30 @@ __global__ void __launch_bounds__(kRmThreads, 2) decode_kernel(const float* __re
 
 using namespace r3dp;
 
+extern "C" int r3dp_grids_to_channels_last(const float* grids_nchw, int N, int C, int D, int H, int W, float* grids_cl, r3dp_stream_t stream) {
+    R3DP_REQUIRE(grids_nchw && grids_cl, "grids_to_channels_last: null pointer");
+    R3DP_REQUIRE(C == kC, "grids_to_channels_last: C must be %d (got %d)", kC, C);
+    R3DP_REQUIRE(N > 0 && H > 0 && W > 0 && D >= 1 && (long long)N * 3 * D <= 65535, "grids_to_channels_last: bad shape");
+    const int HW = H * W;
+    dim3 grid((HW + kTilePx - 1) / kTilePx, N * 3 * D);
+    planes_to_cl_kernel<<<grid, 256, 0, as_stream(stream)>>>(grids_nchw, grids_cl, HW, D);
+    count_launches(1);
+    R3DP_LAUNCH_CHECK();
+    return 0;
+}
 extern "C" int r3dp_planes_to_channels_last(const float* planes_nchw, int N, int C, int H, int W, float* planes_cl,
                                             r3dp_stream_t stream) {
-    R3DP_REQUIRE(planes_nchw && planes_cl, "planes_to_channels_last: null pointer");
-    R3DP_REQUIRE(C == kC, "planes_to_channels_last: C must be %d (got %d)", kC, C);
-    R3DP_REQUIRE(N > 0 && H > 0 && W > 0, "planes_to_channels_last: bad shape");
-    const int HW = H * W;
-    dim3 grid((HW + kTilePx - 1) / kTilePx, N * 3);
-    planes_to_cl_kernel<<<grid, 256, 0, as_stream(stream)>>>(planes_nchw, planes_cl, HW);
+    return r3dp_grids_to_channels_last(planes_nchw, N, C, 1, H, W, planes_cl, stream);
+}
+
+extern "C" int r3dp_trigrid_sample(const float* grids_cl, int N, int C, int D, int H, int W, const float* coords, int P, float box_warp,
+                                   float* out, r3dp_stream_t stream) {
+    R3DP_REQUIRE(grids_cl && coords && out, "trigrid_sample: null pointer");
+    R3DP_REQUIRE(C == kC && D >= 2 && N > 0 && P > 0 && H >= 2 && W >= 2 && box_warp > 0.f, "trigrid_sample: bad shape (C = 32, depth >= 2)");
+    R3DP_REQUIRE((long long)3 * D * H * W * kC < (1ll << 31), "trigrid_sample: grids exceed the 32-bit texel offsets");
+    const long long warps = ((long long)N * P + 3) / 4;
+    const long long need = (warps + 7) / 8, cap = (long long)sm_count() * 3;
+    trigrid_sample_kernel<<<(unsigned)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(grids_cl, N, D, H, W, coords, P, 2.0f / box_warp, out);
     count_launches(1);
     R3DP_LAUNCH_CHECK();
     return 0;
@@ -184,19 +239,27 @@ extern "C" int r3dp_triplane_sample(const float* planes_cl, int N, int C, int H,
     return 0;
 }
 
-extern "C" int r3dp_run_model(const float* planes_cl, int N, int C, int H, int W, const float* coords, int P, float box_warp,
-                              const r3dp_mlp_t* mlp, float* rgb, float* sigma, r3dp_stream_t stream) {
+extern "C" int r3dp_run_model_grid(const float* planes_cl, int N, int C, int D, int H, int W, const float* coords, int P, float box_warp,
+                                   const r3dp_mlp_t* mlp, float* rgb, float* sigma, r3dp_stream_t stream) {
     R3DP_REQUIRE(planes_cl && coords && rgb && sigma && mlp, "run_model: null pointer");
     R3DP_REQUIRE(mlp->in_features == kC && mlp->hidden == kHidden && mlp->out_dim == kOut - 1 && C == kC,
                  "run_model: only the OSGDecoder shape 32->64->1+32 is built");
-    R3DP_REQUIRE(N > 0 && P > 0 && H > 0 && W > 0 && box_warp > 0.f, "run_model: bad shape");
+    R3DP_REQUIRE(N > 0 && P > 0 && H >= 2 && W >= 2 && D >= 1 && box_warp > 0.f, "run_model: bad shape");
+    R3DP_REQUIRE((long long)3 * D * H * W * kC < (1ll << 31), "run_model: planes exceed the 32-bit texel offsets");
     const size_t smem = sizeof(MlpSmem) + (size_t)kRmPoints * kRow * 4;
     R3DP_CUDA(cudaFuncSetAttribute(run_model_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PlaneSet ps;
+    ps.base = planes_cl; ps.depth = D; ps.slice_stride = H * W * kC; ps.plane_stride = D * H * W * kC; ps.frame_stride = 3ll * ps.plane_stride;
+    ps.row_stride = W * kC; ps.texel_stride = kC;
     dim3 grid((P + kRmPoints - 1) / kRmPoints, N);
-    run_model_kernel<<<grid, kRmThreads, smem, as_stream(stream)>>>(planes_cl, N, H, W, coords, P, 2.0f / box_warp, *mlp, rgb, sigma);
+    run_model_kernel<<<grid, kRmThreads, smem, as_stream(stream)>>>(ps, N, H, W, coords, P, 2.0f / box_warp, *mlp, rgb, sigma);
     count_launches(1);
     R3DP_LAUNCH_CHECK();
     return 0;
+}
+extern "C" int r3dp_run_model(const float* planes_cl, int N, int C, int H, int W, const float* coords, int P, float box_warp,
+                              const r3dp_mlp_t* mlp, float* rgb, float* sigma, r3dp_stream_t stream) {
+    return r3dp_run_model_grid(planes_cl, N, C, 1, H, W, coords, P, box_warp, mlp, rgb, sigma, stream);
 }
 
 extern "C" int r3dp_decode(const float* feat, int N, int K, int P, int C, const r3dp_mlp_t* mlp, float* rgb, float* sigma,

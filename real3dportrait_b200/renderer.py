@@ -34,14 +34,22 @@ class PlanesCL:
     A set with N == 1 may be shared by every frame of a call (frame stride 0): the per-clip canonical planes."""
 
     def __init__(self, data: torch.Tensor, layout: str = 'phwc'):
-        assert layout in ('phwc', 'hwpc'), layout
-        assert data.ndim == 5 and data.is_cuda and data.dtype == torch.float32 and data.is_contiguous()
+        assert layout in ('phwc', 'hwpc', 'pdhwc'), layout
+        assert data.is_cuda and data.dtype == torch.float32 and data.is_contiguous()
+        assert data.ndim == (6 if layout == 'pdhwc' else 5), (layout, data.shape)
         self.data, self.layout = data, layout
+
+    @property
+    def depth(self) -> int:
+        """Depth slices per plane: > 1 only for tri-grids ('pdhwc' = [N,3,D,H,W,C], `triplane_feature_type: trigrid | trigrid_v2`)."""
+        return self.data.shape[2] if self.layout == 'pdhwc' else 1
 
     @property
     def dims(self):
         if self.layout == 'phwc':
             N, _, H, W, Cc = self.data.shape
+        elif self.layout == 'pdhwc':
+            N, _, _, H, W, Cc = self.data.shape
         else:
             N, H, W, _, Cc = self.data.shape
         return N, Cc, H, W
@@ -50,10 +58,25 @@ class PlanesCL:
         N, Cc, H, W = self.dims
         if N != n_frames and N != 1:
             raise ValueError(f'plane set holds {N} frames, the call renders {n_frames}')
-        frame = 0 if (N == 1 and n_frames > 1) else 3 * H * W * Cc
+        D = self.depth
+        frame = 0 if (N == 1 and n_frames > 1) else 3 * D * H * W * Cc
         if self.layout == 'phwc':
-            return capi.PlaneLayout(frame, H * W * Cc, W * Cc, Cc)
-        return capi.PlaneLayout(frame, Cc, W * 3 * Cc, 3 * Cc)
+            return capi.PlaneLayout(frame, H * W * Cc, W * Cc, Cc, 1, 0)
+        if self.layout == 'pdhwc':
+            return capi.PlaneLayout(frame, D * H * W * Cc, W * Cc, Cc, D, H * W * Cc)
+        return capi.PlaneLayout(frame, Cc, W * 3 * Cc, 3 * Cc, 1, 0)
+
+
+def grids_to_channels_last(grids: torch.Tensor, depth: int) -> PlanesCL:
+    """Tri-grids [N,3,C*D,H,W] (channel index c*D + d, as cal_plane leaves them: img2plane_baseline.py:131-136) -> PlanesCL 'pdhwc' [N,3,D,H,W,C]."""
+    grids = capi.f32(grids)
+    assert grids.ndim == 5 and grids.shape[1] == 3 and grids.shape[2] % depth == 0, (grids.shape, depth)
+    N, _, CD, H, W = grids.shape
+    Cc = CD // depth
+    out = torch.empty(N, 3, depth, H, W, Cc, device=grids.device, dtype=torch.float32)
+    with capi.region('repack'):
+        capi.check(capi.lib().r3dp_grids_to_channels_last(capi.ptr(grids), N, Cc, depth, H, W, capi.ptr(out), capi.stream()))
+    return PlanesCL(out, 'pdhwc')
 
 
 def planes_to_channels_last(planes: torch.Tensor, out: Optional[torch.Tensor] = None) -> PlanesCL:
@@ -86,23 +109,25 @@ def producer_view(planes: torch.Tensor) -> Optional[PlanesCL]:
     return PlanesCL(t.permute(0, 3, 4, 1, 2), 'hwpc')          # [N,H,W,3,C], contiguous by construction
 
 
-def _as_cl(planes: Union[torch.Tensor, PlanesCL]) -> PlanesCL:
+def _as_cl(planes: Union[torch.Tensor, PlanesCL], depth: int = 1) -> PlanesCL:
     if isinstance(planes, PlanesCL):
         return planes
+    if depth > 1:
+        return grids_to_channels_last(planes, depth)
     pv = producer_view(planes)
     return pv if pv is not None else planes_to_channels_last(planes)
 
 
-def _plane_sets(planes):
+def _plane_sets(planes, depth: int = 1):
     """planes | PlanesCL | (a, b) pair of either -> (first, second-or-None); a pair is sampled set by set and summed in-kernel
     (`cano_planes + secc_planes`, secc_img2plane.py:73-81, without materialising the sum)."""
     if isinstance(planes, (tuple, list)):
         assert len(planes) == 2, 'at most two plane sets'
-        a, b = _as_cl(planes[0]), _as_cl(planes[1])
-        if a.layout != b.layout or a.dims[1:] != b.dims[1:]:
+        a, b = _as_cl(planes[0], depth), _as_cl(planes[1], depth)
+        if a.layout != b.layout or a.dims[1:] != b.dims[1:] or a.depth != b.depth:
             raise ValueError('the two plane sets must share layout and shape')
         return a, b
-    return _as_cl(planes), None
+    return _as_cl(planes, depth), None
 
 
 def _as_phwc(planes) -> PlanesCL:
@@ -128,6 +153,23 @@ def sample_from_planes(plane_axes, plane_features, coordinates, mode='bilinear',
     return out
 
 
+def sample_from_trigrids(plane_axes, plane_features, coordinates, mode='bilinear', padding_mode='zeros', box_warp=None, triplane_depth=1):
+    """renderer.py:78-89: plane_features [N,3,C*D,H,W] (or PlanesCL 'pdhwc'), coordinates [N,P,3] -> [N,3,P,C] (3-D grid_sample)."""
+    assert padding_mode == 'zeros' and mode == 'bilinear'
+    if plane_axes is not None and not torch.equal(plane_axes.detach().cpu().float(), generate_planes()):
+        raise NotImplementedError('only the reference plane axes (generate_planes()) are built')
+    if triplane_depth < 2:
+        raise NotImplementedError('tri-grids need triplane_depth >= 2 (Real3D uses 3, egs/os_avatar/img2plane.yaml:66)')
+    pcl = _as_cl(plane_features, triplane_depth)
+    N, Cc, H, W = pcl.dims
+    coords = capi.f32(coordinates)
+    P = coords.shape[1]
+    out = torch.empty(N, 3, P, Cc, device=coords.device, dtype=torch.float32)
+    capi.check(capi.lib().r3dp_trigrid_sample(capi.ptr(pcl.data), N, Cc, pcl.depth, H, W, capi.ptr(coords), P, C.c_float(float(box_warp)),
+                                              capi.ptr(out), capi.stream()))
+    return out
+
+
 class ImportanceRenderer(torch.nn.Module):
     def __init__(self, hp=None):
         super().__init__()
@@ -137,8 +179,12 @@ class ImportanceRenderer(torch.nn.Module):
         self.ray_marcher = MipRayMarcher2()
         self.plane_axes = generate_planes()
         self.triplane_feature_type = self.hparams.get('triplane_feature_type', 'triplane')
-        if self.triplane_feature_type != 'triplane':
-            raise NotImplementedError(f"triplane_feature_type={self.triplane_feature_type!r}: only 'triplane' is built (SURVEY.md §8f #4)")
+        if self.triplane_feature_type not in ('triplane', 'trigrid', 'trigrid_v2'):
+            raise NotImplementedError(f"triplane_feature_type={self.triplane_feature_type!r}: 'triplane', 'trigrid' and 'trigrid_v2' are built ('3dgrid' is not a Real3D config)")
+        # tri-grids: depth slices per plane (renderer.py:181); 'triplane' ignores triplane_depth as the reference does
+        self.grid_depth = int(self.hparams.get('triplane_depth', 1)) if self.triplane_feature_type != 'triplane' else 1
+        if self.triplane_feature_type != 'triplane' and self.grid_depth < 2:
+            raise NotImplementedError('tri-grids need triplane_depth >= 2')
 
     def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options):
         """planes [N,3,C,H,W] | PlanesCL, decoder: OSGDecoder, rays [N,M,3] ->
@@ -154,7 +200,9 @@ class ImportanceRenderer(torch.nn.Module):
             raise NotImplementedError('training-time density noise / plane rescaling are outside the inference path')
         if not isinstance(decoder, OSGDecoder):
             raise TypeError('the fused renderer needs an OSGDecoder (its four parameter tensors are read by the kernel)')
-        pcl, pcl2 = _plane_sets(planes)
+        pcl, pcl2 = _plane_sets(planes, self.grid_depth)
+        if pcl.depth != self.grid_depth:
+            raise ValueError(f'planes hold {pcl.depth} depth slices, the renderer is configured for {self.grid_depth}')
         _, Cc, H, W = pcl.dims
         ray_o, ray_d = capi.f32(ray_origins), capi.f32(ray_directions)
         N, M = ray_o.shape[0], ray_o.shape[1]
@@ -194,7 +242,7 @@ class ImportanceRenderer(torch.nn.Module):
         """renderer.py:169-188: planes, coords [N,P,3] -> {'rgb': [N,P,C], 'sigma': [N,P,1]}."""
         if options.get('density_noise', 0) > 0:
             raise NotImplementedError('density_noise is a training-time option')
-        pcl = _as_phwc(planes)
+        pcl = _as_cl(planes, self.grid_depth) if self.grid_depth > 1 else _as_phwc(planes)
         N, Cc, H, W = pcl.dims
         coords = capi.f32(sample_coordinates)
         P = coords.shape[1]
@@ -202,9 +250,11 @@ class ImportanceRenderer(torch.nn.Module):
             rgb = torch.empty(N, P, Cc, device=coords.device)
             sigma = torch.empty(N, P, 1, device=coords.device)
             m = decoder.mlp_struct()
-            capi.check(capi.lib().r3dp_run_model(capi.ptr(pcl.data), N, Cc, H, W, capi.ptr(coords), P,
-                                                 C.c_float(float(options['box_warp'])), C.byref(m), capi.ptr(rgb), capi.ptr(sigma),
-                                                 capi.stream()))
+            capi.check(capi.lib().r3dp_run_model_grid(capi.ptr(pcl.data), N, Cc, pcl.depth, H, W, capi.ptr(coords), P,
+                                                      C.c_float(float(options['box_warp'])), C.byref(m), capi.ptr(rgb), capi.ptr(sigma),
+                                                      capi.stream()))
             return {'rgb': rgb, 'sigma': sigma}
+        if self.grid_depth > 1:
+            return decoder(sample_from_trigrids(None, pcl, coords, box_warp=options['box_warp'], triplane_depth=self.grid_depth), coords)
         feats = sample_from_planes(None, pcl, coords, box_warp=options['box_warp'])
         return decoder(feats, coords)

@@ -184,6 +184,35 @@ def warp_case():
     save('sr_warp_full', image=img, seeds=np.array([6, 7]))
 
 
+def trigrid_case():
+    """`triplane_feature_type: trigrid_v2`, `triplane_depth: 3` (egs/os_avatar/img2plane.yaml:65-66): sample_from_trigrids stand-alone and the
+    whole ImportanceRenderer (12 and 12+12 samples) on [2,3,32*3,32,32] tri-grids; wide-angle second camera as in small_cases()."""
+    from modules.eg3ds.volumetric_rendering.renderer import sample_from_trigrids
+    g = torch.Generator().manual_seed(31)
+    D = 3
+    grids = torch.randn(2, 3, 32 * D, 32, 32, generator=g)
+    cam = syn.lookat_camera(torch.tensor([0.1, -0.15]), torch.tensor([-0.3, 0.45]))
+    cam[1, 16] = cam[1, 20] = 1.2
+    mlp = syn.make_decoder_params(seed=12)
+    dec = ref_decoder(mlp)
+    pts = (torch.rand(2, 400, 3, generator=g) - 0.5) * 1.3
+    feat = sample_from_trigrids(generate_planes(), grids, pts, padding_mode='zeros', box_warp=1.0, triplane_depth=D)
+    out = {'planes': grids, 'camera': cam, 'coords': pts, 'feat': feat, 'depth_slices': D}
+    hp = dict(hparams, triplane_feature_type='trigrid_v2', triplane_depth=D)
+    res, S = 16, 12
+    c2w, K = syn.split_camera(cam)
+    o, d = RaySampler()(c2w, K, res)
+    for tag, S_imp in (('a', 0), ('b', 12)):
+        u_c, u_f = syn.make_jitter(2, res * res, S, S_imp, seed=33)
+        opts = dict(syn.RENDERING_OPTIONS, depth_resolution=S, depth_resolution_importance=S_imp)
+        with supplied_uniforms(u_c, u_f):
+            rgb, depth, wsum, valid = ImportanceRenderer(hp=hp)(grids, dec, o, d, opts)
+        out.update({f'{tag}.rgb': rgb, f'{tag}.depth': depth, f'{tag}.wsum': wsum, f'{tag}.valid': valid, f'{tag}.u_coarse': u_c})
+        if u_f is not None:
+            out[f'{tag}.u_fine'] = u_f
+    save('render_trigrid', res=res, S=S, **out, **{'mlp.' + k: v for k, v in mlp.items()})
+
+
 def load(name):
     return np.load(os.path.join(HERE, name + '.npz'))
 
@@ -193,7 +222,11 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'warp':
         warp_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'trigrid':
+        trigrid_case()
+        sys.exit(0)
     small_cases()
     layer_cases()
     full_cases()
     warp_case()
+    trigrid_case()

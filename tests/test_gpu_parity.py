@@ -547,3 +547,28 @@ def test_torso_head_two_frames_per_sample_styles_and_clip_cache():
         img_c2, _ = m(*args, noise_mode='none')
         m.end_clip()
     assert torch.equal(img_c, img) and torch.equal(img_c2, img)
+
+
+def test_trigrid_v2_vs_reference(golden):
+    """`triplane_feature_type: trigrid_v2`, `triplane_depth: 3` (egs/os_avatar/img2plane.yaml:65-66): the trilinear tri-grid gather stand-alone
+    (sample_from_trigrids), inside run_model and inside the fused renderer (streaming kernel for 12 samples, two-pass kernel for 12 + 12)
+    against fixtures produced by the reference's own sample_from_trigrids / ImportanceRenderer."""
+    g = golden('render_trigrid')
+    D = g['depth_slices']
+    grids, coords = g['planes'].to(DEV), g['coords'].to(DEV)
+    feat = r3.sample_from_trigrids(r3.generate_planes(), grids, coords, padding_mode='zeros', box_warp=1.0, triplane_depth=D)
+    assert feat.shape == g['feat'].shape and _maxdiff(feat, g['feat']) < 1e-5
+    cl = r3.grids_to_channels_last(grids, D)
+    assert torch.equal(cl.data, grids.view(2, 3, 32, D, 32, 32).permute(0, 1, 3, 4, 5, 2).contiguous())       # channel c*D + d -> slice d, channel c
+    hp = {'enable_rescale_plane_regulation': False, 'triplane_feature_type': 'trigrid_v2', 'triplane_depth': D}
+    ren, dec = r3.ImportanceRenderer(hp=hp), _decoder(mlp_of(g))
+    ref_rm = orc.decode(g['feat'], mlp_of(g))
+    out = ren.run_model(grids, dec, coords, None, {'box_warp': 1.0})
+    assert _maxdiff(out['rgb'], ref_rm[0]) < RGB_TOL and _maxdiff(out['sigma'], ref_rm[1]) < 1e-3
+    c2w, K = syn.split_camera(g['camera'])
+    o, d = r3.RaySampler()(c2w.to(DEV), K.to(DEV), g['res'])
+    for tag, S_imp in (('a', 0), ('b', 12)):
+        for planes in (grids, cl, (r3.PlanesCL(cl.data * 0.25, 'pdhwc'), r3.PlanesCL(cl.data * 0.75, 'pdhwc'))):
+            rgb, depth, wsum, valid = ren(planes, dec, o, d, _opts(g['S'], S_imp, False, g[tag + '.u_coarse'], g.get(tag + '.u_fine')))
+            assert torch.equal(valid.cpu(), g[tag + '.valid'])
+            assert _maxdiff(rgb, g[tag + '.rgb']) < RGB_TOL and _maxdiff(wsum, g[tag + '.wsum']) < RGB_TOL and _maxdiff(depth, g[tag + '.depth']) < 1e-3

@@ -86,3 +86,19 @@ def test_sr_warp_full(golden):
                                inp['kp_s'], inp['kp_d'], syn.make_sr_warp_params(seed=6), syn.StubTorsoModel())
     ref = golden('sr_warp_full')['image']
     assert _maxdiff(img, ref) < 2e-4 * float(ref.abs().max())
+
+
+def test_trigrid_sample_and_render(golden):
+    """`trigrid_v2` (depth-3 tri-grids, 3-D grid_sample; renderer.py:78-89) against the reference's sample_from_trigrids / ImportanceRenderer."""
+    g = golden('render_trigrid')
+    D = g['depth_slices']
+    f = orc.sample_trigrids(g['planes'], g['coords'], 1.0, D)
+    assert _maxdiff(f, g['feat']) < 1e-5
+    assert _maxdiff(orc.sample_trigrids_lib(g['planes'], g['coords'], 1.0, D), g['feat']) < 1e-5
+    c2w, K = syn.split_camera(g['camera'])
+    o, d = orc.gen_rays(c2w, K, g['res'])
+    for tag, S_imp in (('a', 0), ('b', 12)):
+        rgb, depth, wsum, valid = orc.render(g['planes'], mlp_of(g), o, d, S=g['S'], S_imp=S_imp, u_coarse=g[tag + '.u_coarse'],
+                                             u_fine=g.get(tag + '.u_fine'), trigrid_depth=D)
+        assert torch.equal(valid, g[tag + '.valid'])
+        assert _maxdiff(rgb, g[tag + '.rgb']) < TOL and _maxdiff(wsum, g[tag + '.wsum']) < TOL and _maxdiff(depth, g[tag + '.depth']) < 1e-4

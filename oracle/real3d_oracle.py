@@ -498,3 +498,29 @@ def superres_warp(rgb, x, ws, ref_torso_rgb, ref_bg_rgb, weights_img, segmap, kp
     x = conv_plain(conv_plain(conv_plain(x, p, 'fuse_fg_bg_convs.0', 0.01), p, 'fuse_fg_bg_convs.2', 0.01), p, 'fuse_fg_bg_convs.4')
     x, rgb = synthesis_block(x, rgb, ws3, p, 'block1.')
     return rgb, ret
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# large_sr                                 modules/eg3ds/models/superresolution.py:263-345 (LargeSynthesisBlock0/1, ResBlock2d)
+# ----------------------------------------------------------------------------------------------------------------------
+
+def resblock(x: Tensor, p: Dict[str, Tensor], prefix: str) -> Tensor:
+    """ResBlock2d.forward (superresolution.py:283-288): relu(conv2(relu(conv1(x)))) + x."""
+    out = F.relu(conv_plain(x, p, prefix + 'conv1'))
+    out = F.relu(conv_plain(out, p, prefix + 'conv2'))
+    return out + x
+
+
+def superres_large(rgb: Tensor, x: Tensor, ws: Tensor, p: Dict[str, Tensor], n_res: int) -> Tensor:
+    """SuperresolutionHybrid8XDC.forward with large_sr=True: each LargeSynthesisBlock = SynthesisBlock -> n_res ResBlock2d ->
+    rgb = rgb + to_rgb(x) (superresolution.py:309-312,325-329)."""
+    ws3 = ws[:, -1:, :].repeat(1, 3, 1)
+    if x.shape[-1] != 128:
+        x, rgb = resize_bilinear(x, 128), resize_bilinear(rgb, 128)
+    for blk in ('block0', 'block1'):
+        pre = {k[len(blk) + 7:]: v for k, v in p.items() if k.startswith(blk + '.block.')}
+        x, rgb = synthesis_block(x, rgb, ws3, {f'{blk}.{k}': v for k, v in pre.items()}, blk + '.')
+        for i in range(n_res):
+            x = resblock(x, p, f'{blk}.resblocks.{i}.')
+        rgb = rgb + conv_plain(x, p, f'{blk}.to_rgb')
+    return rgb

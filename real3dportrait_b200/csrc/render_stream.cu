@@ -38,7 +38,12 @@ constexpr int kOffDsc = kOffDep + ND * 128 * 4;
 constexpr int kDscF = 32;                                       // floats per sample descriptor row (15 used by tri-planes, 27 by tri-grids)
 constexpr int kOffRay = kOffDsc + kGatherWarps * kSPW * kDscF * 4;
 constexpr int kOffBar = kOffRay + kGatherWarps * 8 * 8 * 4;
-constexpr int kSmem = kOffBar + 512 + 1024;                     // + alignment slack
+#ifndef R3DP_RS_EXPERIMENT
+#define R3DP_RS_EXPERIMENT 0
+#endif
+constexpr int kOffFake = kOffBar + 512;                         // experiment builds only: 16 KB stand-in for TMA-staged plane tiles
+constexpr int kSmem = kOffFake + (R3DP_RS_EXPERIMENT ? 16384 + 512 : 0) + 1024;     // + alignment slack
+__device__ int g_rs_fake = 0;
 
 struct Bars {
     uint64_t a1_full[NS], a1_empty[NS];
@@ -196,6 +201,29 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
 #pragma unroll
                     for (int e = 0; e < (GRID ? 7 : 4); ++e) { const float4 qv = rw[e]; dscv[4 * e] = qv.x; dscv[4 * e + 1] = qv.y; dscv[4 * e + 2] = qv.z; dscv[4 * e + 3] = qv.w; }
                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#if R3DP_RS_EXPERIMENT
+                    // UPPER-BOUND EXPERIMENT (never in the product build; results are wrong by construction): the taps of planes 1 and 2 - the
+                    // planes whose footprint the rays of an item share, i.e. what a TMA box would stage - are read from a 16 KB shared-memory
+                    // window at zero staging cost.  No staging scheme (cp.async.bulk.tensor boxes, multicast, ...) can beat this variant.
+                    if (!GRID && g_rs_fake) {
+                        const float* fake = reinterpret_cast<const float*>(smem + kOffFake);
+#pragma unroll
+                        for (int p = 0; p < 3; ++p) {
+                            const int off = __float_as_int(dscv[5 * p]);
+                            const float* b = p == 0 ? base0 + off + cq * 4 : fake + ((off >> 5) & 63) * 32 + cq * 4;
+                            const int tsx = p == 0 ? ts : 32, rsx = p == 0 ? rs : 64;
+                            float4 t00, t10, t01, t11;
+                            if (p == 0) { t00 = ldg_nc_f4(b); t10 = ldg_nc_f4(b + tsx); t01 = ldg_nc_f4(b + rsx); t11 = ldg_nc_f4(b + rsx + tsx); }
+                            else { t00 = *reinterpret_cast<const float4*>(b); t10 = *reinterpret_cast<const float4*>(b + tsx);
+                                   t01 = *reinterpret_cast<const float4*>(b + rsx); t11 = *reinterpret_cast<const float4*>(b + rsx + tsx); }
+                            const float w00 = dscv[5 * p + 1], w10 = dscv[5 * p + 2], w01 = dscv[5 * p + 3], w11 = dscv[5 * p + 4];
+                            acc.x += t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
+                            acc.y += t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
+                            acc.z += t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
+                            acc.w += t00.w * w00 + t10.w * w10 + t01.w * w01 + t11.w * w11;
+                        }
+                    } else
+#endif
                     gather_desc<GRID>(base0, dscv, rs, ts, ss, cq, acc);
                     if (base1 != nullptr) gather_desc<GRID>(base1, dscv, rs, ts, ss, cq, acc);     // second plane set, same points (sampling is linear)
                     // mean over the planes as fp16 hi + lo halves into the swizzled A1 stage: lane cq owns K = [4cq, 4cq+4) of both halves
@@ -396,6 +424,9 @@ static int launch(RenderArgs a, cudaStream_t st) {
     constexpr int G = 128 >> LOG2D;
     const bool image = a.res > 0 && a.res * a.res == a.M && (a.res % G) == 0;
     a.tile_cols = image ? a.res : 0;
+#if R3DP_RS_EXPERIMENT
+    { const char* e = getenv("R3DP_RS_FAKE"); const int v = (e && e[0] == '1') ? 1 : 0; R3DP_CUDA(cudaMemcpyToSymbolAsync(g_rs_fake, &v, sizeof(int), 0, cudaMemcpyHostToDevice, st)); }
+#endif
     const int items_per_frame = (a.M + G - 1) / G;
     const int total = a.N * items_per_frame;
     R3DP_CUDA(cudaFuncSetAttribute(render_stream_kernel<LOG2D, GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));

@@ -89,6 +89,7 @@ struct Conv2Args {
     const float* bias; const float* wrgb; const float* brgb; const float* img_prev; float* img_out; int img_H, img_W;
     float act_slope, act_gain;      // epilogue activation: v < 0 ? v*slope : v, then * gain  (0.2, sqrt2 = bias_act lrelu; 0.01, 1 = nn.LeakyReLU; 1, 1 = linear)
     int skip_same_res;              // ToRGB skip image has the output resolution (SynthesisBlockNoUp) instead of half (FIR-upsampled)
+    const __half* residual;         // non-null: added to the activated output before the store (ResBlock2d of large_sr)
     int out_clamp;                  // final image clamped to [-1, 1] (the caller-side imgs.clamp(-1,1), inference/real3d_infer.py:515)
     uint8_t* img_out_u8;            // non-null: final image as uint8 HWC frames [N][H][W][3] = int((clamp(x)+1)/2*255) (real3d_infer.py:519) instead of fp32 NCHW
     unsigned long long* debug;      // R3DP_TC_DEBUG_TIMING builds: [acc wait, strip wait, tap wait, issue, total, #CTAs] clock sums of the MMA warp
@@ -511,9 +512,18 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const int p = i * 8 + (lane >> 2), cch = lane & 3;
-                                const uint4 pk = st[p * 4 + (cch ^ ((p >> 1) & 3))];
+                                uint4 pk = st[p * 4 + (cch ^ ((p >> 1) & 3))];
                                 const int Xp = (col0 + q * 32 + p) * a.ox_mul + P.ox_off;
-                                if (row_ok && Xp < a.out_W) *reinterpret_cast<uint4*>(dst_row + (size_t)Xp * a.out_C + c0 + cch * 8) = pk;
+                                if (row_ok && Xp < a.out_W) {
+                                    const size_t eo = ((size_t)n * a.out_H + Y) * a.out_W * a.out_C + nblk * BN + (size_t)Xp * a.out_C + c0 + cch * 8;
+                                    if (a.residual) {          // ResBlock2d: out = act(conv) + x (superresolution.py:283-288), same NHWC fp16 layout as the output
+                                        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(a.residual + eo));
+                                        __half2* ph = reinterpret_cast<__half2*>(&pk); const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) { const float2 x = __half22float2(ph[e]), r = __half22float2(rh[e]); ph[e] = __floats2half2_rn(x.x + r.x, x.y + r.y); }
+                                    }
+                                    *reinterpret_cast<uint4*>(a.out + eo) = pk;
+                                }
                             }
                             __syncwarp();
                         }
@@ -774,7 +784,7 @@ __global__ void __launch_bounds__(256) fir_tma_kernel(const __grid_constant__ CU
 // ToRGB for the first block: x NHWC fp16 [N][H][W][C] -> img_out NCHW fp32 = upsample2d(img_prev) + conv1x1 + bias.  One warp per
 // 32 consecutive pixels is wasteful on loads, so: one thread per pixel, 16-byte channel vectors, weights in smem.
 __global__ void __launch_bounds__(256) torgb_f16_kernel(const __half* __restrict__ x, const float* __restrict__ wrgb, const float* __restrict__ brgb,
-                                                        const float* __restrict__ img_prev, int H, int W, int C, int w_shared,
+                                                        const float* __restrict__ img_prev, int H, int W, int C, int w_shared, int same_res,
                                                         float* __restrict__ img_out) {
     extern __shared__ float s_w[];                               // [3][C]
     const int n = blockIdx.y;
@@ -799,28 +809,13 @@ __global__ void __launch_bounds__(256) torgb_f16_kernel(const __half* __restrict
         }
     }
     float out[3] = {r + brgb[0], g + brgb[1], b + brgb[2]};
-    if (img_prev) {
+    if (img_prev && same_res) {                                  // rgb = rgb + to_rgb(x) (LargeSynthesisBlock, superresolution.py:311,328)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) out[c] += img_prev[((size_t)n * 3 + c) * H * W + pix];
+    } else if (img_prev) {
         const int h = H / 2, w = W / 2;
-        const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float* ip = img_prev + ((size_t)n * 3 + c) * h * w;
-            float acc = 0.f;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int zy = Y + u - 2;
-                if (zy < 0 || (zy & 1) || (zy >> 1) >= h) continue;
-                float rowv = 0.f;
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const int zx = X + v - 2;
-                    if (zx < 0 || (zx & 1) || (zx >> 1) >= w) continue;
-                    rowv = fmaf(k4[v], ip[(size_t)(zy >> 1) * w + (zx >> 1)], rowv);
-                }
-                acc = fmaf(k4[u], rowv, acc);
-            }
-            out[c] += acc;
-        }
+        for (int c = 0; c < 3; ++c) out[c] += upsampled_skip(img_prev + ((size_t)n * 3 + c) * h * w, h, w, Y, X);
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) img_out[((size_t)n * 3 + c) * H * W + pix] = out[c];
@@ -1075,16 +1070,20 @@ extern "C" int r3dp_sr_tc_last_layer(const void* x_f16, const void* wp_f16, cons
 }
 
 // ToRGB of a non-final block: x NHWC fp16 [N][H][W][C] -> img_out NCHW fp32 [N][3][H][W] (+ upsample2d(img_prev) + bias).
-extern "C" int r3dp_sr_tc_torgb(const void* x_f16, const float* wrgb, const float* brgb, const float* img_prev, int N, int Nw, int C, int H,
-                                int W, float* img_out, r3dp_stream_t stream) {
+extern "C" int r3dp_sr_tc_torgb_ex(const void* x_f16, const float* wrgb, const float* brgb, const float* img_prev, int same_res, int N, int Nw, int C,
+                                   int H, int W, float* img_out, r3dp_stream_t stream) {
     R3DP_REQUIRE(x_f16 && wrgb && brgb && img_out, "sr_tc_torgb: null pointer");
     R3DP_REQUIRE(N > 0 && (Nw == N || Nw == 1) && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "sr_tc_torgb: bad shape");
     dim3 grid((H * W + 255) / 256, N);
     torgb_f16_kernel<<<grid, 256, 3 * C * sizeof(float), as_stream(stream)>>>(reinterpret_cast<const __half*>(x_f16), wrgb, brgb, img_prev, H, W, C,
-                                                                              Nw == 1, img_out);
+                                                                              Nw == 1, same_res, img_out);
     R3DP_LAUNCH_CHECK();
     count_launches(1);
     return 0;
+}
+extern "C" int r3dp_sr_tc_torgb(const void* x_f16, const float* wrgb, const float* brgb, const float* img_prev, int N, int Nw, int C, int H,
+                                int W, float* img_out, r3dp_stream_t stream) {
+    return r3dp_sr_tc_torgb_ex(x_f16, wrgb, brgb, img_prev, 0, N, Nw, C, H, W, img_out, stream);
 }
 
 // SynthesisLayer (up == 1) fused with the block's ToRGB + skip (networks_stylegan2.py:463-469): y [N,H,W,O] fp16 AND
@@ -1220,10 +1219,10 @@ extern "C" int r3dp_sr_tc_layer_up_composed(const void* x_f16, const void* wpc_f
 // Plain nn.Conv2d (k = 1 or 3, stride 1, "same" padding) [+ activation] on the tensor-core path: x [N][H][W][Ip] fp16, weights packed by
 // r3dp_sr_tc_pack_weights from the [1][O][I][k][k] fp32 tensor (k = 1: the value sits in tap 4), y [N][H][W][O] fp16.
 // act: 0 = linear, 1 = lrelu(0.2)*sqrt2 (bias_act), 2 = nn.LeakyReLU() (slope 0.01).
-extern "C" int r3dp_sr_tc_conv(const void* x_f16, const void* wp_f16, const float* bias, int N, int Nw, int I, int O, int H, int W, int ksize,
-                               int act, void* y_f16, r3dp_stream_t stream) {
+extern "C" int r3dp_sr_tc_conv_res(const void* x_f16, const void* wp_f16, const float* bias, int N, int Nw, int I, int O, int H, int W, int ksize,
+                                   int act, const void* residual_f16, void* y_f16, r3dp_stream_t stream) {
     R3DP_REQUIRE(x_f16 && wp_f16 && bias && y_f16, "sr_tc_conv: null pointer");
-    R3DP_REQUIRE(N > 0 && (Nw == N || Nw == 1) && W % BM == 0 && O % BN == 0 && O <= 256 && (ksize == 1 || ksize == 3) && act >= 0 && act <= 2,
+    R3DP_REQUIRE(N > 0 && (Nw == N || Nw == 1) && W % BM == 0 && O % BN == 0 && O <= 256 && (ksize == 1 || ksize == 3) && act >= 0 && act <= 3,
                  "sr_tc_conv: bad shape / options");
     const int Ip = (I + 63) / 64 * 64;
     Conv2Args a = {};
@@ -1234,9 +1233,14 @@ extern "C" int r3dp_sr_tc_conv(const void* x_f16, const void* wp_f16, const floa
     fill_taps2(a.ph[0].taps, t);
     a.ph[0].rows = H;
     a.mode = kStoreAct; a.out = reinterpret_cast<__half*>(y_f16); a.out_H = H; a.out_W = W; a.out_C = O; a.oy_mul = a.ox_mul = 1; a.bias = bias;
-    a.act_slope = act == 0 ? 1.0f : (act == 1 ? 0.2f : 0.01f);
+    a.act_slope = act == 0 ? 1.0f : (act == 1 ? 0.2f : (act == 2 ? 0.01f : 0.0f));      // max(v, v*slope): slope 0 = ReLU
     a.act_gain = act == 1 ? 1.4142135623730951f : 1.0f;
+    a.residual = reinterpret_cast<const __half*>(residual_f16);
     return run_conv2(x_f16, N, H, W, Ip, wp_f16, Nw, O, a, H, as_stream(stream));
+}
+extern "C" int r3dp_sr_tc_conv(const void* x_f16, const void* wp_f16, const float* bias, int N, int Nw, int I, int O, int H, int W, int ksize,
+                               int act, void* y_f16, r3dp_stream_t stream) {
+    return r3dp_sr_tc_conv_res(x_f16, wp_f16, bias, N, Nw, I, O, H, W, ksize, act, nullptr, y_f16, stream);
 }
 
 // SynthesisBlockNoUp tail (superresolution.py:159-258): conv3x3 (modulated, up == 1) + bias/lrelu -> y, and img_out = img_prev (SAME resolution)

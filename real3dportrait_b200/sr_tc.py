@@ -74,12 +74,48 @@ def to_nhwc_f16(x: torch.Tensor, size: int) -> torch.Tensor:
     return y
 
 
+def pack_plain(conv: torch.nn.Conv2d, in_tensor_channels: int, out_pad: int = 128):
+    """nn.Conv2d (k = 1|3) -> packed fp16 weights [1,9,Opad,Ipad] + fp32 bias [Opad]; output channels padded to a multiple of
+    `out_pad` with zero filters, input channels padded (zero weights) to the channel count of the activation tensor it reads."""
+    w = conv.weight.detach().float()
+    O, I, k, _ = w.shape
+    Op = (O + out_pad - 1) // out_pad * out_pad
+    w9 = torch.zeros(1, Op, in_tensor_channels, 3, 3, device=w.device)
+    if k == 3:
+        w9[0, :O, :I] = w
+    else:
+        w9[0, :O, :I, 1, 1] = w[:, :, 0, 0]
+    Ip = (in_tensor_channels + 63) // 64 * 64
+    packed = torch.empty(1, 9, Op, Ip, device=w.device, dtype=torch.float16)
+    capi.check(capi.lib().r3dp_sr_tc_pack_weights(capi.ptr(w9), 1, Op, in_tensor_channels, capi.ptr(packed, torch.float16), capi.stream()))
+    bias = torch.zeros(Op, device=w.device)
+    bias[:O] = conv.bias.detach().float()
+    return packed, bias, k
+
+
+def conv_plain(x16: torch.Tensor, packed, act: int, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x16 [N,H,W,Ct] fp16 -> [N,H,W,Opad] fp16; act 0 linear, 2 nn.LeakyReLU(0.01), 3 ReLU; residual (same shape as the output) is added
+    after the activation (ResBlock2d)."""
+    wp, bias, k = packed
+    N, H, W, Ct = x16.shape
+    y = torch.empty(N, H, W, wp.shape[2], device=x16.device, dtype=torch.float16)
+    with capi.region('sr_conv'):
+        capi.check(capi.lib().r3dp_sr_tc_conv_res(capi.ptr(x16, torch.float16), capi.ptr(wp, torch.float16), capi.ptr(bias), N, 1, Ct, wp.shape[2], H, W, k, act,
+                                                  capi.ptr(residual, torch.float16), capi.ptr(y, torch.float16), capi.stream()))
+    return y
+
+
+def _sblocks(sr):
+    """The two SynthesisBlocks (inside the LargeSynthesisBlocks when large_sr)."""
+    return (sr.block0.block, sr.block1.block) if getattr(sr, 'large_sr', False) else (sr.block0, sr.block1)
+
+
 class Prepared:
     """Folded + packed weights of the four conv layers and the two ToRGB layers for a given set of styles."""
     __slots__ = ('wp', 'wrgb0', 'wrgb1', 'Nw')
 
     def __init__(self, sr, wsel: torch.Tensor):
-        b0, b1 = sr.block0, sr.block1
+        b0, b1 = _sblocks(sr)
         self.Nw = wsel.shape[0]
         self.wp = [pack_for(b0.conv0, wsel[:, 0]), pack_for(b0.conv1, wsel[:, 1]), pack_for(b1.conv0, wsel[:, 0]), pack_for(b1.conv1, wsel[:, 1])]
         self.wrgb0, self.wrgb1 = b0.torgb.folded_weight(wsel[:, 2]), b1.torgb.folded_weight(wsel[:, 2])
@@ -110,7 +146,7 @@ def forward(sr, rgb: torch.Tensor, x: torch.Tensor, ws3: torch.Tensor, shared_st
         else:
             x0 = to_nhwc_f16(x, sr.input_resolution)
         rgb0 = SuperresolutionHybrid8XDC._resize(rgb, sr.input_resolution) if rgb.shape[-1] != sr.input_resolution else capi.f32(rgb)
-    b0, b1, Nw, wp = sr.block0, sr.block1, prep.Nw, prep.wp
+    (b0, b1), Nw, wp = _sblocks(sr), prep.Nw, prep.wp
     a0 = layer(x0, b0.conv0, wp[0], 2)
     a1 = torch.empty(N, 256, 256, 256, device=x.device, dtype=torch.float16)
     img1 = torch.empty(N, 3, 256, 256, device=x.device)
@@ -118,6 +154,8 @@ def forward(sr, rgb: torch.Tensor, x: torch.Tensor, ws3: torch.Tensor, shared_st
         capi.check(L.r3dp_sr_tc_layer_torgb(capi.ptr(a0, torch.float16), capi.ptr(wp[1], torch.float16), capi.ptr(capi.f32(b0.conv1.bias)),
                                             capi.ptr(prep.wrgb0), capi.ptr(capi.f32(b0.torgb.bias)), capi.ptr(rgb0), N, Nw, 256, 256, 256, 256,
                                             capi.ptr(a1, torch.float16), capi.ptr(img1), capi.stream()))
+    if getattr(sr, 'large_sr', False):
+        return _forward_large_tail(sr, a1, img1, prep, out_clamp, out_uint8)
     a2 = layer(a1, b1.conv0, wp[2], 2)
     out = torch.empty(N, 512, 512, 3, device=x.device, dtype=torch.uint8) if out_uint8 else torch.empty(N, 3, 512, 512, device=x.device)
     with capi.region('sr_conv'):                               # block1.conv1 + block1.torgb: the 128-channel activation is never written
@@ -126,3 +164,47 @@ def forward(sr, rgb: torch.Tensor, x: torch.Tensor, ws3: torch.Tensor, shared_st
                                               None if out_uint8 else capi.ptr(out), capi.ptr(out, torch.uint8) if out_uint8 else None,
                                               int(out_clamp or out_uint8), capi.stream()))
     return out
+
+
+def _large_packed(sr):
+    """Packed plain convolutions of the large_sr residual blocks / to_rgb layers (cached until the parameters are reloaded)."""
+    c = getattr(sr, '_large_cache', None)
+    if c is None:
+        c = {}
+        for name, blk, ch in (('b0', sr.block0, 256), ('b1', sr.block1, 128)):
+            c[name] = [(pack_plain(rb.conv1, ch), pack_plain(rb.conv2, ch)) for rb in blk.resblocks]
+            c[name + '_rgb'] = (blk.to_rgb.weight.detach().float().reshape(1, 3, ch).contiguous(), blk.to_rgb.bias.detach().float().contiguous())
+        sr._large_cache = c
+    return c
+
+
+def _forward_large_tail(sr, a1, img1, prep, out_clamp, out_uint8):
+    """LargeSynthesisBlock0/1.forward after the first SynthesisBlock (superresolution.py:296-329): residual blocks on the block output,
+    `rgb = rgb + to_rgb(x)`, then the second block the same way.  x stays NHWC fp16, rgb fp32 NCHW."""
+    if out_uint8:
+        raise NotImplementedError('uint8 frames are written by the standard SR\'s last epilogue; large_sr returns fp32')
+    L = capi.lib()
+    lp = _large_packed(sr)
+    _, b1 = _sblocks(sr)
+    N, Nw, wp = a1.shape[0], prep.Nw, prep.wp
+
+    def tail(x16, img, key, ch, res):
+        for c1, c2 in lp[key]:
+            t = conv_plain(x16, c1, 3)
+            x16 = conv_plain(t, c2, 3, residual=x16)
+        wrgb, brgb = lp[key + '_rgb']
+        out = torch.empty(N, 3, res, res, device=x16.device)
+        capi.check(L.r3dp_sr_tc_torgb_ex(capi.ptr(x16, torch.float16), capi.ptr(wrgb), capi.ptr(brgb), capi.ptr(img), 1, N, 1, ch, res, res, capi.ptr(out),
+                                         capi.stream()))
+        return x16, out
+
+    x16, img1 = tail(a1, img1, 'b0', 256, 256)
+    a2 = layer(x16, b1.conv0, wp[2], 2)
+    a3 = torch.empty(N, 512, 512, 128, device=a1.device, dtype=torch.float16)
+    img2 = torch.empty(N, 3, 512, 512, device=a1.device)
+    with capi.region('sr_conv'):
+        capi.check(L.r3dp_sr_tc_layer_torgb(capi.ptr(a2, torch.float16), capi.ptr(wp[3], torch.float16), capi.ptr(capi.f32(b1.conv1.bias)),
+                                            capi.ptr(prep.wrgb1), capi.ptr(capi.f32(b1.torgb.bias)), capi.ptr(img1), N, Nw, 128, 128, 512, 512,
+                                            capi.ptr(a3, torch.float16), capi.ptr(img2), capi.stream()))
+    _, out = tail(a3, img2, 'b1', 128, 512)
+    return out.clamp_(-1, 1) if out_clamp else out

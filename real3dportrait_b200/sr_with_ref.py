@@ -35,23 +35,7 @@ class SynthesisBlockNoUp(torch.nn.Module):
         self.num_conv, self.num_torgb = 2, 1
 
 
-def _pack_plain(conv: torch.nn.Conv2d, in_tensor_channels: int, out_pad: int = 128):
-    """nn.Conv2d (k = 1|3) -> packed fp16 weights [1,9,Opad,Ipad] + fp32 bias [Opad]; output channels padded to a multiple of
-    `out_pad` with zero filters, input channels padded (zero weights) to the channel count of the activation tensor it reads."""
-    w = conv.weight.detach().float()
-    O, I, k, _ = w.shape
-    Op = (O + out_pad - 1) // out_pad * out_pad
-    w9 = torch.zeros(1, Op, in_tensor_channels, 3, 3, device=w.device)
-    if k == 3:
-        w9[0, :O, :I] = w
-    else:
-        w9[0, :O, :I, 1, 1] = w[:, :, 0, 0]
-    Ip = (in_tensor_channels + 63) // 64 * 64
-    packed = torch.empty(1, 9, Op, Ip, device=w.device, dtype=torch.float16)
-    capi.check(capi.lib().r3dp_sr_tc_pack_weights(capi.ptr(w9), 1, Op, in_tensor_channels, capi.ptr(packed, torch.float16), capi.stream()))
-    bias = torch.zeros(Op, device=w.device)
-    bias[:O] = conv.bias.detach().float()
-    return packed, bias, k
+_pack_plain = sr_tc.pack_plain
 
 
 class SuperresolutionHybrid8XDC_Warp(SuperresolutionHybrid8XDC):

@@ -141,24 +141,68 @@ class SynthesisBlock(torch.nn.Module):
         return x, img
 
 
+class ResBlock2d(torch.nn.Module):
+    """Parameter container of superresolution.py:263-288: out = relu(conv2(relu(conv1(x)))) + x (runs inside sr_tc.forward)."""
+
+    def __init__(self, in_features, kernel_size, padding):
+        super().__init__()
+        self.conv1 = torch.nn.Conv2d(in_features, in_features, kernel_size=kernel_size, padding=padding)
+        self.conv2 = torch.nn.Conv2d(in_features, in_features, kernel_size=kernel_size, padding=padding)
+        self.act = torch.nn.ReLU(inplace=False)
+
+
+class LargeSynthesisBlock0(torch.nn.Module):
+    """superresolution.py:296-312: SynthesisBlock(channels -> 256 @256) + residual blocks + `rgb = rgb + to_rgb(x)`."""
+
+    def __init__(self, channels, use_fp16, resblocks, **block_kwargs):
+        super().__init__()
+        self.block = SynthesisBlock(channels, 256, w_dim=512, resolution=256, img_channels=3, is_last=False, use_fp16=use_fp16, conv_clamp=None,
+                                    **block_kwargs)
+        self.resblocks = torch.nn.Sequential(*[ResBlock2d(256, kernel_size=3, padding=1) for _ in range(resblocks)])
+        self.to_rgb = torch.nn.Conv2d(256, 3, kernel_size=1)
+
+
+class LargeSynthesisBlock1(torch.nn.Module):
+    """superresolution.py:314-329: SynthesisBlock(256 -> 128 @512) + residual blocks + `rgb = rgb + to_rgb(x)`."""
+
+    def __init__(self, use_fp16, resblocks, **block_kwargs):
+        super().__init__()
+        self.block = SynthesisBlock(256, 128, w_dim=512, resolution=512, img_channels=3, is_last=True, use_fp16=use_fp16, conv_clamp=None,
+                                    **block_kwargs)
+        self.resblocks = torch.nn.Sequential(*[ResBlock2d(128, kernel_size=3, padding=1) for _ in range(resblocks)])
+        self.to_rgb = torch.nn.Conv2d(128, 3, kernel_size=1)
+
+
 class SuperresolutionHybrid8XDC(torch.nn.Module):
-    def __init__(self, channels, img_resolution, sr_num_fp16_res, sr_antialias, large_sr=False, sr_mode='fp32', **block_kwargs):
+    def __init__(self, channels, img_resolution, sr_num_fp16_res, sr_antialias, large_sr=False, sr_mode='fp32', resblocks_in_large_sr=None,
+                 **block_kwargs):
+        """large_sr=True (superresolution.py:263-345) needs `resblocks_in_large_sr` (the reference reads hparams['resblocks_in_large_sr']) and
+        runs on the tensor-core path only."""
         super().__init__()
         assert img_resolution == 512
-        if sr_num_fp16_res > 0 or large_sr:
-            raise NotImplementedError('Real3D-Portrait runs the SR in fp32 with large_sr=False (img2plane_baseline.py:102-104)')
+        if sr_num_fp16_res > 0:
+            raise NotImplementedError('Real3D-Portrait runs the SR with sr_num_fp16_res=0 (img2plane_baseline.py:102)')
         assert sr_mode in ('fp32', 'tc')
         self.sr_mode = sr_mode
+        self.large_sr = bool(large_sr)
         self.input_resolution = 128
         self.sr_antialias = sr_antialias
-        self.block0 = SynthesisBlock(channels, 256, w_dim=512, resolution=256, img_channels=3, is_last=False, use_fp16=False,
-                                     conv_clamp=None, **block_kwargs)
-        self.block1 = SynthesisBlock(256, 128, w_dim=512, resolution=512, img_channels=3, is_last=True, use_fp16=False,
-                                     conv_clamp=None, **block_kwargs)
+        if self.large_sr:
+            if sr_mode != 'tc' or resblocks_in_large_sr is None:
+                raise NotImplementedError("large_sr is built on the tensor-core path (sr_mode='tc') and needs resblocks_in_large_sr")
+            self.block0 = LargeSynthesisBlock0(channels, False, int(resblocks_in_large_sr), **block_kwargs)
+            self.block1 = LargeSynthesisBlock1(False, int(resblocks_in_large_sr), **block_kwargs)
+        else:
+            self.block0 = SynthesisBlock(channels, 256, w_dim=512, resolution=256, img_channels=3, is_last=False, use_fp16=False,
+                                         conv_clamp=None, **block_kwargs)
+            self.block1 = SynthesisBlock(256, 128, w_dim=512, resolution=512, img_channels=3, is_last=True, use_fp16=False,
+                                         conv_clamp=None, **block_kwargs)
         self.static_prepared = None
+        self._large_cache = None
 
     def _load_from_state_dict(self, *a, **k):
         self.static_prepared = None          # prepared (folded + packed) weights belong to the parameters being replaced
+        self._large_cache = None
         return super()._load_from_state_dict(*a, **k)
 
     @staticmethod

@@ -102,6 +102,22 @@ def make_sr_params(seed: int = 5, channels: int = 32, w_dim: int = 512) -> Dict[
     return p
 
 
+def make_sr_large_params(seed: int = 8, n_res: int = 2) -> Dict[str, torch.Tensor]:
+    """state_dict of SuperresolutionHybrid8XDC(large_sr=True) (superresolution.py:263-345): the two SynthesisBlocks move under `.block`,
+    plus `resblocks.{i}.conv{1,2}` and `to_rgb` per LargeSynthesisBlock."""
+    base = make_sr_params(seed=seed)
+    p = {k.replace('block0.', 'block0.block.', 1).replace('block1.', 'block1.block.', 1): v for k, v in base.items()}
+    g = torch.Generator().manual_seed(seed + 200)
+    for blk, ch in (('block0', 256), ('block1', 128)):
+        for i in range(n_res):
+            for c in ('conv1', 'conv2'):
+                p[f'{blk}.resblocks.{i}.{c}.weight'] = torch.randn(ch, ch, 3, 3, generator=g) / math.sqrt(ch * 9) * 1.2
+                p[f'{blk}.resblocks.{i}.{c}.bias'] = 0.1 * torch.randn(ch, generator=g)
+        p[f'{blk}.to_rgb.weight'] = torch.randn(3, ch, 1, 1, generator=g) / math.sqrt(ch)
+        p[f'{blk}.to_rgb.bias'] = 0.1 * torch.randn(3, generator=g)
+    return p
+
+
 RENDERING_OPTIONS = {
     'ray_start': 'auto', 'ray_end': 'auto', 'box_warp': 1.0, 'depth_resolution': 48,
     'depth_resolution_importance': 0, 'disparity_space_sampling': False, 'clamp_mode': 'softplus',

@@ -213,6 +213,21 @@ def trigrid_case():
     save('render_trigrid', res=res, S=S, **out, **{'mlp.' + k: v for k, v in mlp.items()})
 
 
+def large_sr_case():
+    """SuperresolutionHybrid8XDC(large_sr=True) with hparams['resblocks_in_large_sr'] = 2 (superresolution.py:263-345) on the rendered
+    feature image of render_full48."""
+    hparams.update({'resblocks_in_large_sr': 2})
+    import modules.eg3ds.models.superresolution as sr_mod
+    sr_mod.hparams['resblocks_in_large_sr'] = 2
+    sr = SuperresolutionHybrid8XDC(channels=32, img_resolution=512, sr_num_fp16_res=0, sr_antialias=True, large_sr=True, channel_base=32768,
+                                   channel_max=512, fused_modconv_default='inference_only').eval()
+    sr.load_state_dict(syn.make_sr_large_params(seed=8, n_res=2), strict=True)
+    g = load('render_full48')
+    fimg = torch.from_numpy(g['rgb']).permute(0, 2, 1).reshape(1, 32, 64, 64).contiguous()
+    img = sr(fimg[:, :3], fimg, torch.ones(1, 14, 512), noise_mode='none')
+    save('sr_large', image=img, seeds=np.array([8]), n_res=2)
+
+
 def load(name):
     return np.load(os.path.join(HERE, name + '.npz'))
 
@@ -222,6 +237,9 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'warp':
         warp_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'large_sr':
+        large_sr_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'trigrid':
         trigrid_case()
         sys.exit(0)
@@ -230,3 +248,4 @@ if __name__ == '__main__':
     full_cases()
     warp_case()
     trigrid_case()
+    large_sr_case()

@@ -572,3 +572,17 @@ def test_trigrid_v2_vs_reference(golden):
             rgb, depth, wsum, valid = ren(planes, dec, o, d, _opts(g['S'], S_imp, False, g[tag + '.u_coarse'], g.get(tag + '.u_fine')))
             assert torch.equal(valid.cpu(), g[tag + '.valid'])
             assert _maxdiff(rgb, g[tag + '.rgb']) < RGB_TOL and _maxdiff(wsum, g[tag + '.wsum']) < RGB_TOL and _maxdiff(depth, g[tag + '.depth']) < 1e-3
+
+
+def test_large_sr_tc_vs_reference(golden):
+    """large_sr=True (LargeSynthesisBlock0/1: SynthesisBlock -> ResBlock2d x n -> rgb += to_rgb(x); superresolution.py:263-345) on the tensor-core
+    path against the REFERENCE class's fp32 image; state_dict keys equal the reference's (strict load on both sides)."""
+    fimg = orc.feature_image(golden('render_full48')['rgb'], 64).to(DEV)
+    sr = r3.SuperresolutionHybrid8XDC(channels=32, img_resolution=512, sr_num_fp16_res=0, sr_antialias=True, large_sr=True, sr_mode='tc',
+                                      resblocks_in_large_sr=2)
+    sr.load_state_dict(syn.make_sr_large_params(seed=8, n_res=2), strict=True)
+    img = sr.to(DEV)(fimg[:, :3], fimg, torch.ones(1, 14, 512, device=DEV), noise_mode='none')
+    ref = golden('sr_large')['image']
+    err, psnr, rng = _maxdiff(img, ref), _psnr(img, ref), float(ref.max() - ref.min())
+    print(f'large_sr (tc): max-abs {err:.3e} on range {rng:.1f}, PSNR {psnr:.1f} dB')
+    assert err < 2e-3 * rng and psnr > 68.0, (err, psnr)

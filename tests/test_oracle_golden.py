@@ -102,3 +102,11 @@ def test_trigrid_sample_and_render(golden):
                                              u_fine=g.get(tag + '.u_fine'), trigrid_depth=D)
         assert torch.equal(valid, g[tag + '.valid'])
         assert _maxdiff(rgb, g[tag + '.rgb']) < TOL and _maxdiff(wsum, g[tag + '.wsum']) < TOL and _maxdiff(depth, g[tag + '.depth']) < 1e-4
+
+
+def test_large_sr(golden):
+    """SuperresolutionHybrid8XDC(large_sr=True) (ResBlock2d + to_rgb tails, superresolution.py:263-345) against the reference class."""
+    fimg = orc.feature_image(golden('render_full48')['rgb'], 64)
+    out = orc.superres_large(fimg[:, :3], fimg, torch.ones(1, 14, 512), syn.make_sr_large_params(seed=8, n_res=2), 2)
+    ref = golden('sr_large')['image']
+    assert _maxdiff(out, ref) < 1e-4 * float(ref.abs().max())

@@ -115,6 +115,7 @@ __device__ __forceinline__ int ray_of(const RenderArgs& a, int tile, int r) {
 // PAIR (CONST only) = two samples per thread in the decoder (halves the constant-load traffic; ~160 regs, 2 CTAs/SM) - used when every
 // pass gives each thread a full pair; otherwise one sample per thread at 80 regs, 4 CTAs/SM
 // TC = decoder on tcgen05 (single-pass renders with R*S <= 384; 256 threads, 2 CTAs/SM); see the MlpTcImage comment
+constexpr int kPfCtas = 32;                            // CTAs of a frame that issue its L2 prefetches
 template <int R, bool CONST, bool PAIR, bool TC = false>
 __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((CONST && !PAIR) ? 4 : 2)) render_kernel(const RenderArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -166,6 +167,11 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
     constexpr int kWarps = kRenderThreads / 32;
     const int n = blockIdx.y, tile = blockIdx.x;
 
+    if (a.lookahead > 0 && tid == 0 && tile < kPfCtas) {    // the first CTAs of frame n ask the TMA unit for frame n + lookahead (frame 0's also for the first frames)
+        if (n == 0)
+            for (int f = 0; f < a.lookahead && f < a.N; ++f) { prefetch_frame_l2(a.p0, a.H, a.W, f, tile, kPfCtas); prefetch_frame_l2(a.p1, a.H, a.W, f, tile, kPfCtas); }
+        if (n + a.lookahead < a.N) { prefetch_frame_l2(a.p0, a.H, a.W, n + a.lookahead, tile, kPfCtas); prefetch_frame_l2(a.p1, a.H, a.W, n + a.lookahead, tile, kPfCtas); }
+    }
     if (!CONST) load_mlp_smem(mlp, a.mlp, tid, kRenderThreads);
     uint32_t tmem_base = 0;
     uint32_t tc_par = 0;                                   // bit t = parity of the phase bar1[t] / bar2[t] complete next (one use per pass)
@@ -684,6 +690,7 @@ extern "C" int r3dp_set_option(const char* key, int value) {
     const std::string k(key);
     if (k == "render") { R3DP_REQUIRE(value == 0 || value == 1, "set_option: render = 0 (stream) | 1 (tile)"); g_render_variant = value; return 0; }
     if (k == "rs_d") { R3DP_REQUIRE(value == 4 || value == 8 || value == 16, "set_option: rs_d = 4 | 8 | 16"); g_rs_chunk_log2 = value == 4 ? 2 : (value == 16 ? 4 : 3); return 0; }
+    if (k == "rs_prefetch") { R3DP_REQUIRE(value >= 0 && value <= 64, "set_option: rs_prefetch = frames of L2 look-ahead (0 = off)"); g_rs_prefetch = value; return 0; }
     R3DP_REQUIRE(false, "set_option: unknown key '%s'", key);
     return 1;
 }
@@ -754,6 +761,7 @@ extern "C" int r3dp_render_ex(const r3dp_render_args_t* g, r3dp_stream_t stream)
     a.S = S; a.S_imp = S_imp; a.box_warp = g->box_warp; a.white_back = g->white_back; a.u_coarse = g->u_coarse; a.u_fine = g->u_fine;
     a.mlp = *g->mlp; a.image = reinterpret_cast<const MlpTcImage*>(wsb + kWsImageOff);
     a.rgb = g->rgb; a.depth = g->depth; a.wsum = g->weights_sum; a.limits = limits; a.valid = g->is_ray_valid; a.ws = ws;
+    a.lookahead = render_lookahead();
     int rc;
     if (render_variant() == 0 && mlp_variant() == 2 && render_stream_fits(a)) {
         mlp_to_tc_kernel<<<4, 256, 0, st>>>(a.mlp, const_cast<MlpTcImage*>(a.image));

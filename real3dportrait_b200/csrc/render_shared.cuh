@@ -68,7 +68,24 @@ struct RenderArgs {
     float* rgb; float* depth; float* wsum;
     const float2* limits; const uint8_t* valid; RenderWs* ws;
     int tiles_per_frame, tile_cols;     // ray tiling of the CTA-per-tile kernel (see ray_of)
+    int lookahead;                      // frames of planes streamed DRAM -> L2 ahead of the gather (0 = off)
 };
+
+// DRAM -> L2 prefetch of one frame's planes: share `part` of `parts` (32 KB chunks, round-robin).  ncu (profiles/r2_render_ab.md): the gather is
+// latency-bound - a warp iteration waits for the slowest of its 48 texel lines, and with cold planes one of them nearly always comes from
+// DRAM.  The TMA unit streams the planes into L2 ahead of the demand loads, which then pay the L2 latency only.
+__device__ __forceinline__ void prefetch_frame_l2(const PlaneSet& ps, int H, int W, int n, int part, int parts) {
+    if (ps.base == nullptr || (ps.frame_stride == 0 && n > 0)) return;
+    const long long span = (2ll * ps.plane_stride + (long long)(ps.depth > 1 ? ps.depth - 1 : 0) * ps.slice_stride + (long long)(H - 1) * ps.row_stride +
+                            (long long)(W - 1) * ps.texel_stride + kC) * 4;          // bytes from the frame's first to its last texel
+    const char* base = reinterpret_cast<const char*>(ps.base + (size_t)n * ps.frame_stride);
+    constexpr long long kChunk = 32768;
+    for (long long off = (long long)part * kChunk; off < span; off += (long long)parts * kChunk) {
+        const long long left = span - off;
+        const uint32_t bytes = (uint32_t)((left < kChunk ? left : kChunk) & ~15ll);
+        if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(bytes) : "memory");
+    }
+}
 
 __device__ __forceinline__ Ray fetch_ray(const float* __restrict__ ray_o, const float* __restrict__ ray_d,
                                          const float* __restrict__ camera, int res, int n, int M, int m) {
@@ -157,7 +174,9 @@ __device__ __forceinline__ unsigned sort_key(float d) {
 
 // render_stream.cu
 extern int g_rs_chunk_log2;      // A/B knob (r3dp_set_option / R3DP_RS_D)
+extern int g_rs_prefetch;        // frames of L2 look-ahead of the streaming kernel (r3dp_set_option / R3DP_RS_PREFETCH)
 bool render_stream_fits(const RenderArgs& a);
 int launch_render_stream(const RenderArgs& a, cudaStream_t st);
+int render_lookahead();
 
 }  // namespace r3dp

@@ -18,6 +18,7 @@
 
 namespace r3dp {
 int g_rs_chunk_log2 = -1;
+int g_rs_prefetch = -1;                                           // frames of L2 look-ahead (0 = off); r3dp_set_option("rs_prefetch") / R3DP_RS_PREFETCH
 namespace rs {
 
 constexpr int kGatherWarps = 8;
@@ -135,8 +136,14 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
         const int rs = a.p0.row_stride, ts = a.p0.texel_stride, ss = a.p0.slice_stride;
         float dmin = __int_as_float(0x7f800000), dmax = __int_as_float(0xff800000);
         uint32_t q = 0;
+        int pf_next = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
             const int n = item / items_per_frame, grp = item - n * items_per_frame;
+            if (gw == 0 && lane == 0 && a.lookahead > 0) {                        // keep `lookahead` frames of planes streaming into L2 ahead of the gather
+                for (; pf_next < a.N && pf_next < n + a.lookahead; ++pf_next) {
+                    prefetch_frame_l2(a.p0, a.H, a.W, pf_next, blockIdx.x, gridDim.x); prefetch_frame_l2(a.p1, a.H, a.W, pf_next, blockIdx.x, gridDim.x);
+                }
+            }
             __syncwarp();
             if (lane < RPW) {
                 const int m = ray_index<LOG2D>(a, grp, gw * RPW + lane);
@@ -353,55 +360,69 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
         if (total_tiles) epi2(total_tiles - 1);
     } else {
         // ====================================================== march ===========================================================
-        // ray_marcher.py:26-57, front to back over the tiles of an item; warp mw owns RM rays, lane = colour channel.
+        // ray_marcher.py:26-57, front to back over the tiles of an item.  Warp mw owns RM = G/4 rays = the 32 tile rows [32 mw, 32 mw + 32).
+        //   weights  lane = tile row = (ray i = lane >> LOG2D, sample j = lane & (D-1)): alpha of the interval that ENDS at this sample, transmittance by a
+        //            segmented product scan over the ray's D lanes times the value carried from the previous tile - one softplus / exp per sample,
+        //            not one per sample and colour channel;
+        //   colours  lane = channel: 32 (ray, sample) pairs per tile, each weight broadcast by a shuffle; acc += w * mid-point colour.
         constexpr int RM = G / 4;
-        const int mw = warp - 4;
+        static_assert(RM * D == 32, "one warp marches 32 tile rows");
+        const int mw = warp - 4, lj = lane & (D - 1), seg_last = lane | (D - 1);
         uint32_t q = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
             const int n = item / items_per_frame, grp = item - n * items_per_frame;
-            float T[RM], acc[RM], wsum[RM], dsum[RM], ps[RM], pc[RM], pd[RM];
+            float Tc = 1.f, last_s = 0.f, last_d = 0.f, wsum = 0.f, dsum = 0.f;        // per tile-row lane; Tc is uniform over the lanes of a ray
+            float acc[RM], pc[RM];                                                    // per channel lane
 #pragma unroll
-            for (int i = 0; i < RM; ++i) { T[i] = 1.f; acc[i] = 0.f; wsum[i] = 0.f; dsum[i] = 0.f; ps[i] = 0.f; pc[i] = 0.f; pd[i] = 0.f; }
+            for (int i = 0; i < RM; ++i) { acc[i] = 0.f; pc[i] = 0.f; }
             for (int t = 0; t < NT; ++t, ++q) {
                 const uint32_t rb = q % NR, dslot = q % ND;
                 tc::mbar_wait(&B.rows_full[rb], (q / NR) & 1u);
-                const float* rbuf = rows + rb * 128 * kRowF;
-                const float* dd = dep + dslot * 128;
-                const int k0 = t << LOG2D;
+                const float* rbuf = rows + (rb * 128 + mw * 32) * kRowF;
+                const int k = (t << LOG2D) + lj;
+                const float s = rbuf[lane * kRowF], d = dep[dslot * 128 + mw * 32 + lane];
+                float ps = __shfl_up_sync(0xffffffffu, s, 1), pd = __shfl_up_sync(0xffffffffu, d, 1);
+                const float cs = __shfl_sync(0xffffffffu, last_s, seg_last), cd = __shfl_sync(0xffffffffu, last_d, seg_last);
+                if (lj == 0) { ps = cs; pd = cd; }
+                float alpha = 0.f, om = 1.f, dmid = 0.f;
+                if (k > 0 && k < a.S) {
+                    const float smid = softplus_fast((ps + s) * 0.5f - 1.0f);         // ray_marcher.py:33
+                    alpha = 1.0f - __expf(-(smid * (d - pd)));
+                    om = 1.0f - alpha + 1e-10f;
+                    dmid = 0.5f * (pd + d);
+                }
+                float incl = om;                                                      // inclusive product over the ray's lanes 0..j
 #pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    const int k = k0 + j;
-                    if (k < a.S) {
+                for (int o = 1; o < D; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, incl, o); if (lj >= o) incl *= v; }
+                float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lj == 0) excl = 1.f;
+                const float w = alpha * (Tc * excl);                                  // ray_marcher.py:41-42
+                Tc *= __shfl_sync(0xffffffffu, incl, seg_last);
+                wsum += w;
+                dsum = fmaf(w, dmid, dsum);
+                last_s = s; last_d = d;
 #pragma unroll
-                        for (int i = 0; i < RM; ++i) {
-                            const int row = ((mw * RM + i) << LOG2D) + j;
-                            const float s = rbuf[row * kRowF], c = rbuf[row * kRowF + 1 + lane], d = dd[row];
-                            if (k > 0) {
-                                const float delta = d - pd[i];
-                                const float smid = softplus_fast((ps[i] + s) * 0.5f - 1.0f);          // ray_marcher.py:33
-                                const float alpha = 1.0f - __expf(-(smid * delta));
-                                const float w = alpha * T[i];
-                                T[i] *= (1.0f - alpha + 1e-10f);
-                                acc[i] = fmaf(w, 0.5f * (pc[i] + c), acc[i]);
-                                wsum[i] += w;
-                                dsum[i] = fmaf(w, 0.5f * (pd[i] + d), dsum[i]);
-                            }
-                            ps[i] = s; pc[i] = c; pd[i] = d;
-                        }
-                    }
+                for (int p = 0; p < 32; ++p) {
+                    const float wp = __shfl_sync(0xffffffffu, w, p);
+                    const float c = rbuf[p * kRowF + 1 + lane];
+                    acc[p >> LOG2D] = fmaf(wp, 0.5f * (pc[p >> LOG2D] + c), acc[p >> LOG2D]);
+                    pc[p >> LOG2D] = c;
                 }
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&B.rows_empty[rb]); mbar_arrive(&B.dep_empty[dslot]); }
             }
 #pragma unroll
+            for (int o = 1; o < D; o <<= 1) { wsum += __shfl_xor_sync(0xffffffffu, wsum, o); dsum += __shfl_xor_sync(0xffffffffu, dsum, o); }
+#pragma unroll
             for (int i = 0; i < RM; ++i) {
                 const int m = ray_index<LOG2D>(a, grp, mw * RM + i);
+                const float wi = __shfl_sync(0xffffffffu, wsum, i << LOG2D), di = __shfl_sync(0xffffffffu, dsum, i << LOG2D);
                 if (m < a.M) {
                     const size_t o = (size_t)n * a.M + m;
                     float v = acc[i];
-                    if (a.white_back) v = v + 1.0f - wsum[i];
+                    if (a.white_back) v = v + 1.0f - wi;
                     a.rgb[o * (kOut - 1) + lane] = v * 2.0f - 1.0f;
-                    if (lane == 0) { a.wsum[o] = wsum[i]; a.depth[o] = dsum[i] / wsum[i]; }      // 0/0 -> NaN, fixed by depth_clamp_kernel
+                    if (lane == 0) { a.wsum[o] = wi; a.depth[o] = di / wi; }           // 0/0 -> NaN, fixed by depth_clamp_kernel
                 }
             }
         }
@@ -443,6 +464,11 @@ bool render_stream_fits(const RenderArgs& a) {
     if (a.p1.base && (a.p1.plane_stride != a.p0.plane_stride || a.p1.row_stride != a.p0.row_stride || a.p1.texel_stride != a.p0.texel_stride ||
                       a.p1.depth != a.p0.depth || a.p1.slice_stride != a.p0.slice_stride)) return false;
     return true;
+}
+
+int render_lookahead() {                           // R3DP_RS_PREFETCH = frames of planes streamed into L2 ahead of the gather (default 2, 0 = off)
+    if (g_rs_prefetch < 0) { const char* e = getenv("R3DP_RS_PREFETCH"); g_rs_prefetch = e ? atoi(e) : 2; if (g_rs_prefetch < 0) g_rs_prefetch = 0; }
+    return g_rs_prefetch;
 }
 
 int launch_render_stream(const RenderArgs& a, cudaStream_t st) {

@@ -90,14 +90,27 @@ __global__ void __launch_bounds__(256, MINB) triplane_sample_kernel(const float*
                                                                     const float* __restrict__ coords, int P, float scale,
                                                                     float* __restrict__ out) {
     const int lane = threadIdx.x & 31, sub = lane >> 3, cq = lane & 7;
-    const long long total4 = ((long long)N * P + 3) / 4;
+    const long long NP = (long long)N * P, total4 = (NP + 3) / 4;
     const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < total4; g += wstride) {
+    if (threadIdx.x == 0) {                       // stream the planes DRAM -> L2 ahead of the gather (at most ~100 MB: what L2 holds)
+        PlaneSet ps; ps.base = planes; ps.frame_stride = 3ll * H * W * kC; ps.plane_stride = H * W * kC; ps.row_stride = W * kC; ps.texel_stride = kC;
+        ps.depth = 1; ps.slice_stride = 0;
+        const long long frame_bytes = ps.frame_stride * 4;
+        for (int f = 0; f < N && (f + 1) * frame_bytes <= (100ll << 20); ++f) prefetch_frame_l2(ps, H, W, f, blockIdx.x, gridDim.x);
+    }
+    long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // the coordinates of the NEXT step are loaded before this step's taps: one exposed memory round trip per step instead of two
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    if (g < total4 && g * 4 + sub < NP) { const float* c = coords + (g * 4 + sub) * 3; nx = __ldg(c); ny = __ldg(c + 1); nz = __ldg(c + 2); }
+    for (; g < total4; g += wstride) {
         const long long pt = g * 4 + sub;
-        if (pt >= (long long)N * P) continue;
+        const float x = nx, y = ny, z = nz;
+        {
+            const long long g2 = g + wstride, pt2 = g2 * 4 + sub;
+            if (g2 < total4 && pt2 < NP) { const float* c = coords + pt2 * 3; nx = __ldg(c); ny = __ldg(c + 1); nz = __ldg(c + 2); }
+        }
+        if (pt >= NP) continue;
         const int n = (int)(pt / P); const int s = (int)(pt - (long long)n * P);
-        const float* c = coords + pt * 3;
-        const float x = __ldg(c), y = __ldg(c + 1), z = __ldg(c + 2);
         PlaneView pv; pv.base = planes + (size_t)n * 3 * H * W * kC; pv.H = H; pv.W = W; pv.scale = scale;
         float4 f0, f1, f2;
         gather3(pv, x, y, z, cq, f0, f1, f2);

@@ -104,8 +104,11 @@ def producer_view(planes: torch.Tensor) -> Optional[PlanesCL]:
     if t.ndim != 5 or t.shape[1] != 3:
         return None
     N, _, Cc, H, W = t.shape
-    if tuple(t.stride()) != (H * W * 3 * Cc, Cc, 1, W * 3 * Cc, 3 * Cc):
+    want = (H * W * 3 * Cc, Cc, 1, W * 3 * Cc, 3 * Cc)
+    if any(s != w for s, w, n in zip(t.stride(), want, t.shape) if n > 1):      # the stride of a size-1 dim (N == 1 sets) is arbitrary
         return None
+    if N == 1:
+        t = t.as_strided(t.shape, want)
     return PlanesCL(t.permute(0, 3, 4, 1, 2), 'hwpc')          # [N,H,W,3,C], contiguous by construction
 
 

@@ -23,6 +23,7 @@ def main():
     ap.add_argument('--pool', type=int, default=32)
     ap.add_argument('--iters', type=int, default=30)
     ap.add_argument('--fine', type=int, default=0)
+    ap.add_argument('--only', default='', help='comma-separated variant names')
     args = ap.parse_args()
     dev = 'cuda'
     B, P = args.frames, args.pool
@@ -65,20 +66,23 @@ def main():
 
     _capi.check(L.r3dp_set_option(b'render', 1))
     ref = run(cl, 0)[0].clone()
-    variants = [('tile', 1, 8, cl), ('stream_d8', 0, 8, cl), ('stream_d4', 0, 4, cl), ('stream_d16', 0, 16, cl), ('stream_d8_hwpc', 0, 8, hw),
-                ('stream_d8_two_sets', 0, 8, None)]
+    variants = [('tile', 1, 8, cl, 2), ('stream_d8', 0, 8, cl, 2), ('stream_d8_nopf', 0, 8, cl, 0), ('stream_d8_pf1', 0, 8, cl, 1), ('stream_d8_pf4', 0, 8, cl, 4),
+                ('stream_d4', 0, 4, cl, 2), ('stream_d16', 0, 16, cl, 2), ('stream_d8_hwpc', 0, 8, hw, 2), ('stream_d8_two_sets', 0, 8, None, 2)]
     if args.fine:
-        variants = [('tile', 1, 8, cl), ('tile_hwpc', 1, 8, hw), ('tile_two_sets', 1, 8, None)]
-    for name, variant, d, pl in variants:
+        variants = [('tile', 1, 8, cl, 2), ('tile_nopf', 1, 8, cl, 0), ('tile_hwpc', 1, 8, hw, 2), ('tile_two_sets', 1, 8, None, 2)]
+    if args.only:
+        variants = [v for v in variants if v[0] in args.only.split(',')]
+    for name, variant, d, pl, pf in variants:
         _capi.check(L.r3dp_set_option(b'render', variant))
         _capi.check(L.r3dp_set_option(b'rs_d', d))
+        _capi.check(L.r3dp_set_option(b'rs_prefetch', pf))
         if pl is None:
             pl = [(h, h) for h in half]                                    # x/2 + x/2: same image, twice the gather
         diff = float((run(pl, 0)[0] - ref).abs().max())
         ms = timed(pl)
         print(json.dumps({'variant': name, 'ms_per_call': round(ms, 4), 'us_per_frame': round(1e3 * ms / B, 2), 'frames': B,
                           'samples_per_ray': 48 + args.fine, 'max_abs_diff_vs_tile': diff}))
-    _capi.check(L.r3dp_set_option(b'render', 0)); _capi.check(L.r3dp_set_option(b'rs_d', 8))
+    _capi.check(L.r3dp_set_option(b'render', 0)); _capi.check(L.r3dp_set_option(b'rs_d', 8)); _capi.check(L.r3dp_set_option(b'rs_prefetch', 2))
 
 
 if __name__ == '__main__':

@@ -78,24 +78,8 @@ def build_debug_timing() -> str:
     return out
 
 
-def build_experiment() -> str:
-    """lib/libr3dp_b200_exp.so: the same library with -DR3DP_RS_EXPERIMENT=1: with R3DP_RS_FAKE=1 the streaming render kernel reads the taps of
-    planes 1 and 2 from a shared-memory window (zero-cost stand-in for TMA-staged plane tiles: the upper bound of any staging scheme; the
-    image is wrong by construction).  Loaded only through R3DP_LIB=<path> by tools/bench_render.py."""
-    build()
-    out = os.path.join(LIB_DIR, 'libr3dp_b200_exp.so')
-    obj = os.path.join(LIB_DIR, 'render_stream_exp.o')
-    subprocess.run([_nvcc(), *NVCC_FLAGS, '-DR3DP_RS_EXPERIMENT=1', '-c', os.path.join(CSRC, 'render_stream.cu'), '-o', obj], check=True)
-    objs = [obj] + [os.path.join(LIB_DIR, os.path.basename(s)[:-3] + '.o') for s in sources() if not s.endswith('render_stream.cu')]
-    subprocess.run([_nvcc(), '-shared', '-o', out, *objs, '-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart_static', '-ldl', '-lrt',
-                    '-lpthread'], check=True)
-    return out
-
-
 if __name__ == '__main__':
-    if '--experiment' in sys.argv:
-        print(build_experiment())
-    elif '--debug-timing' in sys.argv:
+    if '--debug-timing' in sys.argv:
         print(build_debug_timing())
     else:
         print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -140,6 +140,45 @@ __device__ __forceinline__ void sample_desc(const PlaneSet& ps, int H, int W, fl
     }
 }
 
+// tri-plane descriptor in the split layout of the streaming kernel: row[0..2] = the three texel-block offsets, row[4 + 4p .. 7 + 4p] = weights of plane p
+__device__ __forceinline__ void sample_desc_split(const PlaneSet& ps, int H, int W, float gx, float gy, float gz, float* row) {
+    float t[5];
+    tap_desc_s(gx, gy, H, W, 0, ps.row_stride, ps.texel_stride, t);
+    row[0] = t[0]; row[4] = t[1]; row[5] = t[2]; row[6] = t[3]; row[7] = t[4];
+    tap_desc_s(gx, gz, H, W, ps.plane_stride, ps.row_stride, ps.texel_stride, t);
+    row[1] = t[0]; row[8] = t[1]; row[9] = t[2]; row[10] = t[3]; row[11] = t[4];
+    tap_desc_s(gz, gx, H, W, 2 * ps.plane_stride, ps.row_stride, ps.texel_stride, t);
+    row[2] = t[0]; row[12] = t[1]; row[13] = t[2]; row[14] = t[3]; row[15] = t[4];
+}
+
+// the twelve taps of one tri-plane sample with every load issued before the first use: `wrow` points at the 3 x float4 weights in shared memory
+__device__ __forceinline__ void gather12(const float* __restrict__ base, int o0, int o1, int o2, int rs, int ts, int cq, const float4* wrow, float4& acc) {
+    float4 t[12];
+    {
+        const float* b = base + o0 + cq * 4;
+        t[0] = ldg_nc_f4(b); t[1] = ldg_nc_f4(b + ts); t[2] = ldg_nc_f4(b + rs); t[3] = ldg_nc_f4(b + rs + ts);
+        b = base + o1 + cq * 4;
+        t[4] = ldg_nc_f4(b); t[5] = ldg_nc_f4(b + ts); t[6] = ldg_nc_f4(b + rs); t[7] = ldg_nc_f4(b + rs + ts);
+        b = base + o2 + cq * 4;
+        t[8] = ldg_nc_f4(b); t[9] = ldg_nc_f4(b + ts); t[10] = ldg_nc_f4(b + rs); t[11] = ldg_nc_f4(b + rs + ts);
+    }
+    // scheduling fence: every value above is an operand of these (empty) statements, so no use can be hoisted above the last load
+    asm volatile("" : "+f"(t[0].x), "+f"(t[0].y), "+f"(t[0].z), "+f"(t[0].w), "+f"(t[1].x), "+f"(t[1].y), "+f"(t[1].z), "+f"(t[1].w),
+                      "+f"(t[2].x), "+f"(t[2].y), "+f"(t[2].z), "+f"(t[2].w), "+f"(t[3].x), "+f"(t[3].y), "+f"(t[3].z), "+f"(t[3].w));
+    asm volatile("" : "+f"(t[4].x), "+f"(t[4].y), "+f"(t[4].z), "+f"(t[4].w), "+f"(t[5].x), "+f"(t[5].y), "+f"(t[5].z), "+f"(t[5].w),
+                      "+f"(t[6].x), "+f"(t[6].y), "+f"(t[6].z), "+f"(t[6].w), "+f"(t[7].x), "+f"(t[7].y), "+f"(t[7].z), "+f"(t[7].w));
+    asm volatile("" : "+f"(t[8].x), "+f"(t[8].y), "+f"(t[8].z), "+f"(t[8].w), "+f"(t[9].x), "+f"(t[9].y), "+f"(t[9].z), "+f"(t[9].w),
+                      "+f"(t[10].x), "+f"(t[10].y), "+f"(t[10].z), "+f"(t[10].w), "+f"(t[11].x), "+f"(t[11].y), "+f"(t[11].z), "+f"(t[11].w));
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const float4 w = wrow[p];
+        acc.x += t[4 * p].x * w.x + t[4 * p + 1].x * w.y + t[4 * p + 2].x * w.z + t[4 * p + 3].x * w.w;
+        acc.y += t[4 * p].y * w.x + t[4 * p + 1].y * w.y + t[4 * p + 2].y * w.z + t[4 * p + 3].y * w.w;
+        acc.z += t[4 * p].z * w.x + t[4 * p + 1].z * w.y + t[4 * p + 2].z * w.z + t[4 * p + 3].z * w.w;
+        acc.w += t[4 * p].w * w.x + t[4 * p + 1].w * w.y + t[4 * p + 2].w * w.z + t[4 * p + 3].w * w.w;
+    }
+}
+
 // gather of one sample by an 8-lane group (lane cq owns channels 4cq..4cq+3): SUM over the three planes of the (bi|tri)linear taps
 // described by `d` (15 or 27 floats, already in registers), read from `base`.  GRID is a compile-time flag.
 template <bool GRID>

@@ -22,9 +22,14 @@ int g_rs_prefetch = -1;                                           // frames of L
 namespace rs {
 
 constexpr int kGatherWarps = 8;
-constexpr int kMmaWarp = 8;                                     // warps 0-3 decode (TMEM lane quadrant = warp), 4-7 march, 8 MMA, 9-16 gather
-constexpr int kFirstGather = 9;
-constexpr int kThreads = (kFirstGather + kGatherWarps) * 32;    // 544
+// warps 0-3 decode (TMEM lane quadrant = warp), 4-7 march, 8-15 gather, 16 MMA: every role is a whole warpgroup (4 aligned warps), so the
+// register file can be re-split with setmaxnreg - the march warps give up registers, the gather warps take them to keep all twelve
+// 16-byte loads of a sample in flight (at the launch-wide 96 ptxas split them into four dependent groups)
+constexpr int kFirstGather = 8;
+constexpr int kMmaWarp = kFirstGather + kGatherWarps;
+constexpr int kThreads = (kMmaWarp + 1) * 32;                   // 544
+#define R3DP_RS_REGS_MARCH "48"
+#define R3DP_RS_REGS_GATHER "120"
 constexpr int NS = 3;                                           // A1 stages
 constexpr int NR = 2;                                           // decoded-row buffers
 constexpr int ND = 8;                                           // depth ring slots
@@ -39,12 +44,7 @@ constexpr int kOffDsc = kOffDep + ND * 128 * 4;
 constexpr int kDscF = 32;                                       // floats per sample descriptor row (15 used by tri-planes, 27 by tri-grids)
 constexpr int kOffRay = kOffDsc + kGatherWarps * kSPW * kDscF * 4;
 constexpr int kOffBar = kOffRay + kGatherWarps * 8 * 8 * 4;
-#ifndef R3DP_RS_EXPERIMENT
-#define R3DP_RS_EXPERIMENT 0
-#endif
-constexpr int kOffFake = kOffBar + 512;                         // experiment builds only: 16 KB stand-in for TMA-staged plane tiles
-constexpr int kSmem = kOffFake + (R3DP_RS_EXPERIMENT ? 16384 + 512 : 0) + 1024;     // + alignment slack
-__device__ int g_rs_fake = 0;
+constexpr int kSmem = kOffBar + 512 + 1024;                     // + alignment slack
 
 struct Bars {
     uint64_t a1_full[NS], a1_empty[NS];
@@ -125,8 +125,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
     tc::tc_fence_after();
     const uint32_t tmem_base = B.tmem_slot;
 
-    if (warp >= kFirstGather) {
+    if (warp >= kFirstGather && warp < kMmaWarp) {
         // ===================================================== gather ===========================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " R3DP_RS_REGS_GATHER ";");
         constexpr int RPW = kSPW >> LOG2D;                                      // rays per gather warp
         static_assert(RPW >= 1, "D must not exceed the samples of one gather warp");
         const int gw = warp - kFirstGather, sub = lane >> 3, cq = lane & 7;
@@ -190,7 +191,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
                         const float x = __fadd_rn(rf[0], __fmul_rn(d, rf[3]));
                         const float y = __fadd_rn(rf[1], __fmul_rn(d, rf[4]));
                         const float z = __fadd_rn(rf[2], __fmul_rn(d, rf[5]));
-                        sample_desc(a.p0, a.H, a.W, scale * x, scale * y, scale * z, row);
+                        if (GRID) sample_desc(a.p0, a.H, a.W, scale * x, scale * y, scale * z, row);
+                        else sample_desc_split(a.p0, a.H, a.W, scale * x, scale * y, scale * z, row);
                     } else {
 #pragma unroll
                         for (int e = 0; e < (GRID ? 27 : 15); ++e) row[e] = 0.f;                   // offset 0, weights 0: a harmless tap
@@ -204,35 +206,21 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
                 for (int it = 0; it < kSPW / 4; ++it) {
                     const int s = it * 4 + sub;
                     const float4* rw = reinterpret_cast<const float4*>(dsc + s * kDscF);
-                    float dscv[GRID ? 28 : 16];
-#pragma unroll
-                    for (int e = 0; e < (GRID ? 7 : 4); ++e) { const float4 qv = rw[e]; dscv[4 * e] = qv.x; dscv[4 * e + 1] = qv.y; dscv[4 * e + 2] = qv.z; dscv[4 * e + 3] = qv.w; }
                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#if R3DP_RS_EXPERIMENT
-                    // UPPER-BOUND EXPERIMENT (never in the product build; results are wrong by construction): the taps of planes 1 and 2 - the
-                    // planes whose footprint the rays of an item share, i.e. what a TMA box would stage - are read from a 16 KB shared-memory
-                    // window at zero staging cost.  No staging scheme (cp.async.bulk.tensor boxes, multicast, ...) can beat this variant.
-                    if (!GRID && g_rs_fake) {
-                        const float* fake = reinterpret_cast<const float*>(smem + kOffFake);
+                    if (GRID) {
+                        float dscv[28];
 #pragma unroll
-                        for (int p = 0; p < 3; ++p) {
-                            const int off = __float_as_int(dscv[5 * p]);
-                            const float* b = p == 0 ? base0 + off + cq * 4 : fake + ((off >> 5) & 63) * 32 + cq * 4;
-                            const int tsx = p == 0 ? ts : 32, rsx = p == 0 ? rs : 64;
-                            float4 t00, t10, t01, t11;
-                            if (p == 0) { t00 = ldg_nc_f4(b); t10 = ldg_nc_f4(b + tsx); t01 = ldg_nc_f4(b + rsx); t11 = ldg_nc_f4(b + rsx + tsx); }
-                            else { t00 = *reinterpret_cast<const float4*>(b); t10 = *reinterpret_cast<const float4*>(b + tsx);
-                                   t01 = *reinterpret_cast<const float4*>(b + rsx); t11 = *reinterpret_cast<const float4*>(b + rsx + tsx); }
-                            const float w00 = dscv[5 * p + 1], w10 = dscv[5 * p + 2], w01 = dscv[5 * p + 3], w11 = dscv[5 * p + 4];
-                            acc.x += t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
-                            acc.y += t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
-                            acc.z += t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
-                            acc.w += t00.w * w00 + t10.w * w10 + t01.w * w01 + t11.w * w11;
-                        }
-                    } else
-#endif
-                    gather_desc<GRID>(base0, dscv, rs, ts, ss, cq, acc);
-                    if (base1 != nullptr) gather_desc<GRID>(base1, dscv, rs, ts, ss, cq, acc);     // second plane set, same points (sampling is linear)
+                        for (int e = 0; e < 7; ++e) { const float4 qv = rw[e]; dscv[4 * e] = qv.x; dscv[4 * e + 1] = qv.y; dscv[4 * e + 2] = qv.z; dscv[4 * e + 3] = qv.w; }
+                        gather_desc<true>(base0, dscv, rs, ts, ss, cq, acc);
+                        if (base1 != nullptr) gather_desc<true>(base1, dscv, rs, ts, ss, cq, acc);
+                    } else {
+                        // row = [off0 off1 off2 - | 4 weights x 3 planes]: the offsets first, ALL twelve LDG.128 of the sample issued back to back
+                        // (48 registers in flight per lane), the weights fetched from smem under their latency, only then the FMAs.  ncu on the
+                        // previous form: ptxas interleaved the loads with their uses in 4 groups = 4 exposed L2 round trips per step.
+                        const float4 offs = rw[0];
+                        gather12(base0, __float_as_int(offs.x), __float_as_int(offs.y), __float_as_int(offs.z), rs, ts, cq, rw + 1, acc);
+                        if (base1 != nullptr) gather12(base1, __float_as_int(offs.x), __float_as_int(offs.y), __float_as_int(offs.z), rs, ts, cq, rw + 1, acc);
+                    }
                     // mean over the planes as fp16 hi + lo halves into the swizzled A1 stage: lane cq owns K = [4cq, 4cq+4) of both halves
                     const float third = 1.0f / 3.0f;
                     const float f0 = acc.x * third, f1 = acc.y * third, f2 = acc.z * third, f3 = acc.w * third;
@@ -365,6 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
         //            segmented product scan over the ray's D lanes times the value carried from the previous tile - one softplus / exp per sample,
         //            not one per sample and colour channel;
         //   colours  lane = channel: 32 (ray, sample) pairs per tile, each weight broadcast by a shuffle; acc += w * mid-point colour.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " R3DP_RS_REGS_MARCH ";");
         constexpr int RM = G / 4;
         static_assert(RM * D == 32, "one warp marches 32 tile rows");
         const int mw = warp - 4, lj = lane & (D - 1), seg_last = lane | (D - 1);
@@ -445,9 +434,6 @@ static int launch(RenderArgs a, cudaStream_t st) {
     constexpr int G = 128 >> LOG2D;
     const bool image = a.res > 0 && a.res * a.res == a.M && (a.res % G) == 0;
     a.tile_cols = image ? a.res : 0;
-#if R3DP_RS_EXPERIMENT
-    { const char* e = getenv("R3DP_RS_FAKE"); const int v = (e && e[0] == '1') ? 1 : 0; R3DP_CUDA(cudaMemcpyToSymbolAsync(g_rs_fake, &v, sizeof(int), 0, cudaMemcpyHostToDevice, st)); }
-#endif
     const int items_per_frame = (a.M + G - 1) / G;
     const int total = a.N * items_per_frame;
     R3DP_CUDA(cudaFuncSetAttribute(render_stream_kernel<LOG2D, GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));

@@ -48,8 +48,13 @@ int r3dp_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Running total of CUDA kernels this library has launched in the process (bench.py's `gpu_launches`). */
 unsigned long long r3dp_launch_count(void);
 /* A/B switches for profiling runs (same meaning as the R3DP_* environment variables, settable at run time):
- *   "render": 0 = streaming kernel for single-pass renders (default), 1 = CTA-per-ray-tile kernel;  "rs_d": 4 | 8 | 16 samples per ray and tile */
+ *   "render": 0 = streaming kernel for single-pass renders (default), 1 = CTA-per-ray-tile kernel;  "rs_d": 4 | 8 | 16 samples per ray and tile;
+ *   "rs_prefetch": frames of planes the fused render streams DRAM -> L2 ahead of its gather (default 2, 0 = off) */
 int r3dp_set_option(const char* key, int value);
+/* Frame exchange of a sharded clip (inference/real3d_infer.py:515-521 collects the frames of a clip on one device): copy-engine peer copy of
+ * `bytes` from `src` on device `src_device` to `dst` on device `dst_device` (e.g. a CUDA-IPC mapping of rank 0's clip buffer), enqueued on
+ * `stream` (a stream of the CALLING device); no SM is used and nothing is synchronised. */
+int r3dp_peer_copy(void* dst, int dst_device, const void* src, int src_device, size_t bytes, r3dp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------- rays ---
  * RaySampler.forward (modules/eg3ds/volumetric_rendering/ray_sampler.py:24-63).

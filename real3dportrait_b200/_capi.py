@@ -48,6 +48,7 @@ _SIGNATURES = {
     'r3dp_device_info': (_I, [C.POINTER(_I)] * 3),
     'r3dp_launch_count': (C.c_ulonglong, []),
     'r3dp_set_option': (_I, [C.c_char_p, _I]),
+    'r3dp_peer_copy': (_I, [_P, _I, _P, _I, _Z, _P]),
     'r3dp_gen_rays': (_I, [_P, _P, _I, _I, _P, _P, _P]),
     'r3dp_planes_to_channels_last': (_I, [_P, _I, _I, _I, _I, _P, _P]),
     'r3dp_grids_to_channels_last': (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),

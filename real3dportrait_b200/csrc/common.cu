@@ -49,3 +49,18 @@ extern "C" int r3dp_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 extern "C" unsigned long long r3dp_launch_count(void) { return __atomic_load_n(&r3dp::g_launches, __ATOMIC_RELAXED); }
+
+extern "C" int r3dp_peer_copy(void* dst, int dst_device, const void* src, int src_device, size_t bytes, r3dp_stream_t stream) {
+    R3DP_REQUIRE(dst && src && dst_device >= 0 && src_device >= 0, "peer_copy: bad arguments");
+    if (bytes == 0) return 0;
+    if (dst_device == src_device) { R3DP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, r3dp::as_stream(stream))); return 0; }
+    int can = 0;
+    R3DP_CUDA(cudaDeviceCanAccessPeer(&can, src_device, dst_device));
+    if (can) {                                       // direct NVLink path; without it the driver stages the copy through the host
+        cudaError_t e = cudaDeviceEnablePeerAccess(dst_device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { R3DP_CUDA(e); }
+        (void)cudaGetLastError();
+    }
+    R3DP_CUDA(cudaMemcpyPeerAsync(dst, dst_device, src, src_device, bytes, r3dp::as_stream(stream)));
+    return 0;
+}

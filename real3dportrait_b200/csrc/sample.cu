@@ -82,42 +82,73 @@ __global__ void __launch_bounds__(256, 3) trigrid_sample_kernel(const float* __r
 }
 
 // ---- sample_from_planes ---------------------------------------------------------------------------------------------
-// Persistent grid-stride kernel: a warp handles 4 points per step (8 lanes x float4 = one 128 B texel line per tap),
-// 12 independent 16 B loads in flight per lane, outputs written with streaming stores (never re-read here).
-// MINB = resident CTAs per SM the register allocation targets; the grid is exactly MINB x #SM CTAs (one wave, no tail).
+// Persistent kernel, a warp owns chunks of 32 CONSECUTIVE points (chunk-cyclic over the grid; consecutive points are consecutive depths of a
+// ray in the renderer's use, so the (x,y)-plane taps of a chunk hit L1).  Per chunk: lane = point computes the three tap descriptors ONCE
+// (zero padding folded into the weights: no bounds checks, no predicated loads) into a 2 KB shared-memory block; then 8 steps of 4 points,
+// 8 lanes x float4 = one 128-byte texel line per tap, ALL twelve 16-byte loads of a point issued before the first use, streaming stores
+// (the output is never re-read here).  The coordinates of the next chunk are requested before this chunk's taps.
+// ncu history (profiles/r2_sample_op.md): descriptors recomputed by all 8 lanes of a point + loads split into dependent groups at 64
+// registers -> 59 % of the HBM peak with 60 % issue-active; MINB = resident CTAs per SM the register allocation targets.
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB) triplane_sample_kernel(const float* __restrict__ planes, int N, int H, int W,
                                                                     const float* __restrict__ coords, int P, float scale,
                                                                     float* __restrict__ out) {
-    const int lane = threadIdx.x & 31, sub = lane >> 3, cq = lane & 7;
-    const long long NP = (long long)N * P, total4 = (NP + 3) / 4;
-    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-    if (threadIdx.x == 0) {                       // stream the planes DRAM -> L2 ahead of the gather (at most ~100 MB: what L2 holds)
-        PlaneSet ps; ps.base = planes; ps.frame_stride = 3ll * H * W * kC; ps.plane_stride = H * W * kC; ps.row_stride = W * kC; ps.texel_stride = kC;
-        ps.depth = 1; ps.slice_stride = 0;
-        const long long frame_bytes = ps.frame_stride * 4;
-        for (int f = 0; f < N && (f + 1) * frame_bytes <= (100ll << 20); ++f) prefetch_frame_l2(ps, H, W, f, blockIdx.x, gridDim.x);
-    }
-    long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    // the coordinates of the NEXT step are loaded before this step's taps: one exposed memory round trip per step instead of two
+    __shared__ __align__(16) float s_desc[8][32][16];           // per warp: [point][off0 off1 off2 frame | 4 weights x 3 planes]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane >> 3, cq = lane & 7;
+    const long long NP = (long long)N * P, n_chunks = (NP + 31) / 32;
+    const long long wstride = (long long)gridDim.x * 8;
+    long long chunk = (long long)blockIdx.x * 8 + warp;
+    float (*row)[16] = s_desc[warp];
+    const size_t fstride = (size_t)3 * H * W * kC;
+    const int rs = W * kC;
     float nx = 0.f, ny = 0.f, nz = 0.f;
-    if (g < total4 && g * 4 + sub < NP) { const float* c = coords + (g * 4 + sub) * 3; nx = __ldg(c); ny = __ldg(c + 1); nz = __ldg(c + 2); }
-    for (; g < total4; g += wstride) {
-        const long long pt = g * 4 + sub;
-        const float x = nx, y = ny, z = nz;
+    if (chunk < n_chunks && chunk * 32 + lane < NP) { const float* c = coords + (chunk * 32 + lane) * 3; nx = __ldg(c); ny = __ldg(c + 1); nz = __ldg(c + 2); }
+    for (; chunk < n_chunks; chunk += wstride) {
+        const long long pt0 = chunk * 32;
+        const float gx = scale * nx, gy = scale * ny, gz = scale * nz;
         {
-            const long long g2 = g + wstride, pt2 = g2 * 4 + sub;
-            if (g2 < total4 && pt2 < NP) { const float* c = coords + pt2 * 3; nx = __ldg(c); ny = __ldg(c + 1); nz = __ldg(c + 2); }
+            const long long pt2 = (chunk + wstride) * 32 + lane;
+            if (chunk + wstride < n_chunks && pt2 < NP) { const float* c = coords + pt2 * 3; nx = __ldg(c); ny = __ldg(c + 1); nz = __ldg(c + 2); }
         }
-        if (pt >= NP) continue;
-        const int n = (int)(pt / P); const int s = (int)(pt - (long long)n * P);
-        PlaneView pv; pv.base = planes + (size_t)n * 3 * H * W * kC; pv.H = H; pv.W = W; pv.scale = scale;
-        float4 f0, f1, f2;
-        gather3(pv, x, y, z, cq, f0, f1, f2);
-        float* o = out + (((size_t)n * 3) * P + s) * kC + cq * 4;
-        stg_cs_f4(o, f0);
-        stg_cs_f4(o + (size_t)P * kC, f1);
-        stg_cs_f4(o + 2 * (size_t)P * kC, f2);
+        {   // plane 0 <- (x,y), plane 1 <- (x,z), plane 2 <- (z,x)   (generate_planes + project_onto_planes, renderer.py:30-63)
+            float t[5];
+            float* r = row[lane];
+            tap_desc(gx, gy, H, W, 0, t); r[0] = t[0]; r[4] = t[1]; r[5] = t[2]; r[6] = t[3]; r[7] = t[4];
+            tap_desc(gx, gz, H, W, 1, t); r[1] = t[0]; r[8] = t[1]; r[9] = t[2]; r[10] = t[3]; r[11] = t[4];
+            tap_desc(gz, gx, H, W, 2, t); r[2] = t[0]; r[12] = t[1]; r[13] = t[2]; r[14] = t[3]; r[15] = t[4];
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int it = 0; it < 8; ++it) {
+            const int sp = it * 4 + sub;
+            const long long pt = pt0 + sp;
+            if (pt >= NP) break;                                                  // only the last chunk; whole 8-lane groups leave together
+            const int n = (int)(pt / P); const int s = (int)(pt - (long long)n * P);
+            const float4* rw = reinterpret_cast<const float4*>(row[sp]);
+            const float4 offs = rw[0];
+            const float* base = planes + (size_t)n * fstride + cq * 4;
+            float4 t[12];
+            {
+                const float* b = base + __float_as_int(offs.x);
+                t[0] = ldg_nc_f4(b); t[1] = ldg_nc_f4(b + kC); t[2] = ldg_nc_f4(b + rs); t[3] = ldg_nc_f4(b + rs + kC);
+                b = base + __float_as_int(offs.y);
+                t[4] = ldg_nc_f4(b); t[5] = ldg_nc_f4(b + kC); t[6] = ldg_nc_f4(b + rs); t[7] = ldg_nc_f4(b + rs + kC);
+                b = base + __float_as_int(offs.z);
+                t[8] = ldg_nc_f4(b); t[9] = ldg_nc_f4(b + kC); t[10] = ldg_nc_f4(b + rs); t[11] = ldg_nc_f4(b + rs + kC);
+            }
+            float* o = out + (((size_t)n * 3) * P + s) * kC + cq * 4;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                const float4 w = rw[1 + p];
+                float4 r;
+                r.x = t[4 * p].x * w.x + t[4 * p + 1].x * w.y + t[4 * p + 2].x * w.z + t[4 * p + 3].x * w.w;
+                r.y = t[4 * p].y * w.x + t[4 * p + 1].y * w.y + t[4 * p + 2].y * w.z + t[4 * p + 3].y * w.w;
+                r.z = t[4 * p].z * w.x + t[4 * p + 1].z * w.y + t[4 * p + 2].z * w.z + t[4 * p + 3].z * w.w;
+                r.w = t[4 * p].w * w.x + t[4 * p + 1].w * w.y + t[4 * p + 2].w * w.z + t[4 * p + 3].w * w.w;
+                stg_cs_f4(o + (size_t)p * P * kC, r);
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -233,20 +264,18 @@ extern "C" int r3dp_triplane_sample(const float* planes_cl, int N, int C, int H,
     R3DP_REQUIRE(planes_cl && coords && out, "triplane_sample: null pointer");
     R3DP_REQUIRE(C == kC, "triplane_sample: C must be %d (got %d)", kC, C);
     R3DP_REQUIRE(N > 0 && P > 0 && H > 0 && W > 0 && box_warp > 0.f, "triplane_sample: bad shape");
-    const long long warps = ((long long)N * P + 3) / 4;
-    long long need = (warps + 7) / 8;
-    static int minb = -1;                          // R3DP_SAMPLE_MINB = 4 | 5 | 6 | 8 (register/occupancy trade-off, tuned on B200)
-    if (minb < 0) { const char* e = getenv("R3DP_SAMPLE_MINB"); minb = e ? atoi(e) : 4; if (minb != 4 && minb != 5 && minb != 6 && minb != 8) minb = 4; }
+    const long long chunks = ((long long)N * P + 31) / 32;          // one warp-chunk = 32 consecutive points
+    long long need = (chunks + 7) / 8;
+    static int minb = -1;                          // R3DP_SAMPLE_MINB = 2 | 3 | 4 (register/occupancy trade-off: A/B knob)
+    if (minb < 0) { const char* e = getenv("R3DP_SAMPLE_MINB"); minb = e ? atoi(e) : 3; if (minb < 2 || minb > 4) minb = 3; }
     const long long cap = (long long)sm_count() * minb;
     const unsigned blocks = (unsigned)(need < cap ? need : cap);
     const float sc = 2.0f / box_warp;
     cudaStream_t st = as_stream(stream);
     switch (minb) {
+        case 2: triplane_sample_kernel<2><<<blocks, 256, 0, st>>>(planes_cl, N, H, W, coords, P, sc, out); break;
         case 4: triplane_sample_kernel<4><<<blocks, 256, 0, st>>>(planes_cl, N, H, W, coords, P, sc, out); break;
-        case 5: triplane_sample_kernel<5><<<blocks, 256, 0, st>>>(planes_cl, N, H, W, coords, P, sc, out); break;
-        case 8: triplane_sample_kernel<8><<<blocks, 256, 0, st>>>(planes_cl, N, H, W, coords, P, sc, out); break;
-        case 6: triplane_sample_kernel<6><<<blocks, 256, 0, st>>>(planes_cl, N, H, W, coords, P, sc, out); break;
-        default: triplane_sample_kernel<4><<<blocks, 256, 0, st>>>(planes_cl, N, H, W, coords, P, sc, out); break;
+        default: triplane_sample_kernel<3><<<blocks, 256, 0, st>>>(planes_cl, N, H, W, coords, P, sc, out); break;
     }
     R3DP_LAUNCH_CHECK();
     return 0;

@@ -316,7 +316,11 @@ class FrameEngine:
         p['ready'][k].record(cur)
         with torch.cuda.stream(p['stream']):
             p['stream'].wait_event(p['ready'][k])
-            dst.copy_(p['stage'][k][:n], non_blocking=True)             # peer copy over NVLink by the copy engine (no SMs)
+            src = p['stage'][k][:n]
+            # peer copy over NVLink by the copy engine (no SMs), enqueued directly: torch's cross-device copy_ brackets every copy with
+            # event record/wait pairs on BOTH devices' current streams (measured: 1.3 ms/step of host-side stalls at 2 GPUs)
+            capi.check(capi.lib().r3dp_peer_copy(dst.data_ptr(), dst.device.index, src.data_ptr(), src.device.index,
+                                                 src.numel() * src.element_size(), capi.stream()))
             p['done'][k].record(p['stream'])
 
     def close_clip(self) -> Optional[torch.Tensor]:

@@ -278,7 +278,7 @@ def main():
     ap.add_argument('--batch', type=int, default=4)
     ap.add_argument('--pool', type=int, default=32, help='distinct resident frames per GPU (32 x 25 MB = 805 MB > L2)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--sr-mode', default=None, choices=[None, 'fp32', 'tc'])
+    ap.add_argument('--sr-mode', default=None, choices=[None, 'fp32', 'tc', 'tc_exact'])
     ap.add_argument('--planes', default='cl', choices=['cl', 'nchw'],
                     help="resident tri-plane layout: 'cl' = channels-last as the producer's conv emits them (no repack in the step); "
                          "'nchw' = the reference's [N,3,32,256,256] (repacked every step)")
@@ -308,7 +308,7 @@ def main():
     _capi.check(L.r3dp_device_info(None, None, None))
 
     sr_mode = args.sr_mode or engine.default_sr_mode()
-    u8 = (world > 1) and not args.frames_f32 and sr_mode == 'tc'
+    u8 = (world > 1) and not args.frames_f32 and sr_mode in ('tc', 'tc_exact')
     exchange = 'none' if world == 1 else ('p2p' if args.exchange in ('auto', 'p2p') else 'allgather')
     exchange_note = ''
 
@@ -518,7 +518,7 @@ def main():
     line = {
         'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32 render (decoder GEMMs: split-fp16 operands on tcgen05, f32 accumulate, f32-grade results); SR ' + ('f16 operands / f32 accumulate (tcgen05)' if sr_mode == 'tc' else 'f32'),
+        'vs_baseline': None, 'dtype': 'f32 render (decoder GEMMs: split-fp16 operands on tcgen05, f32 accumulate, f32-grade results); SR ' + {'tc': 'f16 operands / f32 accumulate (tcgen05)', 'tc_exact': 'split-f16 operands (3 products) / f32 accumulate (tcgen05), f32-grade results'}.get(sr_mode, 'f32'),
         'data': 'synthetic',
         'config': {'workload': workload_text(args, world), 'frames_per_step_per_gpu': B, 'samples_per_ray': 48, 'render_res': 64, 'out_res': 512,
                    'parallelism': f'frames sharded over {world} GPU(s); no data-path collective, one frame exchange per step',

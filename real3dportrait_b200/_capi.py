@@ -68,6 +68,15 @@ _SIGNATURES = {
     'r3dp_sr_layer_fp32': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'r3dp_sr_torgb_fp32': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     'r3dp_sr_tc_pack_weights': (_I, [_P, _I, _I, _I, _P, _P]),
+    'r3dp_sr_tcx_pack_weights': (_I, [_P, _I, _I, _I, _P, _P]),
+    'r3dp_sr_tcx_pack_weights_up_composed': (_I, [_P, _I, _I, _I, _P, _P]),
+    'r3dp_sr_tcx_input': (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    'r3dp_sr_tcx_input_nhwc': (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    'r3dp_sr_tcx_scratch_bytes': (_Z, [_I, _I, _I, _I]),
+    'r3dp_sr_tcx_layer': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    'r3dp_sr_tcx_layer_up_composed': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    'r3dp_sr_tcx_layer_torgb': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    'r3dp_sr_tcx_last_layer': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     'r3dp_sr_tc_input': (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     'r3dp_sr_tc_scratch_bytes': (_Z, [_I, _I, _I, _I]),
     'r3dp_sr_tc_layer': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),

@@ -27,6 +27,7 @@ namespace r3dp {
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16;
+constexpr float kSplitWeightScale = 1024.0f;       // split-fp16 weights are stored x 2^10: their lo halves (|w| 2^-11) stay normal fp16 numbers
 
 // kind::f16 instruction descriptor: D=f32 (bit 4), A=B=f16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -51,6 +52,7 @@ struct ConvArgs {
     const float* img_prev;
     float* img_out;
     int out_clamp; uint8_t* img_out_u8;
+    int split;               // fp32-grade [hi | lo] operands (see Conv2Args)
 };
 
 // =====================================================================================================================
@@ -92,6 +94,9 @@ struct Conv2Args {
     const __half* residual;         // non-null: added to the activated output before the store (ResBlock2d of large_sr)
     int out_clamp;                  // final image clamped to [-1, 1] (the caller-side imgs.clamp(-1,1), inference/real3d_infer.py:515)
     uint8_t* img_out_u8;            // non-null: final image as uint8 HWC frames [N][H][W][3] = int((clamp(x)+1)/2*255) (real3d_infer.py:519) instead of fp32 NCHW
+    int split;                      // fp32-grade operands: activations [hi | lo] (2 x Cin_pad channels), weights [hi | lo]; K loop = hi*hi + lo*hi + hi*lo
+    int lo_off;                     // split: channel offset of the lo half in the OUTPUT tensor (= logical output channels); out_C is the physical pixel stride
+    float acc_scale;                // accumulator scale applied before the bias (split weights are stored x 2^10 so their lo halves stay normal fp16)
     unsigned long long* debug;      // R3DP_TC_DEBUG_TIMING builds: [acc wait, strip wait, tap wait, issue, total, #CTAs] clock sums of the MMA warp
 };
 
@@ -288,8 +293,11 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                 const Taps2& tp = a.ph[ph].taps;
                 const int DY = tp.ngroups;
                 const int wn = a.w_shared ? 0 : n;
+                const int K3 = a.split ? 3 * a.k_chunks : a.k_chunks;             // split: [x_hi w_hi | x_lo w_hi | x_hi w_lo] over the channel chunks
                 for (int nblk = 0; nblk < a.n_blocks; ++nblk)
-                    for (int kc = 0; kc < a.k_chunks; ++kc)
+                    for (int kq = 0; kq < K3; ++kq) {
+                        const int kc = kq < 2 * a.k_chunks ? kq : kq - 2 * a.k_chunks;    // activation chunk: hi, lo (at k_chunks + c), hi again
+                        const int kb = kq < a.k_chunks ? kq : kq - a.k_chunks;            // weight chunk: hi, hi, lo (at k_chunks + c)
                         for (int d = 0; d < DY; ++d) {
                             const int s_lo = d == 0 ? 0 : R - 1 + d, s_hi = R - 1 + d;
                             for (int s = s_lo; s <= s_hi; ++s, ++aq) {
@@ -302,9 +310,10 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                                 const int slot = bq % C::NB;
                                 mbar_wait(&b_empty[slot], ((bq / C::NB) & 1) ^ 1);
                                 if (leader) mbar_expect_tx(&b_full[slot], 2 * B3_BYTES);
-                                tma_load_4d_2sm(b_ring + slot * B3_BYTES, &tmB, &b_full[slot], kc * BK, nblk * BN + (int)cta_rank * (BN / 2), tp.widx[t], wn);
+                                tma_load_4d_2sm(b_ring + slot * B3_BYTES, &tmB, &b_full[slot], kb * BK, nblk * BN + (int)cta_rank * (BN / 2), tp.widx[t], wn);
                             }
                         }
+                    }
             }
         }
     } else if (warp == 1) {
@@ -330,7 +339,8 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                 tc_fence_after();
                 DT_END(t_acc);
                 const uint32_t acc0 = tmem_base + buf * (R * BN);
-                for (int kc = 0; kc < a.k_chunks; ++kc) {
+                const int K3 = a.split ? 3 * a.k_chunks : a.k_chunks;
+                for (int kc = 0; kc < K3; ++kc) {
                     const uint32_t a_base = aq;                               // sequence number of strip 0 of this chunk
                     for (int d = 0; d < DY; ++d) {
                         const int s_lo = d == 0 ? 0 : R - 1 + d, s_hi = R - 1 + d;
@@ -477,7 +487,6 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                     const bool row_ok = (row < P.rows) && (Y < a.out_H);
                     const bool in_img = row_ok && (X < a.out_W);
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (R * BN) + j * BN;
-                    __half* dst_row = a.out + ((size_t)n * a.out_H + Y) * a.out_W * a.out_C + nblk * BN;
 #pragma unroll 1
                     for (int c0 = cg * (BN / 2); c0 < (cg + 1) * (BN / 2); c0 += 32) {
                         uint32_t r[32];
@@ -486,16 +495,17 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                         ET_END(e_ld);
                         ET_BEGIN();
                         float2 f2[16];
+                        const float2 sc2 = make_float2(a.acc_scale, a.acc_scale);
                         if (a.mode == kStoreRaw) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) f2[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                            for (int i = 0; i < 16; ++i) f2[i] = mul2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2);
                         } else {
                             // bias, leaky relu as max(v, v*slope) (slope <= 1), gain: bias_act lrelu*sqrt2 | nn.LeakyReLU | linear
                             const float2* b2 = reinterpret_cast<const float2*>(s_bias + nblk * BN + c0);
                             const float2 sl2 = make_float2(a.act_slope, a.act_slope), g2 = make_float2(a.act_gain, a.act_gain);
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
-                                const float2 v = add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), b2[i]);
+                                const float2 v = fma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, b2[i]);
                                 const float2 t = mul2(v, sl2);
                                 f2[i] = mul2(make_float2(fmaxf(v.x, t.x), fmaxf(v.y, t.y)), g2);
                             }
@@ -504,28 +514,42 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                         if (a.mode != kToRgbFinal) {
                             // NHWC fp16 store through smem: the thread owns a pixel (32 channels = 64 B); written directly, every
                             // STG.128 of the warp would touch 32 different lines.  Staged, 4 lanes write one pixel's 64 contiguous bytes.
+                            // Split mode: a second pass stores the fp16 remainders (v - fp16(v)) lo_off channels further.
                             uint4* st = s_stage + (warp - 2) * 128;
                             const int sw = (lane >> 1) & 3;
+                            const int passes = a.split ? 2 : 1;
+                            for (int pass = 0; pass < passes; ++pass) {
+                                if (pass == 0) {
 #pragma unroll
-                            for (int v = 0; v < 4; ++v) st[lane * 4 + (v ^ sw)] = pack_half8(f + 8 * v);
-                            __syncwarp();
+                                    for (int v = 0; v < 4; ++v) st[lane * 4 + (v ^ sw)] = pack_half8(f + 8 * v);
+                                } else {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int p = i * 8 + (lane >> 2), cch = lane & 3;
-                                uint4 pk = st[p * 4 + (cch ^ ((p >> 1) & 3))];
-                                const int Xp = (col0 + q * 32 + p) * a.ox_mul + P.ox_off;
-                                if (row_ok && Xp < a.out_W) {
-                                    const size_t eo = ((size_t)n * a.out_H + Y) * a.out_W * a.out_C + nblk * BN + (size_t)Xp * a.out_C + c0 + cch * 8;
-                                    if (a.residual) {          // ResBlock2d: out = act(conv) + x (superresolution.py:283-288), same NHWC fp16 layout as the output
-                                        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(a.residual + eo));
-                                        __half2* ph = reinterpret_cast<__half2*>(&pk); const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+                                    for (int v = 0; v < 4; ++v) {
+                                        float lo[8];
 #pragma unroll
-                                        for (int e = 0; e < 4; ++e) { const float2 x = __half22float2(ph[e]), r = __half22float2(rh[e]); ph[e] = __floats2half2_rn(x.x + r.x, x.y + r.y); }
+                                        for (int e = 0; e < 8; ++e) lo[e] = f[8 * v + e] - __half2float(__float2half_rn(f[8 * v + e]));
+                                        st[lane * 4 + (v ^ sw)] = pack_half8(lo);
                                     }
-                                    *reinterpret_cast<uint4*>(a.out + eo) = pk;
                                 }
+                                __syncwarp();
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int p = i * 8 + (lane >> 2), cch = lane & 3;
+                                    uint4 pk = st[p * 4 + (cch ^ ((p >> 1) & 3))];
+                                    const int Xp = (col0 + q * 32 + p) * a.ox_mul + P.ox_off;
+                                    if (row_ok && Xp < a.out_W) {
+                                        const size_t eo = ((size_t)n * a.out_H + Y) * a.out_W * a.out_C + nblk * BN + (size_t)Xp * a.out_C + c0 + cch * 8 + pass * a.lo_off;
+                                        if (a.residual) {          // ResBlock2d: out = act(conv) + x (superresolution.py:283-288), same NHWC fp16 layout as the output
+                                            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(a.residual + eo));
+                                            __half2* ph = reinterpret_cast<__half2*>(&pk); const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                                            for (int e = 0; e < 4; ++e) { const float2 x = __half22float2(ph[e]), r = __half22float2(rh[e]); ph[e] = __floats2half2_rn(x.x + r.x, x.y + r.y); }
+                                        }
+                                        *reinterpret_cast<uint4*>(a.out + eo) = pk;
+                                    }
+                                }
+                                __syncwarp();
                             }
-                            __syncwarp();
                         }
                         if (want_rgb) {
 #pragma unroll
@@ -598,18 +622,29 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
 }
 
 // ---- helpers around the GEMMs ---------------------------------------------------------------------------------------
-// wf fp32 [Nw][O][I][3][3] -> packed fp16 [Nw][9][O][Ip]  (zero for i >= I)
-__global__ void pack_weights_kernel(const float* __restrict__ wf, int Nw, int O, int I, int Ip, __half* __restrict__ out) {
+// fp16 pair of a fp32 value: hi = fp16(v), lo = fp16(v - hi)  (v = hi + lo to ~2^-22 |v| while lo is a normal fp16 number)
+__device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
+// wf fp32 [Nw][O][I][3][3] -> packed fp16 [Nw][9][O][Ip]  (zero for i >= I); split: [Nw][9][O][2*Ip] = [hi | lo] of wf * 2^10
+__global__ void pack_weights_kernel(const float* __restrict__ wf, int Nw, int O, int I, int Ip, int split, __half* __restrict__ out) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)Nw * 9 * O * Ip;
     if (idx >= total) return;
     const int i = (int)(idx % Ip); const int o = (int)((idx / Ip) % O); const int t = (int)((idx / ((long long)Ip * O)) % 9);
     const int nw = (int)(idx / ((long long)Ip * O * 9));
-    out[idx] = __float2half_rn(i < I ? wf[(((size_t)nw * O + o) * I + i) * 9 + t] : 0.f);
+    const float v = i < I ? wf[(((size_t)nw * O + o) * I + i) * 9 + t] : 0.f;
+    if (!split) { out[idx] = __float2half_rn(v); return; }
+    __half hi, lo;
+    split_half(v * kSplitWeightScale, hi, lo);
+    const size_t row = (idx / Ip) * (size_t)(2 * Ip);
+    out[row + i] = hi; out[row + Ip + i] = lo;
 }
 
 // bilinear up-resize (or copy when size == h) of NCHW fp32 -> NHWC fp16 with channel padding to Cp
-__global__ void resize_to_nhwc_f16_kernel(const float* __restrict__ x, int N, int C, int h, int w, int size, int Cp, __half* __restrict__ y) {
+__global__ void resize_to_nhwc_f16_kernel(const float* __restrict__ x, int N, int C, int h, int w, int size, int Cp, int split, __half* __restrict__ y) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)N * size * size * Cp) return;
     const int c = (int)(idx % Cp); const int ox = (int)((idx / Cp) % size); const int oy = (int)((idx / ((long long)Cp * size)) % size);
@@ -625,7 +660,11 @@ __global__ void resize_to_nhwc_f16_kernel(const float* __restrict__ x, int N, in
         const float r1 = p[y0 * w + x1] * (1.f - ty) + p[y1 * w + x1] * ty;
         v = r0 * (1.f - tx) + r1 * tx;
     }
-    y[idx] = __float2half_rn(v);
+    if (!split) { y[idx] = __float2half_rn(v); return; }
+    __half hi, lo;
+    split_half(v, hi, lo);
+    const size_t pix = (idx / Cp) * (size_t)(2 * Cp);
+    y[pix + c] = hi; y[pix + Cp + c] = lo;
 }
 
 // last column X = 2W of the transposed-conv result (the only part of the (2H+1)x(2W+1) grid the 128-wide GEMM tiles do not
@@ -699,14 +738,19 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
         "mov.b64 {%0, %1}, rc;\n\t}"
         : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) fir_tma_kernel(const __grid_constant__ CUtensorMap tmY, const float* __restrict__ bias, int N, int OH,
                                                       int OW, int C, __half* __restrict__ y) {
+    // SPLIT: yb and y hold [hi | lo] fp16 halves of C channels each (fp32-grade path): both halves of a tile are loaded, summed in fp32,
+    // filtered, and the result is split again
+    constexpr int NSL = SPLIT ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem_1024(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * FIR_SLOT);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * NSL * FIR_SLOT);
     const int tid = threadIdx.x, px = tid >> 3, c8 = tid & 7;
     const int tiles_x = OW / FIR_TW, tiles_y = (OH + FIR_TH - 1) / FIR_TH, cgs = C / 64;
     const int total = N * cgs * tiles_y * tiles_x;
+    const int CS = SPLIT ? 2 * C : C;                                      // physical channels per pixel
     if (tid == 0) {
         mbar_init(&full[0], 1); mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -717,8 +761,9 @@ __global__ void __launch_bounds__(256) fir_tma_kernel(const __grid_constant__ CU
         const int tx = tile % tiles_x; int r = tile / tiles_x;
         const int ty = r % tiles_y; r /= tiles_y;
         const int cg = r % cgs, n = r / cgs;
-        mbar_expect_tx(&full[buf], FIR_BOX_BYTES);
-        tma_load_4d(smem + buf * FIR_SLOT, &tmY, &full[buf], cg * 64, tx * FIR_TW - 1, ty * FIR_TH - 1, n);
+        mbar_expect_tx(&full[buf], NSL * FIR_BOX_BYTES);
+        tma_load_4d(smem + buf * NSL * FIR_SLOT, &tmY, &full[buf], cg * 64, tx * FIR_TW - 1, ty * FIR_TH - 1, n);
+        if (SPLIT) tma_load_4d(smem + (buf * NSL + 1) * FIR_SLOT, &tmY, &full[buf], C + cg * 64, tx * FIR_TW - 1, ty * FIR_TH - 1, n);
     };
     if (tid == 0) {
         if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
@@ -735,7 +780,7 @@ __global__ void __launch_bounds__(256) fir_tma_kernel(const __grid_constant__ CU
 #pragma unroll
         for (int j = 0; j < 8; ++j) b[j] = bias[cg * 64 + c8 * 8 + j];
         mbar_wait(&full[buf], (it >> 1) & 1);
-        const uint8_t* sb = smem + buf * FIR_SLOT;
+        const uint8_t* sb = smem + buf * NSL * FIR_SLOT;
         float win[4][8];
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr)
@@ -751,9 +796,13 @@ __global__ void __launch_bounds__(256) fir_tma_kernel(const __grid_constant__ CU
                 const int row = ry * FIR_BW + px + v;                            // 128-byte row of the box; swizzle = chunk ^ (row & 7)
                 const uint4 raw = *reinterpret_cast<const uint4*>(sb + row * 128 + ((c8 ^ (row & 7)) << 4));
                 const __half2* h = reinterpret_cast<const __half2*>(&raw);
+                uint4 rawl = make_uint4(0, 0, 0, 0);
+                if (SPLIT) rawl = *reinterpret_cast<const uint4*>(sb + FIR_SLOT + row * 128 + ((c8 ^ (row & 7)) << 4));
+                const __half2* hl = reinterpret_cast<const __half2*>(&rawl);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float2 f = __half22float2(h[j]);
+                    float2 f = __half22float2(h[j]);
+                    if (SPLIT) { const float2 g = __half22float2(hl[j]); f.x += g.x; f.y += g.y; }
                     ffma2(win[3][2 * j], win[3][2 * j + 1], k4[v], k4[v], f.x, f.y);      // packed f32x2: the kernel is issue-bound
                 }
             }
@@ -761,6 +810,7 @@ __global__ void __launch_bounds__(256) fir_tma_kernel(const __grid_constant__ CU
                 const int oy = ty * FIR_TH + ry - 3;
                 if (oy < OH) {
                     uint4 pk; __half2* ph = reinterpret_cast<__half2*>(&pk);
+                    uint4 pl; __half2* pq = reinterpret_cast<__half2*>(&pl);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float a0 = b[2 * j], a1 = b[2 * j + 1];
@@ -768,8 +818,11 @@ __global__ void __launch_bounds__(256) fir_tma_kernel(const __grid_constant__ CU
                         for (int u = 0; u < 4; ++u) ffma2(a0, a1, k4[u], k4[u], win[u][2 * j], win[u][2 * j + 1]);
                         a0 = (a0 < 0.f ? a0 * 0.2f : a0) * 1.4142135623730951f; a1 = (a1 < 0.f ? a1 * 0.2f : a1) * 1.4142135623730951f;
                         ph[j] = __floats2half2_rn(a0, a1);
+                        if (SPLIT) { const float2 hf = __half22float2(ph[j]); pq[j] = __floats2half2_rn(a0 - hf.x, a1 - hf.y); }
                     }
-                    *reinterpret_cast<uint4*>(y + (((size_t)n * OH + oy) * OW + ox) * C + cg * 64 + c8 * 8) = pk;
+                    __half* dst = y + (((size_t)n * OH + oy) * OW + ox) * CS + cg * 64 + c8 * 8;
+                    *reinterpret_cast<uint4*>(dst) = pk;
+                    if (SPLIT) *reinterpret_cast<uint4*>(dst + C) = pl;
                 }
             }
         }
@@ -778,6 +831,55 @@ __global__ void __launch_bounds__(256) fir_tma_kernel(const __grid_constant__ CU
             const int nxt = tile + 2 * gridDim.x;
             if (nxt < total) issue(nxt, buf);
         }
+    }
+}
+
+// split-operand version of upconv_edge_kernel (fp32-grade path): x [N][H][W][2*Cp] and the packed weights [..][2*Cp] hold [hi | lo] halves, the
+// weights x 2^10; both are summed to fp32 while they are staged, the dot products run in fp32, the result is written as [hi | lo] of O channels.
+__global__ void __launch_bounds__(256) upconv_edge_split_kernel(const __half* __restrict__ x, const __half* __restrict__ wp, int H, int W, int Cp, int O,
+                                                                int w_shared, __half* __restrict__ yb) {
+    extern __shared__ __align__(16) uint8_t edge_smem[];
+    float* s_x = reinterpret_cast<float*>(edge_smem);                        // [10][Cp]
+    float* s_w = s_x + (kEdgeRows / 2 + 2) * Cp;                             // [3][32][Cp + 4]
+    const int WS = Cp + 4;
+    const int n = blockIdx.z, Y0 = blockIdx.x * kEdgeRows, co0 = blockIdx.y * kEdgeCo;
+    const int BH = 2 * H + 1, BW = 2 * W + 1;
+    const int wn = w_shared ? 0 : n;
+    const int iy0 = Y0 / 2 - 1;
+    for (int e = threadIdx.x; e < (kEdgeRows / 2 + 2) * Cp; e += 256) {
+        const int r = e / Cp, c = e - r * Cp, iy = iy0 + r;
+        float v = 0.f;
+        if (iy >= 0 && iy < H) { const __half* px = x + (((size_t)n * H + iy) * W + (W - 1)) * 2 * Cp; v = __half2float(px[c]) + __half2float(px[Cp + c]); }
+        s_x[r * Cp + c] = v;
+    }
+    for (int e = threadIdx.x; e < 3 * kEdgeCo * Cp; e += 256) {
+        const int c = e % Cp, co = (e / Cp) % kEdgeCo, ky = e / (Cp * kEdgeCo);
+        float v = 0.f;
+        if (co0 + co < O) { const __half* pw = wp + (((size_t)wn * 9 + ky * 3 + 2) * O + co0 + co) * 2 * Cp; v = __half2float(pw[c]) + __half2float(pw[Cp + c]); }
+        s_w[(ky * kEdgeCo + co) * WS + c] = v;
+    }
+    __syncthreads();
+    const int co = threadIdx.x & 31, yp = threadIdx.x >> 5;
+    if (co0 + co >= O) return;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int yy = yp * 2 + half, Y = Y0 + yy;
+        if (Y >= BH) continue;
+        float acc = 0.f;
+        for (int ky = (yy & 1); ky < 3; ky += 2) {
+            const int r = ((yy - ky) >> 1) + 1;
+            const float4* xr = reinterpret_cast<const float4*>(s_x + r * Cp);
+            const float4* wr = reinterpret_cast<const float4*>(s_w + (ky * kEdgeCo + co) * WS);
+            for (int c4 = 0; c4 < Cp / 4; ++c4) {
+                const float4 a = xr[c4], b = wr[c4];
+                acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+            }
+        }
+        acc *= 1.0f / kSplitWeightScale;
+        __half hi, lo;
+        split_half(acc, hi, lo);
+        __half* dst = yb + (((size_t)n * BH + Y) * BW + 2 * W) * 2 * O + co0 + co;
+        dst[0] = hi; dst[O] = lo;
     }
 }
 
@@ -870,7 +972,7 @@ static int make_map_fir(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d
 }
 
 static int launch_conv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, const ConvArgs& a1, cudaStream_t st);
-static int launch_upconv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, __half* yb, const float* bias, cudaStream_t st);
+static int launch_upconv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, __half* yb, const float* bias, int split, cudaStream_t st);
 static int launch_conv(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, ConvArgs a, cudaStream_t st) {
     return launch_conv2(x, N, H, W, Cp, wp, Nw, O, a, st);
 }
@@ -938,8 +1040,11 @@ static void fill_taps2(Taps2& t2, const Taps& t) {
 
 static int run_conv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, Conv2Args& a, int max_rows, cudaStream_t st, int n_taps = 9) {
     CUtensorMap tmA, tmB;
-    if (make_map_4d_box(&tmA, x, (uint64_t)Cp, (uint64_t)W, (uint64_t)H, (uint64_t)N, A2_ROWS)) return 1;
-    if (make_map_4d_box(&tmB, wp, (uint64_t)Cp, (uint64_t)O, (uint64_t)n_taps, (uint64_t)Nw, BN / 2)) return 1;
+    const uint64_t Cphys = (uint64_t)Cp * (a.split ? 2 : 1);                      // split: [hi | lo] halves of Cp channels each
+    if (make_map_4d_box(&tmA, x, Cphys, (uint64_t)W, (uint64_t)H, (uint64_t)N, A2_ROWS)) return 1;
+    if (make_map_4d_box(&tmB, wp, Cphys, (uint64_t)O, (uint64_t)n_taps, (uint64_t)Nw, BN / 2)) return 1;
+    if (a.split) { R3DP_REQUIRE(a.residual == nullptr, "conv_tc3: the residual epilogue is not built for split operands"); a.acc_scale = 1.0f / kSplitWeightScale; a.lo_off = a.out_C; a.out_C *= 2; }
+    else { a.acc_scale = 1.0f; a.lo_off = 0; }
     a.k_chunks = Cp / BK; a.tiles_x = W / BM; a.n_blocks = O / BN; a.n_images = N; a.w_shared = (Nw == 1);
     if (a.act_gain == 0.f) { a.act_slope = 0.2f; a.act_gain = 1.4142135623730951f; }      // default: bias_act lrelu
     R3DP_REQUIRE(a.n_blocks >= 1 && a.n_blocks <= 2, "conv_tc3: 128 or 256 output channels");
@@ -954,14 +1059,14 @@ static int launch_conv2(const void* x, int N, int H, int W, int Cp, const void* 
     a.ph[0].rows = a1.rows; a.ph[0].oy_off = a1.oy_off; a.ph[0].ox_off = a1.ox_off;
     a.mode = a1.mode; a.out = a1.out; a.out_H = a1.out_H; a.out_W = a1.out_W; a.out_C = a1.out_C; a.oy_mul = a1.oy_mul; a.ox_mul = a1.ox_mul;
     a.bias = a1.bias; a.wrgb = a1.wrgb; a.brgb = a1.brgb; a.img_prev = a1.img_prev; a.img_out = a1.img_out; a.img_H = a1.out_H; a.img_W = a1.out_W;
-    a.out_clamp = a1.out_clamp; a.img_out_u8 = a1.img_out_u8;
+    a.out_clamp = a1.out_clamp; a.img_out_u8 = a1.img_out_u8; a.split = a1.split;
     return run_conv2(x, N, H, W, Cp, wp, Nw, O, a, a1.rows, st);
 }
 
 // all four output-parity phases of the stride-2 transposed conv in ONE persistent launch (raw fp16 result on the (2H+1)x(2W+1) grid)
-static int launch_upconv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, __half* yb, const float* bias, cudaStream_t st) {
+static int launch_upconv2(const void* x, int N, int H, int W, int Cp, const void* wp, int Nw, int O, __half* yb, const float* bias, int split, cudaStream_t st) {
     Conv2Args a = {};
-    a.n_phases = 4;
+    a.n_phases = 4; a.split = split;
     for (int pa = 0; pa < 2; ++pa)
         for (int pb = 0; pb < 2; ++pb) {
             Taps t = {};
@@ -981,34 +1086,39 @@ static int launch_upconv2(const void* x, int N, int H, int W, int Cp, const void
 using namespace r3dp;
 using namespace r3dp::tc;
 
-extern "C" int r3dp_sr_tc_pack_weights(const float* wf, int Nw, int O, int I, void* packed_f16, r3dp_stream_t stream) {
+static int pack_weights_impl(const float* wf, int Nw, int O, int I, void* packed_f16, int split, r3dp_stream_t stream) {
     R3DP_REQUIRE(wf && packed_f16, "sr_tc_pack_weights: null pointer");
     R3DP_REQUIRE(Nw > 0 && O > 0 && I > 0, "sr_tc_pack_weights: bad shape");
     const int Ip = (I + 63) / 64 * 64;
     const long long total = (long long)Nw * 9 * O * Ip;
-    pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(wf, Nw, O, I, Ip, reinterpret_cast<__half*>(packed_f16));
+    pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(wf, Nw, O, I, Ip, split, reinterpret_cast<__half*>(packed_f16));
     R3DP_LAUNCH_CHECK();
     count_launches(1);
     return 0;
 }
+extern "C" int r3dp_sr_tc_pack_weights(const float* wf, int Nw, int O, int I, void* packed_f16, r3dp_stream_t stream) { return pack_weights_impl(wf, Nw, O, I, packed_f16, 0, stream); }
+extern "C" int r3dp_sr_tcx_pack_weights(const float* wf, int Nw, int O, int I, void* packed_f16, r3dp_stream_t stream) { return pack_weights_impl(wf, Nw, O, I, packed_f16, 1, stream); }
 
-extern "C" int r3dp_sr_tc_input(const float* x, int N, int C, int h, int w, int size, void* y_f16, r3dp_stream_t stream) {
+static int input_impl(const float* x, int N, int C, int h, int w, int size, void* y_f16, int split, r3dp_stream_t stream) {
     R3DP_REQUIRE(x && y_f16, "sr_tc_input: null pointer");
     R3DP_REQUIRE(N > 0 && C > 0 && h > 0 && w > 0 && size >= h && size >= w, "sr_tc_input: up-scaling (or copy) only");
     const int Cp = (C + 63) / 64 * 64;
     const long long total = (long long)N * size * size * Cp;
-    resize_to_nhwc_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, N, C, h, w, size, Cp, reinterpret_cast<__half*>(y_f16));
+    resize_to_nhwc_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, N, C, h, w, size, Cp, split, reinterpret_cast<__half*>(y_f16));
     R3DP_LAUNCH_CHECK();
     count_launches(1);
     return 0;
 }
+extern "C" int r3dp_sr_tc_input(const float* x, int N, int C, int h, int w, int size, void* y_f16, r3dp_stream_t stream) { return input_impl(x, N, C, h, w, size, y_f16, 0, stream); }
+extern "C" int r3dp_sr_tcx_input(const float* x, int N, int C, int h, int w, int size, void* y_f16, r3dp_stream_t stream) { return input_impl(x, N, C, h, w, size, y_f16, 1, stream); }
 
 extern "C" size_t r3dp_sr_tc_scratch_bytes(int N, int O, int H, int W) { return (size_t)N * (2 * H + 1) * (2 * W + 1) * O * sizeof(__half); }
+extern "C" size_t r3dp_sr_tcx_scratch_bytes(int N, int O, int H, int W) { return 2 * r3dp_sr_tc_scratch_bytes(N, O, H, W); }
 
 // SynthesisLayer on tensor cores.  x [N][H][W][Ip] fp16 NHWC (Ip = I rounded up to 64), wp packed weights [Nw][9][O][Ip] fp16
 // (Nw == N per-sample, or 1 shared), bias [O] fp32.  up == 1: y [N][H][W][O]; up == 2: y [N][2H][2W][O], scratch >= r3dp_sr_tc_scratch_bytes.
-extern "C" int r3dp_sr_tc_layer(const void* x_f16, const void* wp_f16, const float* bias, int N, int Nw, int I, int O, int H, int W, int up,
-                                void* y_f16, void* scratch, r3dp_stream_t stream) {
+static int layer_impl(const void* x_f16, const void* wp_f16, const float* bias, int N, int Nw, int I, int O, int H, int W, int up,
+                      void* y_f16, void* scratch, int split, r3dp_stream_t stream) {
     R3DP_REQUIRE(x_f16 && wp_f16 && bias && y_f16, "sr_tc_layer: null pointer");
     R3DP_REQUIRE(N > 0 && (Nw == N || Nw == 1) && I > 0 && H > 0, "sr_tc_layer: bad shape");
     R3DP_REQUIRE(W % BM == 0 && O % BN == 0, "sr_tc_layer: needs W %% 128 == 0 and Cout %% 128 == 0 (got W=%d, Cout=%d)", W, O);
@@ -1016,7 +1126,7 @@ extern "C" int r3dp_sr_tc_layer(const void* x_f16, const void* wp_f16, const flo
     const int Ip = (I + 63) / 64 * 64;
     cudaStream_t st = as_stream(stream);
     ConvArgs a = {};
-    a.bias = bias;
+    a.bias = bias; a.split = split;
     if (up == 1) {
         a.taps.n = 9;
         for (int t = 0; t < 9; ++t) { a.taps.dy[t] = t / 3 - 1; a.taps.dx[t] = t % 3 - 1; a.taps.widx[t] = t; }
@@ -1026,43 +1136,76 @@ extern "C" int r3dp_sr_tc_layer(const void* x_f16, const void* wp_f16, const flo
     }
     R3DP_REQUIRE(scratch, "sr_tc_layer: up=2 needs scratch");
     __half* yb = reinterpret_cast<__half*>(scratch);
-    if (launch_upconv2(x_f16, N, H, W, Ip, wp_f16, Nw, O, yb, bias, st)) return 1;
+    if (launch_upconv2(x_f16, N, H, W, Ip, wp_f16, Nw, O, yb, bias, split, st)) return 1;
     {
         R3DP_REQUIRE(Ip <= 256, "sr_tc_layer: up=2 supports at most 256 input channels");
         dim3 grid((2 * H + 1 + kEdgeRows - 1) / kEdgeRows, (O + kEdgeCo - 1) / kEdgeCo, N);
         const size_t esmem = ((size_t)(kEdgeRows / 2 + 2) * Ip + 3 * (size_t)kEdgeCo * (Ip + 8)) * sizeof(__half);
+        if (split) {
+            const size_t ssmem = ((size_t)(kEdgeRows / 2 + 2) * Ip + 3 * (size_t)kEdgeCo * (Ip + 4)) * sizeof(float);
+            R3DP_CUDA(cudaFuncSetAttribute(upconv_edge_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            upconv_edge_split_kernel<<<grid, 256, ssmem, st>>>(reinterpret_cast<const __half*>(x_f16), reinterpret_cast<const __half*>(wp_f16), H, W, Ip, O,
+                                                           Nw == 1, yb);
+        } else {
         R3DP_CUDA(cudaFuncSetAttribute(upconv_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         upconv_edge_kernel<<<grid, 256, esmem, st>>>(reinterpret_cast<const __half*>(x_f16), reinterpret_cast<const __half*>(wp_f16), H, W, Ip, O,
                                                  Nw == 1, yb);
+        }
     }
     {
         R3DP_REQUIRE((2 * W) % FIR_TW == 0 && O % 64 == 0, "sr_tc_layer: FIR needs 2W %% 32 == 0 and Cout %% 64 == 0");
         CUtensorMap tmY;
-        if (make_map_fir(&tmY, yb, (uint64_t)O, (uint64_t)(2 * W + 1), (uint64_t)(2 * H + 1), (uint64_t)N)) return 1;
-                    R3DP_CUDA(cudaFuncSetAttribute(fir_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIR_SMEM));
+        if (make_map_fir(&tmY, yb, (uint64_t)O * (split ? 2 : 1), (uint64_t)(2 * W + 1), (uint64_t)(2 * H + 1), (uint64_t)N)) return 1;
         const int total = N * (O / 64) * ((2 * H + FIR_TH - 1) / FIR_TH) * (2 * W / FIR_TW);
-        const int grid = total < 2 * sm_count() ? total : 2 * sm_count();
-        fir_tma_kernel<<<grid, 256, FIR_SMEM, st>>>(tmY, bias, N, 2 * H, 2 * W, O, reinterpret_cast<__half*>(y_f16));
+        if (split) {
+            const int smem = 4 * FIR_SLOT + 1024 + 64;
+            R3DP_CUDA(cudaFuncSetAttribute(fir_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            const int grid = total < sm_count() ? total : sm_count();
+            fir_tma_kernel<true><<<grid, 256, smem, st>>>(tmY, bias, N, 2 * H, 2 * W, O, reinterpret_cast<__half*>(y_f16));
+        } else {
+            R3DP_CUDA(cudaFuncSetAttribute(fir_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIR_SMEM));
+            const int grid = total < 2 * sm_count() ? total : 2 * sm_count();
+            fir_tma_kernel<false><<<grid, 256, FIR_SMEM, st>>>(tmY, bias, N, 2 * H, 2 * W, O, reinterpret_cast<__half*>(y_f16));
+        }
     }
     R3DP_LAUNCH_CHECK();
     count_launches(2);
     return 0;
 }
+extern "C" int r3dp_sr_tc_layer(const void* x_f16, const void* wp_f16, const float* bias, int N, int Nw, int I, int O, int H, int W, int up,
+                                void* y_f16, void* scratch, r3dp_stream_t stream) {
+    return layer_impl(x_f16, wp_f16, bias, N, Nw, I, O, H, W, up, y_f16, scratch, 0, stream);
+}
+extern "C" int r3dp_sr_tcx_layer(const void* x_f16, const void* wp_f16, const float* bias, int N, int Nw, int I, int O, int H, int W, int up,
+                                 void* y_f16, void* scratch, r3dp_stream_t stream) {
+    return layer_impl(x_f16, wp_f16, bias, N, Nw, I, O, H, W, up, y_f16, scratch, 1, stream);
+}
 
 // Last layer fused with ToRGB: conv3x3 (I -> 128) + bias + lrelu, then img_out = upsample2d(img_prev) + torgb + brgb; the 128-channel
 // activation itself is never written (SynthesisBlock is_last: only the image leaves the block).
-extern "C" int r3dp_sr_tc_last_layer_ex(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
-                                        const float* img_prev, int N, int Nw, int I, int H, int W, float* img_out, uint8_t* img_out_u8, int clamp,
-                                        r3dp_stream_t stream) {
+static int last_layer_impl(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
+                           const float* img_prev, int N, int Nw, int I, int H, int W, float* img_out, uint8_t* img_out_u8, int clamp, int split,
+                           r3dp_stream_t stream) {
     R3DP_REQUIRE(x_f16 && wp_f16 && bias && wrgb && brgb && (img_out || img_out_u8), "sr_tc_last_layer: null pointer");
     R3DP_REQUIRE(N > 0 && (Nw == N || Nw == 1) && W % BM == 0 && H % 2 == 0, "sr_tc_last_layer: bad shape");
     const int Ip = (I + 63) / 64 * 64;
     ConvArgs a = {};
     a.bias = bias; a.wrgb = wrgb; a.brgb = brgb; a.img_prev = img_prev; a.img_out = img_out; a.img_out_u8 = img_out_u8; a.out_clamp = clamp || img_out_u8;
+    a.split = split;
     a.taps.n = 9;
     for (int t = 0; t < 9; ++t) { a.taps.dy[t] = t / 3 - 1; a.taps.dx[t] = t % 3 - 1; a.taps.widx[t] = t; }
     a.tiles_x = W / BM; a.rows = H; a.mode = kToRgbFinal; a.out_H = H; a.out_W = W; a.out_C = BN; a.oy_mul = a.ox_mul = 1;
     return launch_conv(x_f16, N, H, W, Ip, wp_f16, Nw, BN, a, as_stream(stream));
+}
+extern "C" int r3dp_sr_tc_last_layer_ex(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
+                                        const float* img_prev, int N, int Nw, int I, int H, int W, float* img_out, uint8_t* img_out_u8, int clamp,
+                                        r3dp_stream_t stream) {
+    return last_layer_impl(x_f16, wp_f16, bias, wrgb, brgb, img_prev, N, Nw, I, H, W, img_out, img_out_u8, clamp, 0, stream);
+}
+extern "C" int r3dp_sr_tcx_last_layer(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
+                                      const float* img_prev, int N, int Nw, int I, int H, int W, float* img_out, uint8_t* img_out_u8, int clamp,
+                                      r3dp_stream_t stream) {
+    return last_layer_impl(x_f16, wp_f16, bias, wrgb, brgb, img_prev, N, Nw, I, H, W, img_out, img_out_u8, clamp, 1, stream);
 }
 extern "C" int r3dp_sr_tc_last_layer(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
                                      const float* img_prev, int N, int Nw, int I, int H, int W, float* img_out, r3dp_stream_t stream) {
@@ -1088,9 +1231,9 @@ extern "C" int r3dp_sr_tc_torgb(const void* x_f16, const float* wrgb, const floa
 
 // SynthesisLayer (up == 1) fused with the block's ToRGB + skip (networks_stylegan2.py:463-469): y [N,H,W,O] fp16 AND
 // img_out [N,3,H,W] fp32 = upsample2d(img_prev [N,3,H/2,W/2]) + conv1x1(y, wrgb [Nw,3,O]) + brgb.  O = 128 or 256.
-extern "C" int r3dp_sr_tc_layer_torgb(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
-                                      const float* img_prev, int N, int Nw, int I, int O, int H, int W, void* y_f16, float* img_out,
-                                      r3dp_stream_t stream) {
+static int layer_torgb_impl(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
+                            const float* img_prev, int N, int Nw, int I, int O, int H, int W, void* y_f16, float* img_out, int split,
+                            r3dp_stream_t stream) {
     R3DP_REQUIRE(x_f16 && wp_f16 && bias && wrgb && brgb && y_f16 && img_out, "sr_tc_layer_torgb: null pointer");
     R3DP_REQUIRE(N > 0 && (Nw == N || Nw == 1) && W % BM == 0 && O % BN == 0 && O <= 256 && H % 2 == 0, "sr_tc_layer_torgb: bad shape");
     const int Ip = (I + 63) / 64 * 64;
@@ -1102,13 +1245,23 @@ extern "C" int r3dp_sr_tc_layer_torgb(const void* x_f16, const void* wp_f16, con
     fill_taps2(a.ph[0].taps, t);
     a.ph[0].rows = H; a.ph[0].oy_off = 0; a.ph[0].ox_off = 0;
     a.mode = kActRgb; a.out = reinterpret_cast<__half*>(y_f16); a.out_H = H; a.out_W = W; a.out_C = O; a.oy_mul = a.ox_mul = 1;
-    a.bias = bias; a.wrgb = wrgb; a.brgb = brgb; a.img_prev = img_prev; a.img_out = img_out; a.img_H = H; a.img_W = W;
+    a.bias = bias; a.wrgb = wrgb; a.brgb = brgb; a.img_prev = img_prev; a.img_out = img_out; a.img_H = H; a.img_W = W; a.split = split;
     return run_conv2(x_f16, N, H, W, Ip, wp_f16, Nw, O, a, H, as_stream(stream));
+}
+extern "C" int r3dp_sr_tc_layer_torgb(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
+                                      const float* img_prev, int N, int Nw, int I, int O, int H, int W, void* y_f16, float* img_out,
+                                      r3dp_stream_t stream) {
+    return layer_torgb_impl(x_f16, wp_f16, bias, wrgb, brgb, img_prev, N, Nw, I, O, H, W, y_f16, img_out, 0, stream);
+}
+extern "C" int r3dp_sr_tcx_layer_torgb(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
+                                       const float* img_prev, int N, int Nw, int I, int O, int H, int W, void* y_f16, float* img_out,
+                                       r3dp_stream_t stream) {
+    return layer_torgb_impl(x_f16, wp_f16, bias, wrgb, brgb, img_prev, N, Nw, I, O, H, W, y_f16, img_out, 1, stream);
 }
 
 // bilinear up-resize of a CHANNELS-LAST fp32 image [N,h,w,C] (e.g. the renderer's [N,M,32] output viewed as an image) to
 // NHWC fp16 [N,size,size,Cpad]: one thread = one output pixel x 8 channels.
-__global__ void resize_nhwc_to_f16_kernel(const float* __restrict__ x, int N, int C, int h, int w, int size, int Cp, __half* __restrict__ y) {
+__global__ void resize_nhwc_to_f16_kernel(const float* __restrict__ x, int N, int C, int h, int w, int size, int Cp, int split, __half* __restrict__ y) {
     const int cv = Cp / 8;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)N * size * size * cv) return;
@@ -1140,19 +1293,27 @@ __global__ void resize_nhwc_to_f16_kernel(const float* __restrict__ x, int N, in
     uint4 pk; __half2* ph = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
     for (int j = 0; j < 4; ++j) ph[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-    *reinterpret_cast<uint4*>(y + idx * 8) = pk;
+    if (!split) { *reinterpret_cast<uint4*>(y + idx * 8) = pk; return; }
+    uint4 pl; __half2* pq = reinterpret_cast<__half2*>(&pl);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 hf = __half22float2(ph[j]); pq[j] = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y); }
+    const size_t pix = (size_t)(idx / cv) * (size_t)(2 * Cp);
+    *reinterpret_cast<uint4*>(y + pix + c8 * 8) = pk;
+    *reinterpret_cast<uint4*>(y + pix + Cp + c8 * 8) = pl;
 }
 
-extern "C" int r3dp_sr_tc_input_nhwc(const float* x_nhwc, int N, int C, int h, int w, int size, void* y_f16, r3dp_stream_t stream) {
+static int input_nhwc_impl(const float* x_nhwc, int N, int C, int h, int w, int size, void* y_f16, int split, r3dp_stream_t stream) {
     R3DP_REQUIRE(x_nhwc && y_f16, "sr_tc_input_nhwc: null pointer");
     R3DP_REQUIRE(N > 0 && C > 0 && C % 8 == 0 && h > 0 && w > 0 && size >= h && size >= w, "sr_tc_input_nhwc: bad shape (C %% 8 == 0, up-scaling only)");
     const int Cp = (C + 63) / 64 * 64;
     const long long total = (long long)N * size * size * (Cp / 8);
-    resize_nhwc_to_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x_nhwc, N, C, h, w, size, Cp, reinterpret_cast<__half*>(y_f16));
+    resize_nhwc_to_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x_nhwc, N, C, h, w, size, Cp, split, reinterpret_cast<__half*>(y_f16));
     R3DP_LAUNCH_CHECK();
     count_launches(1);
     return 0;
 }
+extern "C" int r3dp_sr_tc_input_nhwc(const float* x_nhwc, int N, int C, int h, int w, int size, void* y_f16, r3dp_stream_t stream) { return input_nhwc_impl(x_nhwc, N, C, h, w, size, y_f16, 0, stream); }
+extern "C" int r3dp_sr_tcx_input_nhwc(const float* x_nhwc, int N, int C, int h, int w, int size, void* y_f16, r3dp_stream_t stream) { return input_nhwc_impl(x_nhwc, N, C, h, w, size, y_f16, 1, stream); }
 
 // ---- composed up-convolution for small Cin -------------------------------------------------------------------------------
 // FIR(conv_transpose(x, w)) == four 3x3 correlations on the low-resolution input, one per output parity (p,q), with weights
@@ -1160,7 +1321,7 @@ extern "C" int r3dp_sr_tc_input_nhwc(const float* x_nhwc, int N, int C, int h, i
 // g = [1,3,3,1]/4 (FIR * gain 4), dy,dx in {-1,0,1}  (derivation in DESIGN.md).  This costs 4x the MACs of the two-step form but
 // needs no (2H+1)x(2W+1) intermediate, no FIR pass and no edge column: a win when Cin is small (block0.conv0: 32 -> 256).
 // wf fp32 [Nw][O][I][3][3] -> packed fp16 [Nw][36][O][Ip], tap index = (p*2+q)*9 + (dy+1)*3 + (dx+1).
-__global__ void compose_up_weights_kernel(const float* __restrict__ wf, int Nw, int O, int I, int Ip, __half* __restrict__ out) {
+__global__ void compose_up_weights_kernel(const float* __restrict__ wf, int Nw, int O, int I, int Ip, int split, __half* __restrict__ out) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)Nw * 36 * O * Ip;
     if (idx >= total) return;
@@ -1181,23 +1342,29 @@ __global__ void compose_up_weights_kernel(const float* __restrict__ wf, int Nw, 
             }
         }
     }
-    out[idx] = __float2half_rn(acc);
+    if (!split) { out[idx] = __float2half_rn(acc); return; }
+    __half hi, lo;
+    split_half(acc * kSplitWeightScale, hi, lo);
+    const size_t row = (idx / Ip) * (size_t)(2 * Ip);
+    out[row + i] = hi; out[row + Ip + i] = lo;
 }
 
-extern "C" int r3dp_sr_tc_pack_weights_up_composed(const float* wf, int Nw, int O, int I, void* packed_f16, r3dp_stream_t stream) {
+static int pack_up_composed_impl(const float* wf, int Nw, int O, int I, void* packed_f16, int split, r3dp_stream_t stream) {
     R3DP_REQUIRE(wf && packed_f16, "sr_tc_pack_weights_up_composed: null pointer");
     R3DP_REQUIRE(Nw > 0 && O > 0 && I > 0, "sr_tc_pack_weights_up_composed: bad shape");
     const int Ip = (I + 63) / 64 * 64;
     const long long total = (long long)Nw * 36 * O * Ip;
-    compose_up_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(wf, Nw, O, I, Ip, reinterpret_cast<__half*>(packed_f16));
+    compose_up_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(wf, Nw, O, I, Ip, split, reinterpret_cast<__half*>(packed_f16));
     R3DP_LAUNCH_CHECK();
     count_launches(1);
     return 0;
 }
+extern "C" int r3dp_sr_tc_pack_weights_up_composed(const float* wf, int Nw, int O, int I, void* packed_f16, r3dp_stream_t stream) { return pack_up_composed_impl(wf, Nw, O, I, packed_f16, 0, stream); }
+extern "C" int r3dp_sr_tcx_pack_weights_up_composed(const float* wf, int Nw, int O, int I, void* packed_f16, r3dp_stream_t stream) { return pack_up_composed_impl(wf, Nw, O, I, packed_f16, 1, stream); }
 
 // SynthesisLayer with up == 2 through the composed weights: x [N][H][W][Ip] fp16 -> y [N][2H][2W][O] fp16 (bias + lrelu fused).
-extern "C" int r3dp_sr_tc_layer_up_composed(const void* x_f16, const void* wpc_f16, const float* bias, int N, int Nw, int I, int O, int H,
-                                            int W, void* y_f16, r3dp_stream_t stream) {
+static int layer_up_composed_impl(const void* x_f16, const void* wpc_f16, const float* bias, int N, int Nw, int I, int O, int H,
+                                  int W, void* y_f16, int split, r3dp_stream_t stream) {
     R3DP_REQUIRE(x_f16 && wpc_f16 && bias && y_f16, "sr_tc_layer_up_composed: null pointer");
     R3DP_REQUIRE(N > 0 && (Nw == N || Nw == 1) && W % BM == 0 && O % BN == 0 && O <= 256, "sr_tc_layer_up_composed: bad shape");
     const int Ip = (I + 63) / 64 * 64;
@@ -1211,8 +1378,16 @@ extern "C" int r3dp_sr_tc_layer_up_composed(const void* x_f16, const void* wpc_f
         a.ph[ph].rows = H; a.ph[ph].oy_off = ph >> 1; a.ph[ph].ox_off = ph & 1;
     }
     a.mode = kStoreAct; a.out = reinterpret_cast<__half*>(y_f16); a.out_H = 2 * H; a.out_W = 2 * W; a.out_C = O; a.oy_mul = a.ox_mul = 2;
-    a.bias = bias;
+    a.bias = bias; a.split = split;
     return run_conv2(x_f16, N, H, W, Ip, wpc_f16, Nw, O, a, H, as_stream(stream), 36);
+}
+extern "C" int r3dp_sr_tc_layer_up_composed(const void* x_f16, const void* wpc_f16, const float* bias, int N, int Nw, int I, int O, int H,
+                                            int W, void* y_f16, r3dp_stream_t stream) {
+    return layer_up_composed_impl(x_f16, wpc_f16, bias, N, Nw, I, O, H, W, y_f16, 0, stream);
+}
+extern "C" int r3dp_sr_tcx_layer_up_composed(const void* x_f16, const void* wpc_f16, const float* bias, int N, int Nw, int I, int O, int H,
+                                             int W, void* y_f16, r3dp_stream_t stream) {
+    return layer_up_composed_impl(x_f16, wpc_f16, bias, N, Nw, I, O, H, W, y_f16, 1, stream);
 }
 
 // ---- building blocks of the torso head (modules/real3d/super_resolution/sr_with_ref.py:16-162) --------------------------------

@@ -107,7 +107,7 @@ class FrameEngine:
         self.head = RenderHead(hp=hp, sr_mode=sr_mode).to(self.device).eval()
         self.static_styles, self.use_graph = static_styles, use_graph
         self.out_uint8 = bool(out_uint8)
-        if self.out_uint8 and sr_mode != 'tc':
+        if self.out_uint8 and sr_mode not in ('tc', 'tc_exact'):
             raise NotImplementedError('uint8 frames are written by the tensor-core SR epilogue (sr_mode="tc")')
         self.exchange = exchange if world > 1 else 'none'
         self.graph = None
@@ -133,11 +133,11 @@ class FrameEngine:
         self.inplace = {}
         sr = self.head.superresolution
         sr.static_prepared = None
-        if self.static_styles and sr.sr_mode == 'tc' and not self.head.torso:
+        if self.static_styles and sr.sr_mode in ('tc', 'tc_exact') and not self.head.torso:
             from . import sr_tc
             ones = torch.ones(1, 3, self.head.hparams['w_dim'], device=self.device)
             with torch.no_grad():
-                sr.static_prepared = sr_tc.Prepared(sr, ones)
+                sr.static_prepared = sr_tc.Prepared(sr, ones, sr.sr_mode == 'tc_exact')
 
     @torch.no_grad()
     def _body(self, planes, cameras, u_coarse, u_fine=None) -> torch.Tensor:
@@ -330,6 +330,11 @@ class FrameEngine:
         if self.world > 1 and self.dist is not None:
             self.dist.barrier()
         clip = self._clip if self.rank == 0 else None
+        if self.rank != 0 and getattr(self, '_p2p', None) is not None:      # drop this process's mapping of rank 0's buffer before rank 0 may free it
+            self._clip_view = self._clip = None
+            torch.cuda.ipc_collect()
+        if self.world > 1 and self.dist is not None and getattr(self, '_p2p', None) is not None:
+            self.dist.barrier()
         return clip
 
     # ---- host-buffer entry point: H2D / compute / D2H of consecutive steps overlap on three streams -----------------------
@@ -397,7 +402,7 @@ class FrameEngine:
         torch.cuda.synchronize()
         capi.PROF = capi.Profiler()
         L = capi.lib()
-        tc = self.head.superresolution.sr_mode == 'tc'
+        tc = self.head.superresolution.sr_mode in ('tc', 'tc_exact')
         if tc:
             L.r3dp_sr_tc_prof(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

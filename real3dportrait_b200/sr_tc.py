@@ -15,62 +15,66 @@ def available() -> bool:
     return hasattr(capi.lib(), 'r3dp_sr_tc_layer')
 
 
-def _pack(layer, w_lat: torch.Tensor) -> torch.Tensor:
-    """SynthesisLayer -> packed fp16 weights [Nw,9,O,Ipad]."""
+def _fn(name: str, split: bool):
+    """C entry point `r3dp_sr_tc_<name>` or its split-operand twin `r3dp_sr_tcx_<name>` (sr_mode='tc_exact')."""
+    return getattr(capi.lib(), ('r3dp_sr_tcx_' if split else 'r3dp_sr_tc_') + name)
+
+
+def _pack(layer, w_lat: torch.Tensor, split: bool = False) -> torch.Tensor:
+    """SynthesisLayer -> packed fp16 weights [Nw,9,O,Ipad] ([Nw,9,O,2*Ipad] = [hi | lo] of w * 2^10 when split)."""
     wf = layer.folded_weight(w_lat)                                  # [Nw,O,I,3,3] fp32
     Nw, O, I = wf.shape[:3]
     Ip = (I + 63) // 64 * 64
-    out = torch.empty(Nw, 9, O, Ip, device=wf.device, dtype=torch.float16)
-    capi.check(capi.lib().r3dp_sr_tc_pack_weights(capi.ptr(wf), Nw, O, I, capi.ptr(out, torch.float16), capi.stream()))
+    out = torch.empty(Nw, 9, O, Ip * (2 if split else 1), device=wf.device, dtype=torch.float16)
+    capi.check(_fn('pack_weights', split)(capi.ptr(wf), Nw, O, I, capi.ptr(out, torch.float16), capi.stream()))
     return out
 
 
 COMPOSE_MAX_CIN = 64      # up layers with at most this many input channels run through FIR-composed weights
 
 
-def _pack_up_composed(layer_, w_lat: torch.Tensor) -> torch.Tensor:
+def _pack_up_composed(layer_, w_lat: torch.Tensor, split: bool = False) -> torch.Tensor:
     """Up SynthesisLayer -> FIR-composed packed fp16 weights [Nw,36,O,Ipad] (4 output parities x 3x3 taps)."""
     wf = layer_.folded_weight(w_lat)
     Nw, O, I = wf.shape[:3]
     Ip = (I + 63) // 64 * 64
-    out = torch.empty(Nw, 36, O, Ip, device=wf.device, dtype=torch.float16)
-    capi.check(capi.lib().r3dp_sr_tc_pack_weights_up_composed(capi.ptr(wf), Nw, O, I, capi.ptr(out, torch.float16), capi.stream()))
+    out = torch.empty(Nw, 36, O, Ip * (2 if split else 1), device=wf.device, dtype=torch.float16)
+    capi.check(_fn('pack_weights_up_composed', split)(capi.ptr(wf), Nw, O, I, capi.ptr(out, torch.float16), capi.stream()))
     return out
 
 
-def pack_for(layer_, w_lat: torch.Tensor) -> torch.Tensor:
+def pack_for(layer_, w_lat: torch.Tensor, split: bool = False) -> torch.Tensor:
     if layer_.up == 2 and layer_.in_channels <= COMPOSE_MAX_CIN:
-        return _pack_up_composed(layer_, w_lat)
-    return _pack(layer_, w_lat)
+        return _pack_up_composed(layer_, w_lat, split)
+    return _pack(layer_, w_lat, split)
 
 
-def layer(x16: torch.Tensor, lay, wp: torch.Tensor, up: int) -> torch.Tensor:
-    """x16 [N,H,W,Ipad] fp16 NHWC -> [N,H*up,W*up,O] fp16 NHWC."""
+def layer(x16: torch.Tensor, lay, wp: torch.Tensor, up: int, split: bool = False) -> torch.Tensor:
+    """x16 [N,H,W,Ipad] fp16 NHWC -> [N,H*up,W*up,O] fp16 NHWC (channel dims doubled = [hi | lo] halves when split)."""
     N, H, W, _ = x16.shape
     O, Nw = lay.out_channels, wp.shape[0]
-    L = capi.lib()
-    y = torch.empty(N, H * up, W * up, O, device=x16.device, dtype=torch.float16)
+    y = torch.empty(N, H * up, W * up, O * (2 if split else 1), device=x16.device, dtype=torch.float16)
     if up == 2 and wp.shape[1] == 36:                             # FIR-composed weights
         with capi.region('sr_conv'):
-            capi.check(L.r3dp_sr_tc_layer_up_composed(capi.ptr(x16, torch.float16), capi.ptr(wp, torch.float16), capi.ptr(capi.f32(lay.bias)), N, Nw,
-                                                      lay.in_channels, O, H, W, capi.ptr(y, torch.float16), capi.stream()))
+            capi.check(_fn('layer_up_composed', split)(capi.ptr(x16, torch.float16), capi.ptr(wp, torch.float16), capi.ptr(capi.f32(lay.bias)), N, Nw,
+                                                       lay.in_channels, O, H, W, capi.ptr(y, torch.float16), capi.stream()))
         return y
     scratch = None
     if up == 2:
-        scratch = torch.empty(L.r3dp_sr_tc_scratch_bytes(N, O, H, W), device=x16.device, dtype=torch.uint8)
+        scratch = torch.empty(_fn('scratch_bytes', split)(N, O, H, W), device=x16.device, dtype=torch.uint8)
     with capi.region('sr_conv'):
-        capi.check(L.r3dp_sr_tc_layer(capi.ptr(x16, torch.float16), capi.ptr(wp, torch.float16), capi.ptr(capi.f32(lay.bias)), N, Nw,
-                                      lay.in_channels, O, H, W, up, capi.ptr(y, torch.float16), capi.ptr(scratch, torch.uint8), capi.stream()))
+        capi.check(_fn('layer', split)(capi.ptr(x16, torch.float16), capi.ptr(wp, torch.float16), capi.ptr(capi.f32(lay.bias)), N, Nw,
+                                       lay.in_channels, O, H, W, up, capi.ptr(y, torch.float16), capi.ptr(scratch, torch.uint8), capi.stream()))
     return y
 
 
-def to_nhwc_f16(x: torch.Tensor, size: int) -> torch.Tensor:
+def to_nhwc_f16(x: torch.Tensor, size: int, split: bool = False) -> torch.Tensor:
     """fp32 NCHW [N,C,h,w] -> (bilinear to size) -> NHWC fp16 [N,size,size,Cpad]."""
     x = capi.f32(x)
     N, Cc, h, w = x.shape
     Cp = (Cc + 63) // 64 * 64
-    y = torch.empty(N, size, size, Cp, device=x.device, dtype=torch.float16)
-    capi.check(capi.lib().r3dp_sr_tc_input(capi.ptr(x), N, Cc, h, w, size, capi.ptr(y, torch.float16), capi.stream()))
+    y = torch.empty(N, size, size, Cp * (2 if split else 1), device=x.device, dtype=torch.float16)
+    capi.check(_fn('input', split)(capi.ptr(x), N, Cc, h, w, size, capi.ptr(y, torch.float16), capi.stream()))
     return y
 
 
@@ -112,12 +116,13 @@ def _sblocks(sr):
 
 class Prepared:
     """Folded + packed weights of the four conv layers and the two ToRGB layers for a given set of styles."""
-    __slots__ = ('wp', 'wrgb0', 'wrgb1', 'Nw')
+    __slots__ = ('wp', 'wrgb0', 'wrgb1', 'Nw', 'split')
 
-    def __init__(self, sr, wsel: torch.Tensor):
+    def __init__(self, sr, wsel: torch.Tensor, split: bool = False):
         b0, b1 = _sblocks(sr)
-        self.Nw = wsel.shape[0]
-        self.wp = [pack_for(b0.conv0, wsel[:, 0]), pack_for(b0.conv1, wsel[:, 1]), pack_for(b1.conv0, wsel[:, 0]), pack_for(b1.conv1, wsel[:, 1])]
+        self.Nw, self.split = wsel.shape[0], bool(split)
+        self.wp = [pack_for(b0.conv0, wsel[:, 0], split), pack_for(b0.conv1, wsel[:, 1], split), pack_for(b1.conv0, wsel[:, 0], split),
+                   pack_for(b1.conv1, wsel[:, 1], split)]
         self.wrgb0, self.wrgb1 = b0.torgb.folded_weight(wsel[:, 2]), b1.torgb.folded_weight(wsel[:, 2])
 
 
@@ -132,34 +137,40 @@ def forward(sr, rgb: torch.Tensor, x: torch.Tensor, ws3: torch.Tensor, shared_st
     from .superresolution import SuperresolutionHybrid8XDC
     L = capi.lib()
     N = x.shape[0]
+    split = getattr(sr, 'sr_mode', 'tc') == 'tc_exact'          # fp32-grade: split fp16 operands, three MMAs per product
+    wide = 2 if split else 1
+    if split and getattr(sr, 'large_sr', False):
+        raise NotImplementedError("large_sr runs with sr_mode='tc' (its residual epilogue is not built for split operands)")
     prep = getattr(sr, 'static_prepared', None)
+    if prep is not None and prep.split != split:
+        prep = None
     with capi.region('sr_prep'):
         if prep is None:
             if shared_styles is None:
                 shared_styles = N == 1 or getattr(sr, 'assume_shared_styles', False)
-            prep = Prepared(sr, ws3[:1] if shared_styles else ws3)
+            prep = Prepared(sr, ws3[:1] if shared_styles else ws3, split)
         if x_nhwc is not None:
             xn = capi.f32(x_nhwc)
             _, h, w, Cc = xn.shape
-            x0 = torch.empty(N, sr.input_resolution, sr.input_resolution, (Cc + 63) // 64 * 64, device=xn.device, dtype=torch.float16)
-            capi.check(L.r3dp_sr_tc_input_nhwc(capi.ptr(xn), N, Cc, h, w, sr.input_resolution, capi.ptr(x0, torch.float16), capi.stream()))
+            x0 = torch.empty(N, sr.input_resolution, sr.input_resolution, (Cc + 63) // 64 * 64 * wide, device=xn.device, dtype=torch.float16)
+            capi.check(_fn('input_nhwc', split)(capi.ptr(xn), N, Cc, h, w, sr.input_resolution, capi.ptr(x0, torch.float16), capi.stream()))
         else:
-            x0 = to_nhwc_f16(x, sr.input_resolution)
+            x0 = to_nhwc_f16(x, sr.input_resolution, split)
         rgb0 = SuperresolutionHybrid8XDC._resize(rgb, sr.input_resolution) if rgb.shape[-1] != sr.input_resolution else capi.f32(rgb)
     (b0, b1), Nw, wp = _sblocks(sr), prep.Nw, prep.wp
-    a0 = layer(x0, b0.conv0, wp[0], 2)
-    a1 = torch.empty(N, 256, 256, 256, device=x.device, dtype=torch.float16)
+    a0 = layer(x0, b0.conv0, wp[0], 2, split)
+    a1 = torch.empty(N, 256, 256, 256 * wide, device=x.device, dtype=torch.float16)
     img1 = torch.empty(N, 3, 256, 256, device=x.device)
     with capi.region('sr_conv'):                               # block0.conv1 + block0.torgb (+ upsampled skip) in one kernel
-        capi.check(L.r3dp_sr_tc_layer_torgb(capi.ptr(a0, torch.float16), capi.ptr(wp[1], torch.float16), capi.ptr(capi.f32(b0.conv1.bias)),
+        capi.check(_fn('layer_torgb', split)(capi.ptr(a0, torch.float16), capi.ptr(wp[1], torch.float16), capi.ptr(capi.f32(b0.conv1.bias)),
                                             capi.ptr(prep.wrgb0), capi.ptr(capi.f32(b0.torgb.bias)), capi.ptr(rgb0), N, Nw, 256, 256, 256, 256,
                                             capi.ptr(a1, torch.float16), capi.ptr(img1), capi.stream()))
     if getattr(sr, 'large_sr', False):
         return _forward_large_tail(sr, a1, img1, prep, out_clamp, out_uint8)
-    a2 = layer(a1, b1.conv0, wp[2], 2)
+    a2 = layer(a1, b1.conv0, wp[2], 2, split)
     out = torch.empty(N, 512, 512, 3, device=x.device, dtype=torch.uint8) if out_uint8 else torch.empty(N, 3, 512, 512, device=x.device)
     with capi.region('sr_conv'):                               # block1.conv1 + block1.torgb: the 128-channel activation is never written
-        capi.check(L.r3dp_sr_tc_last_layer_ex(capi.ptr(a2, torch.float16), capi.ptr(wp[3], torch.float16), capi.ptr(capi.f32(b1.conv1.bias)),
+        capi.check((L.r3dp_sr_tcx_last_layer if split else L.r3dp_sr_tc_last_layer_ex)(capi.ptr(a2, torch.float16), capi.ptr(wp[3], torch.float16), capi.ptr(capi.f32(b1.conv1.bias)),
                                               capi.ptr(prep.wrgb1), capi.ptr(capi.f32(b1.torgb.bias)), capi.ptr(img1), N, Nw, 128, 512, 512,
                                               None if out_uint8 else capi.ptr(out), capi.ptr(out, torch.uint8) if out_uint8 else None,
                                               int(out_clamp or out_uint8), capi.stream()))

@@ -182,7 +182,7 @@ class SuperresolutionHybrid8XDC(torch.nn.Module):
         assert img_resolution == 512
         if sr_num_fp16_res > 0:
             raise NotImplementedError('Real3D-Portrait runs the SR with sr_num_fp16_res=0 (img2plane_baseline.py:102)')
-        assert sr_mode in ('fp32', 'tc')
+        assert sr_mode in ('fp32', 'tc', 'tc_exact')      # tc_exact: tensor cores with split fp16 operands, fp32-grade results
         self.sr_mode = sr_mode
         self.large_sr = bool(large_sr)
         self.input_resolution = 128
@@ -217,13 +217,13 @@ class SuperresolutionHybrid8XDC(torch.nn.Module):
         """rgb [N,3,h,w], x [N,channels,h,w], ws [N,>=1,512] -> [N,3,512,512]   (superresolution.py:348-359)."""
         x_nhwc = block_kwargs.pop('x_nhwc', None)          # optional: the same features channels-last (tensor-core path only)
         out_clamp, out_uint8 = bool(block_kwargs.pop('out_clamp', False)), bool(block_kwargs.pop('out_uint8', False))
-        if (out_clamp or out_uint8) and self.sr_mode != 'tc':
+        if (out_clamp or out_uint8) and self.sr_mode not in ('tc', 'tc_exact'):
             raise NotImplementedError('fused clamp / uint8 output is an option of the tensor-core SR path')
         block_kwargs = {k: v for k, v in block_kwargs.items() if k != 'sr_mode'}
         ws = ws[:, -1:, :].repeat(1, 3, 1)
         if x.shape[-1] > self.input_resolution:
             raise NotImplementedError('down-scaling inputs (antialiased) is not on the Real3D path')
-        if self.sr_mode == 'tc':
+        if self.sr_mode in ('tc', 'tc_exact'):
             from . import sr_tc
             return sr_tc.forward(self, rgb, x, ws, x_nhwc=x_nhwc, out_clamp=out_clamp, out_uint8=out_uint8)
         if x.shape[-1] != self.input_resolution:

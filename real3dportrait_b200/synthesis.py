@@ -65,7 +65,7 @@ class RenderHead(torch.nn.Module):
         out_uint8 = bool(render_overrides.pop('out_uint8', False))
         opts = dict(self.rendering_kwargs, **render_overrides)
         feat, depth, wsum, valid = self.renderer(planes, self.decoder, ray_o, ray_d, opts)
-        if lean and not self.torso and self.superresolution.sr_mode == 'tc' and not self.hparams.get('mask_invalid_rays', False):
+        if lean and not self.torso and self.superresolution.sr_mode in ('tc', 'tc_exact') and not self.hparams.get('mask_invalid_rays', False):
             # frame-loop fast path (FrameEngine): only ret['image'] is wanted, so the NCHW copies of the feature / weight images, the
             # clamped raw image and the per-call ones_ws are not materialised; the SR reads the renderer's channels-last output directly
             x_nhwc = feat.view(N, res, res, feat.shape[-1])
@@ -93,7 +93,7 @@ class RenderHead(torch.nn.Module):
                                                          cond['segmap'], cond['kp_s'], cond['kp_d'], cond.get('target_torso_mask'), noise_mode='none')
             ret.update(facev2v_ret)
         else:
-            extra = {'x_nhwc': feat.view(N, res, res, feat.shape[-1])} if self.superresolution.sr_mode == 'tc' else {}
+            extra = {'x_nhwc': feat.view(N, res, res, feat.shape[-1])} if self.superresolution.sr_mode in ('tc', 'tc_exact') else {}
             sr_image = self.superresolution(rgb_image, feature_image, ones_ws, noise_mode='none', **extra)
         ret.update({'image_raw': rgb_image.clamp(-1, 1), 'image_depth': depth_image, 'image': sr_image.clamp(-1, 1),
                     'image_feature': feature_image[:, 3:], 'plane': planes, 'is_ray_valid': valid})

@@ -228,6 +228,9 @@ int r3dp_sr_tc_layer_torgb(const void* x_f16, const void* wp_f16, const float* b
                            r3dp_stream_t stream);
 /* r3dp_sr_tc_input for a channels-last fp32 source [N,h,w,C] (the renderer's [N,M,C] output viewed as an image). */
 int r3dp_sr_tc_input_nhwc(const float* x_nhwc, int N, int C, int h, int w, int size, void* y_f16, r3dp_stream_t stream);
+/* ... and rgb_out [N,3,size,size] fp32 = the same resize of channels 0..2 (`rgb_image = feature_image[:, :3]`, secc_img2plane.py:126) in the same
+ * launch; split != 0 writes the [hi | lo] activation layout of the r3dp_sr_tcx_* path. */
+int r3dp_sr_tc_input_nhwc_rgb(const float* x_nhwc, int N, int C, int h, int w, int size, void* y_f16, float* rgb_out, int split, r3dp_stream_t stream);
 int r3dp_sr_tc_last_layer(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
                           const float* img_prev, int N, int Nw, int I, int H, int W, float* img_out, r3dp_stream_t stream);
 /* The same with the caller loop's output conversion fused into the epilogue (inference/real3d_infer.py:515-519):

@@ -85,6 +85,7 @@ _SIGNATURES = {
     'r3dp_sr_tc_layer_up_composed': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     'r3dp_sr_tc_layer_torgb': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'r3dp_sr_tc_input_nhwc': (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    'r3dp_sr_tc_input_nhwc_rgb': (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     'r3dp_sr_tc_conv': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'r3dp_sr_tc_conv_res': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'r3dp_sr_tc_torgb_ex': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),

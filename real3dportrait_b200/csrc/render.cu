@@ -22,8 +22,12 @@ __global__ void mlp_to_const_kernel(const r3dp_mlp_t m, MlpConst* dst) {
 
 
 
-__global__ void mlp_to_tc_kernel(const r3dp_mlp_t m, MlpTcImage* dst) {
+struct RenderWs;
+__device__ __forceinline__ void init_ws(RenderWs* ws);
+// decoder operand image for tcgen05 (+ the call's workspace header, so that a render needs one set-up launch instead of two)
+__global__ void mlp_to_tc_kernel(const r3dp_mlp_t m, MlpTcImage* dst, RenderWs* ws) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    if (tid == 0 && ws != nullptr) init_ws(ws);
     const float g1 = 0.17677669529663687f, g2 = 0.125f;        // 1/sqrt(32), 1/sqrt(64)  (networks_stylegan2.py:113)
     for (int i = tid; i < kHidden * kC; i += nt) {
         const int j = i / kC, c = i - j * kC;
@@ -46,9 +50,10 @@ constexpr int kTcThreads = 256;                          // 8 warps: TMEM lane q
 constexpr int kTcMaxTiles = 3;                           // 128-sample tiles per pass (TMEM: 64 columns each)
 constexpr int kTcA1Bytes = 51200;                        // 3 x 16 KB A1 tiles; later the [R*ST][33] fp32 decoded rows (<= 384 x 132 B)
 constexpr int kTcA2Bytes = 32768;                        // two 16 KB atoms; before the decode: tap descriptors [nsamp][16]; after: march scratch
-__global__ void init_ws_kernel(RenderWs* ws) {
+__device__ __forceinline__ void init_ws(RenderWs* ws) {
     ws->t0_min = 0xffffffffu; ws->t0_max = 0u; ws->d_min = 0xffffffffu; ws->d_max = 0u; ws->n_valid = 0u;
 }
+__global__ void init_ws_kernel(RenderWs* ws) { init_ws(ws); }
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void gen_rays_kernel(const float* __restrict__ c2w, const float* __restrict__ K, int N, int res,
@@ -630,9 +635,7 @@ template <int R>
 static int launch_render_tc(const RenderArgs& a, cudaStream_t st) {
     const size_t smem = render_tc_smem(R, a.S, a.S_imp);
     R3DP_CUDA(cudaFuncSetAttribute(render_kernel<R, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_to_tc_kernel<<<4, 256, 0, st>>>(a.mlp, const_cast<MlpTcImage*>(a.image));
-    count_launches(1);
-    dim3 grid(a.tiles_per_frame, a.N);
+    dim3 grid(a.tiles_per_frame, a.N);                     // (the decoder image was written by r3dp_render_ex's set-up launch)
     render_kernel<R, true, false, true><<<grid, kTcThreads, smem, st>>>(a);
     R3DP_LAUNCH_CHECK();
     return 0;
@@ -745,7 +748,8 @@ extern "C" int r3dp_render_ex(const r3dp_render_args_t* g, r3dp_stream_t stream)
     char* wsb = reinterpret_cast<char*>(g->workspace);
     RenderWs* ws = reinterpret_cast<RenderWs*>(wsb);
     float2* limits = reinterpret_cast<float2*>(wsb + kWsLimitsOff);
-    init_ws_kernel<<<1, 1, 0, st>>>(ws);
+    if (mlp_variant() == 2) mlp_to_tc_kernel<<<4, 256, 0, st>>>(*g->mlp, reinterpret_cast<MlpTcImage*>(wsb + kWsImageOff), ws);      // + workspace header
+    else init_ws_kernel<<<1, 1, 0, st>>>(ws);
     const int total = N * M;
     ray_limits_kernel<<<(total + 255) / 256, 256, 0, st>>>(g->ray_o, g->ray_d, g->camera, res, N, M, g->box_warp, limits, g->is_ray_valid, ws);
     R3DP_LAUNCH_CHECK();
@@ -764,8 +768,6 @@ extern "C" int r3dp_render_ex(const r3dp_render_args_t* g, r3dp_stream_t stream)
     a.lookahead = render_lookahead();
     int rc;
     if (render_variant() == 0 && mlp_variant() == 2 && render_stream_fits(a)) {
-        mlp_to_tc_kernel<<<4, 256, 0, st>>>(a.mlp, const_cast<MlpTcImage*>(a.image));
-        count_launches(1);
         rc = launch_render_stream(a, st);
     } else {
         const int R = ST <= 48 ? 8 : ST <= 96 ? 4 : ST <= 192 ? 2 : 1;

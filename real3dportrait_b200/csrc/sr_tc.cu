@@ -18,6 +18,7 @@
 #include "tc_prims.cuh"
 #include <mutex>
 #include <vector>
+#include <type_traits>
 #include <stdlib.h>
 
 #ifndef R3DP_TC_DEBUG_TIMING
@@ -96,6 +97,7 @@ struct Conv2Args {
     uint8_t* img_out_u8;            // non-null: final image as uint8 HWC frames [N][H][W][3] = int((clamp(x)+1)/2*255) (real3d_infer.py:519) instead of fp32 NCHW
     int split;                      // fp32-grade operands: activations [hi | lo] (2 x Cin_pad channels), weights [hi | lo]; K loop = hi*hi + lo*hi + hi*lo
     int lo_off;                     // split: channel offset of the lo half in the OUTPUT tensor (= logical output channels); out_C is the physical pixel stride
+    int phase_mix;                  // interleave the phases of a multi-phase launch over the units (see decode)
     float acc_scale;                // accumulator scale applied before the bias (split weights are stored x 2^10 so their lo halves stay normal fp16)
     unsigned long long* debug;      // R3DP_TC_DEBUG_TIMING builds: [acc wait, strip wait, tap wait, issue, total, #CTAs] clock sums of the MMA warp
 };
@@ -227,7 +229,7 @@ __device__ __forceinline__ void tc_mma_f16_2sm(uint32_t tmem_d, uint64_t desc_a,
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-template <int R>
+template <int R, bool SPLIT>
 __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB, const Conv2Args a) {
     using C = Cfg3<R>;
@@ -277,10 +279,16 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
 
     // unit index -> (image n, phase, row group, x block); x fastest so neighbouring CTAs share strips in L2
+    // Multi-phase launches with an even number of x blocks (the 4/2/2/1-tap phases of a transposed conv at W = 256): phases are interleaved,
+    // slot = rg * n_phases + p' with ph = (p' + rg) mod n_phases, so that at any moment the CTA pairs are spread over all phases (the 1- and
+    // 2-tap phases need 60-80 B/clk/SM of operands, above the L2 share of an SM, the 4-tap phase 40) and every pair sees every phase.
+    const bool mix = a.phase_mix && a.n_phases > 1 && (a.tiles_x & 1) == 0;
     auto decode = [&](int unit, int& n, int& ph, int& row0, int& col0) {
         n = unit / units_per_image; int r = unit - n * units_per_image;
         const int xb = r % a.tiles_x; r /= a.tiles_x;
-        const int rg = r % a.row_groups; ph = r / a.row_groups;
+        int rg;
+        if (mix) { rg = r / a.n_phases; ph = (r - rg * a.n_phases + rg) % a.n_phases; }
+        else { rg = r % a.row_groups; ph = r / a.row_groups; }
         row0 = rg * R; col0 = xb * BM;
     };
 
@@ -293,7 +301,7 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                 const Taps2& tp = a.ph[ph].taps;
                 const int DY = tp.ngroups;
                 const int wn = a.w_shared ? 0 : n;
-                const int K3 = a.split ? 3 * a.k_chunks : a.k_chunks;             // split: [x_hi w_hi | x_lo w_hi | x_hi w_lo] over the channel chunks
+                const int K3 = SPLIT ? 3 * a.k_chunks : a.k_chunks;               // split: [x_hi w_hi | x_lo w_hi | x_hi w_lo] over the channel chunks
                 for (int nblk = 0; nblk < a.n_blocks; ++nblk)
                     for (int kq = 0; kq < K3; ++kq) {
                         const int kc = kq < 2 * a.k_chunks ? kq : kq - 2 * a.k_chunks;    // activation chunk: hi, lo (at k_chunks + c), hi again
@@ -339,7 +347,7 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                 tc_fence_after();
                 DT_END(t_acc);
                 const uint32_t acc0 = tmem_base + buf * (R * BN);
-                const int K3 = a.split ? 3 * a.k_chunks : a.k_chunks;
+                const int K3 = SPLIT ? 3 * a.k_chunks : a.k_chunks;
                 for (int kc = 0; kc < K3; ++kc) {
                     const uint32_t a_base = aq;                               // sequence number of strip 0 of this chunk
                     for (int d = 0; d < DY; ++d) {
@@ -498,14 +506,18 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                         const float2 sc2 = make_float2(a.acc_scale, a.acc_scale);
                         if (a.mode == kStoreRaw) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) f2[i] = mul2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2);
+                            for (int i = 0; i < 16; ++i) {
+                                f2[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                                if (SPLIT) f2[i] = mul2(f2[i], sc2);
+                            }
                         } else {
                             // bias, leaky relu as max(v, v*slope) (slope <= 1), gain: bias_act lrelu*sqrt2 | nn.LeakyReLU | linear
                             const float2* b2 = reinterpret_cast<const float2*>(s_bias + nblk * BN + c0);
                             const float2 sl2 = make_float2(a.act_slope, a.act_slope), g2 = make_float2(a.act_gain, a.act_gain);
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
-                                const float2 v = fma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, b2[i]);
+                                const float2 acc2 = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                                const float2 v = SPLIT ? fma2(acc2, sc2, b2[i]) : add2(acc2, b2[i]);
                                 const float2 t = mul2(v, sl2);
                                 f2[i] = mul2(make_float2(fmaxf(v.x, t.x), fmaxf(v.y, t.y)), g2);
                             }
@@ -517,7 +529,8 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                             // Split mode: a second pass stores the fp16 remainders (v - fp16(v)) lo_off channels further.
                             uint4* st = s_stage + (warp - 2) * 128;
                             const int sw = (lane >> 1) & 3;
-                            const int passes = a.split ? 2 : 1;
+                            constexpr int passes = SPLIT ? 2 : 1;
+#pragma unroll
                             for (int pass = 0; pass < passes; ++pass) {
                                 if (pass == 0) {
 #pragma unroll
@@ -727,7 +740,8 @@ __global__ void __launch_bounds__(256) upconv_edge_kernel(const __half* __restri
 // into shared memory with ONE TMA instruction each (double-buffered on mbarriers; the box is zero-filled outside the image,
 // which IS the FIR's zero padding), then 256 threads (32 px x 8 channel-vectors) march down the tile: 4 swizzled LDS.128 per
 // input row -> horizontal taps -> 4-row register window -> vertical taps, bias, lrelu -> one 16-byte store per output row.
-constexpr int FIR_TW = 32, FIR_TH = 8, FIR_BW = FIR_TW + 3, FIR_BH = FIR_TH + 3;
+constexpr int FIR_TW = 32, FIR_TH = 8, FIR_SEG = 32, FIR_BW = FIR_TW + 3, FIR_BH = FIR_TH + 3;
+constexpr int FIR_BOX8_BYTES = FIR_BW * FIR_TH * 128;
 constexpr int FIR_BOX_BYTES = FIR_BW * FIR_BH * 128, FIR_SLOT = (FIR_BOX_BYTES + 1023) / 1024 * 1024;
 constexpr int FIR_SMEM = 2 * FIR_SLOT + 1024 + 64;
 // packed 2 x fp32 FMA (sm_100 fma.rn.f32x2): (d0,d1) += (a0,a1) * (b0,b1)
@@ -738,99 +752,116 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
         "mov.b64 {%0, %1}, rc;\n\t}"
         : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
+// Work item = a strip of FIR_TW px x FIR_SEG output rows of one 64-channel group, streamed as FIR_SEG / FIR_TH chunks: the first box has the
+// 3 halo rows (35 px x 11 rows), the following boxes only new rows (35 x 8) - the 4-row register window simply keeps rolling across the
+// chunks, so only 35 input rows are loaded and converted per 32 output rows (ncu on the one-box-per-tile form: 386 MB read for 270 MB of
+// input, the vertical halo rows came from DRAM twice).
 template <bool SPLIT>
-__global__ void __launch_bounds__(256) fir_tma_kernel(const __grid_constant__ CUtensorMap tmY, const float* __restrict__ bias, int N, int OH,
-                                                      int OW, int C, __half* __restrict__ y) {
+__global__ void __launch_bounds__(256) fir_tma_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmY8,
+                                                      const float* __restrict__ bias, int N, int OH, int OW, int C, __half* __restrict__ y) {
     // SPLIT: yb and y hold [hi | lo] fp16 halves of C channels each (fp32-grade path): both halves of a tile are loaded, summed in fp32,
     // filtered, and the result is split again
     constexpr int NSL = SPLIT ? 2 : 1;
+    constexpr int NCH = FIR_SEG / FIR_TH;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem_1024(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * NSL * FIR_SLOT);
     const int tid = threadIdx.x, px = tid >> 3, c8 = tid & 7;
-    const int tiles_x = OW / FIR_TW, tiles_y = (OH + FIR_TH - 1) / FIR_TH, cgs = C / 64;
-    const int total = N * cgs * tiles_y * tiles_x;
+    const int tiles_x = OW / FIR_TW, segs = (OH + FIR_SEG - 1) / FIR_SEG, cgs = C / 64;
+    const int total = N * cgs * segs * tiles_x;
+    const int my_items = (int)blockIdx.x < total ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int nseq = my_items * NCH;
     const int CS = SPLIT ? 2 * C : C;                                      // physical channels per pixel
     if (tid == 0) {
         mbar_init(&full[0], 1); mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY8) : "memory");
     }
     __syncthreads();
-    auto issue = [&](int tile, int buf) {
-        const int tx = tile % tiles_x; int r = tile / tiles_x;
-        const int ty = r % tiles_y; r /= tiles_y;
-        const int cg = r % cgs, n = r / cgs;
-        mbar_expect_tx(&full[buf], NSL * FIR_BOX_BYTES);
-        tma_load_4d(smem + buf * NSL * FIR_SLOT, &tmY, &full[buf], cg * 64, tx * FIR_TW - 1, ty * FIR_TH - 1, n);
-        if (SPLIT) tma_load_4d(smem + (buf * NSL + 1) * FIR_SLOT, &tmY, &full[buf], C + cg * 64, tx * FIR_TW - 1, ty * FIR_TH - 1, n);
+    auto item_of = [&](int s, int& tx, int& sg, int& cg, int& n) {
+        int r = blockIdx.x + (s / NCH) * gridDim.x;
+        tx = r % tiles_x; r /= tiles_x;
+        sg = r % segs; r /= segs;
+        cg = r % cgs; n = r / cgs;
+    };
+    auto issue = [&](int s, int buf) {
+        int tx, sg, cg, n; item_of(s, tx, sg, cg, n);
+        const int c = s % NCH;
+        const int y0 = sg * FIR_SEG - 1 + (c == 0 ? 0 : FIR_BH + FIR_TH * (c - 1));
+        const CUtensorMap* map = c == 0 ? &tmY : &tmY8;
+        mbar_expect_tx(&full[buf], NSL * (c == 0 ? FIR_BOX_BYTES : FIR_BOX8_BYTES));
+        tma_load_4d(smem + buf * NSL * FIR_SLOT, map, &full[buf], cg * 64, tx * FIR_TW - 1, y0, n);
+        if (SPLIT) tma_load_4d(smem + (buf * NSL + 1) * FIR_SLOT, map, &full[buf], C + cg * 64, tx * FIR_TW - 1, y0, n);
     };
     if (tid == 0) {
-        if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
-        if ((int)(blockIdx.x + gridDim.x) < total) issue(blockIdx.x + gridDim.x, 1);
+        if (nseq > 0) issue(0, 0);
+        if (nseq > 1) issue(1, 1);
     }
     const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const int tx = tile % tiles_x; int r = tile / tiles_x;
-        const int ty = r % tiles_y; r /= tiles_y;
-        const int cg = r % cgs, n = r / cgs;
-        float b[8];
+    float win[4][8];
+    float b[8];
+    for (int s = 0; s < nseq; ++s) {
+        const int buf = s & 1, c = s % NCH;
+        int tx, sg, cg, n; item_of(s, tx, sg, cg, n);
+        if (c == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) b[j] = bias[cg * 64 + c8 * 8 + j];
-        mbar_wait(&full[buf], (it >> 1) & 1);
+            for (int j = 0; j < 8; ++j) b[j] = bias[cg * 64 + c8 * 8 + j];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) win[rr][j] = 0.f;
+        }
+        mbar_wait(&full[buf], (s >> 1) & 1);
         const uint8_t* sb = smem + buf * NSL * FIR_SLOT;
-        float win[4][8];
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) win[rr][j] = 0.f;
         const int ox = tx * FIR_TW + px;
+        const int gy0 = c == 0 ? 0 : FIR_BH + FIR_TH * (c - 1);            // index of this box's first row inside the item's 35 input rows
+        auto rows = [&](auto nrows_tag) {
+            constexpr int NROWS = decltype(nrows_tag)::value;
 #pragma unroll
-        for (int ry = 0; ry < FIR_BH; ++ry) {
+            for (int ry = 0; ry < NROWS; ++ry) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { win[0][j] = win[1][j]; win[1][j] = win[2][j]; win[2][j] = win[3][j]; win[3][j] = 0.f; }
+                for (int j = 0; j < 8; ++j) { win[0][j] = win[1][j]; win[1][j] = win[2][j]; win[2][j] = win[3][j]; win[3][j] = 0.f; }
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const int row = ry * FIR_BW + px + v;                            // 128-byte row of the box; swizzle = chunk ^ (row & 7)
-                const uint4 raw = *reinterpret_cast<const uint4*>(sb + row * 128 + ((c8 ^ (row & 7)) << 4));
-                const __half2* h = reinterpret_cast<const __half2*>(&raw);
-                uint4 rawl = make_uint4(0, 0, 0, 0);
-                if (SPLIT) rawl = *reinterpret_cast<const uint4*>(sb + FIR_SLOT + row * 128 + ((c8 ^ (row & 7)) << 4));
-                const __half2* hl = reinterpret_cast<const __half2*>(&rawl);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float2 f = __half22float2(h[j]);
-                    if (SPLIT) { const float2 g = __half22float2(hl[j]); f.x += g.x; f.y += g.y; }
-                    ffma2(win[3][2 * j], win[3][2 * j + 1], k4[v], k4[v], f.x, f.y);      // packed f32x2: the kernel is issue-bound
-                }
-            }
-            if (ry >= 3) {
-                const int oy = ty * FIR_TH + ry - 3;
-                if (oy < OH) {
-                    uint4 pk; __half2* ph = reinterpret_cast<__half2*>(&pk);
-                    uint4 pl; __half2* pq = reinterpret_cast<__half2*>(&pl);
+                for (int v = 0; v < 4; ++v) {
+                    const int row = ry * FIR_BW + px + v;                        // 128-byte row of the box; swizzle = chunk ^ (row & 7)
+                    const uint4 raw = *reinterpret_cast<const uint4*>(sb + row * 128 + ((c8 ^ (row & 7)) << 4));
+                    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+                    uint4 rawl = make_uint4(0, 0, 0, 0);
+                    if (SPLIT) rawl = *reinterpret_cast<const uint4*>(sb + FIR_SLOT + row * 128 + ((c8 ^ (row & 7)) << 4));
+                    const __half2* hl = reinterpret_cast<const __half2*>(&rawl);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        float a0 = b[2 * j], a1 = b[2 * j + 1];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) ffma2(a0, a1, k4[u], k4[u], win[u][2 * j], win[u][2 * j + 1]);
-                        a0 = (a0 < 0.f ? a0 * 0.2f : a0) * 1.4142135623730951f; a1 = (a1 < 0.f ? a1 * 0.2f : a1) * 1.4142135623730951f;
-                        ph[j] = __floats2half2_rn(a0, a1);
-                        if (SPLIT) { const float2 hf = __half22float2(ph[j]); pq[j] = __floats2half2_rn(a0 - hf.x, a1 - hf.y); }
+                        float2 f = __half22float2(h[j]);
+                        if (SPLIT) { const float2 g = __half22float2(hl[j]); f.x += g.x; f.y += g.y; }
+                        ffma2(win[3][2 * j], win[3][2 * j + 1], k4[v], k4[v], f.x, f.y);  // packed f32x2: the kernel is issue-bound
                     }
-                    __half* dst = y + (((size_t)n * OH + oy) * OW + ox) * CS + cg * 64 + c8 * 8;
-                    *reinterpret_cast<uint4*>(dst) = pk;
-                    if (SPLIT) *reinterpret_cast<uint4*>(dst + C) = pl;
+                }
+                const int gy = gy0 + ry;
+                if (gy >= 3) {
+                    const int oy = sg * FIR_SEG + gy - 3;
+                    if (oy < OH) {
+                        uint4 pk; __half2* ph = reinterpret_cast<__half2*>(&pk);
+                        uint4 pl; __half2* pq = reinterpret_cast<__half2*>(&pl);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float a0 = b[2 * j], a1 = b[2 * j + 1];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) ffma2(a0, a1, k4[u], k4[u], win[u][2 * j], win[u][2 * j + 1]);
+                            a0 = (a0 < 0.f ? a0 * 0.2f : a0) * 1.4142135623730951f; a1 = (a1 < 0.f ? a1 * 0.2f : a1) * 1.4142135623730951f;
+                            ph[j] = __floats2half2_rn(a0, a1);
+                            if (SPLIT) { const float2 hf = __half22float2(ph[j]); pq[j] = __floats2half2_rn(a0 - hf.x, a1 - hf.y); }
+                        }
+                        __half* dst = y + (((size_t)n * OH + oy) * OW + ox) * CS + cg * 64 + c8 * 8;
+                        *reinterpret_cast<uint4*>(dst) = pk;
+                        if (SPLIT) *reinterpret_cast<uint4*>(dst + C) = pl;
+                    }
                 }
             }
-        }
+        };
+        if (c == 0) rows(std::integral_constant<int, FIR_BH>{}); else rows(std::integral_constant<int, FIR_TH>{});
         __syncthreads();                                                      // everyone is done reading this buffer
-        if (tid == 0) {
-            const int nxt = tile + 2 * gridDim.x;
-            if (nxt < total) issue(nxt, buf);
-        }
+        if (tid == 0 && s + 2 < nseq) issue(s + 2, buf);
     }
 }
 
@@ -958,12 +989,12 @@ static int make_map_4d_box(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_
     return 0;
 }
 
-static int make_map_fir(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3) {
+static int make_map_fir(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     R3DP_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[4] = {d0, d1, d2, d3};
     cuuint64_t strides[3] = {d0 * 2, d0 * d1 * 2, d0 * d1 * d2 * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)FIR_BW, (cuuint32_t)FIR_BH, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)FIR_BW, box_rows, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -994,10 +1025,10 @@ static int tc_rows() {                         // R3DP_TC_ROWS = 1 | 2 | 4 outpu
     return v;
 }
 
-template <int R>
-static int launch_conv3_r(const CUtensorMap& tmA, const CUtensorMap& tmB, Conv2Args a, int max_rows, cudaStream_t st) {
+template <int R, bool SPLIT>
+static int launch_conv3_rs(const CUtensorMap& tmA, const CUtensorMap& tmB, Conv2Args a, int max_rows, cudaStream_t st) {
     using C = Cfg3<R>;
-            R3DP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    R3DP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<R, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     a.debug = g_debug_buf ? g_debug_buf + 24 * (g_debug_launch++ % 32) : nullptr;
     a.row_groups = (max_rows + R - 1) / R;
     if ((a.row_groups * a.tiles_x) & 1) a.row_groups += 1;       // the two CTAs of a pair must work on units of the same (image, phase)
@@ -1011,10 +1042,14 @@ static int launch_conv3_r(const CUtensorMap& tmA, const CUtensorMap& tmB, Conv2A
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     prof_mark(st);
-    R3DP_CUDA(cudaLaunchKernelEx(&cfg, conv_tc3_kernel<R>, tmA, tmB, a));
+    R3DP_CUDA(cudaLaunchKernelEx(&cfg, conv_tc3_kernel<R, SPLIT>, tmA, tmB, a));
     prof_mark(st);
     count_launches(1);
     return 0;
+}
+template <int R>
+static int launch_conv3_r(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv2Args& a, int max_rows, cudaStream_t st) {
+    return a.split ? launch_conv3_rs<R, true>(tmA, tmB, a, max_rows, st) : launch_conv3_rs<R, false>(tmA, tmB, a, max_rows, st);
 }
 
 // taps given as (dy, dx, widx) lists -> sorted/grouped Taps2 (dy groups are contiguous for 3x3 and every transposed-conv phase)
@@ -1046,6 +1081,7 @@ static int run_conv2(const void* x, int N, int H, int W, int Cp, const void* wp,
     if (a.split) { R3DP_REQUIRE(a.residual == nullptr, "conv_tc3: the residual epilogue is not built for split operands"); a.acc_scale = 1.0f / kSplitWeightScale; a.lo_off = a.out_C; a.out_C *= 2; }
     else { a.acc_scale = 1.0f; a.lo_off = 0; }
     a.k_chunks = Cp / BK; a.tiles_x = W / BM; a.n_blocks = O / BN; a.n_images = N; a.w_shared = (Nw == 1);
+    { static int mixv = -1; if (mixv < 0) { const char* e = getenv("R3DP_TC_MIX"); mixv = (e && e[0] == '0') ? 0 : 1; } a.phase_mix = mixv; }      // A/B knob
     if (a.act_gain == 0.f) { a.act_slope = 0.2f; a.act_gain = 1.4142135623730951f; }      // default: bias_act lrelu
     R3DP_REQUIRE(a.n_blocks >= 1 && a.n_blocks <= 2, "conv_tc3: 128 or 256 output channels");
     return tc_rows() == 1 ? launch_conv3_r<1>(tmA, tmB, a, max_rows, st) : (tc_rows() == 4 ? launch_conv3_r<4>(tmA, tmB, a, max_rows, st) : launch_conv3_r<2>(tmA, tmB, a, max_rows, st));
@@ -1154,18 +1190,19 @@ static int layer_impl(const void* x_f16, const void* wp_f16, const float* bias, 
     }
     {
         R3DP_REQUIRE((2 * W) % FIR_TW == 0 && O % 64 == 0, "sr_tc_layer: FIR needs 2W %% 32 == 0 and Cout %% 64 == 0");
-        CUtensorMap tmY;
-        if (make_map_fir(&tmY, yb, (uint64_t)O * (split ? 2 : 1), (uint64_t)(2 * W + 1), (uint64_t)(2 * H + 1), (uint64_t)N)) return 1;
-        const int total = N * (O / 64) * ((2 * H + FIR_TH - 1) / FIR_TH) * (2 * W / FIR_TW);
+        CUtensorMap tmY, tmY8;
+        if (make_map_fir(&tmY, yb, (uint64_t)O * (split ? 2 : 1), (uint64_t)(2 * W + 1), (uint64_t)(2 * H + 1), (uint64_t)N, FIR_BH)) return 1;
+        if (make_map_fir(&tmY8, yb, (uint64_t)O * (split ? 2 : 1), (uint64_t)(2 * W + 1), (uint64_t)(2 * H + 1), (uint64_t)N, FIR_TH)) return 1;
+        const int total = N * (O / 64) * ((2 * H + FIR_SEG - 1) / FIR_SEG) * (2 * W / FIR_TW);
         if (split) {
             const int smem = 4 * FIR_SLOT + 1024 + 64;
             R3DP_CUDA(cudaFuncSetAttribute(fir_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             const int grid = total < sm_count() ? total : sm_count();
-            fir_tma_kernel<true><<<grid, 256, smem, st>>>(tmY, bias, N, 2 * H, 2 * W, O, reinterpret_cast<__half*>(y_f16));
+            fir_tma_kernel<true><<<grid, 256, smem, st>>>(tmY, tmY8, bias, N, 2 * H, 2 * W, O, reinterpret_cast<__half*>(y_f16));
         } else {
             R3DP_CUDA(cudaFuncSetAttribute(fir_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIR_SMEM));
             const int grid = total < 2 * sm_count() ? total : 2 * sm_count();
-            fir_tma_kernel<false><<<grid, 256, FIR_SMEM, st>>>(tmY, bias, N, 2 * H, 2 * W, O, reinterpret_cast<__half*>(y_f16));
+            fir_tma_kernel<false><<<grid, 256, FIR_SMEM, st>>>(tmY, tmY8, bias, N, 2 * H, 2 * W, O, reinterpret_cast<__half*>(y_f16));
         }
     }
     R3DP_LAUNCH_CHECK();
@@ -1261,7 +1298,8 @@ extern "C" int r3dp_sr_tcx_layer_torgb(const void* x_f16, const void* wp_f16, co
 
 // bilinear up-resize of a CHANNELS-LAST fp32 image [N,h,w,C] (e.g. the renderer's [N,M,32] output viewed as an image) to
 // NHWC fp16 [N,size,size,Cpad]: one thread = one output pixel x 8 channels.
-__global__ void resize_nhwc_to_f16_kernel(const float* __restrict__ x, int N, int C, int h, int w, int size, int Cp, int split, __half* __restrict__ y) {
+__global__ void resize_nhwc_to_f16_kernel(const float* __restrict__ x, int N, int C, int h, int w, int size, int Cp, int split, __half* __restrict__ y,
+                                          float* __restrict__ rgb_out) {
     const int cv = Cp / 8;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)N * size * size * cv) return;
@@ -1290,6 +1328,10 @@ __global__ void resize_nhwc_to_f16_kernel(const float* __restrict__ x, int N, in
             }
         }
     }
+    if (rgb_out != nullptr && c8 == 0) {                       // channels 0..2 = the raw RGB image the SR takes beside the features (secc_img2plane.py:126), fp32 NCHW
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rgb_out[(((size_t)n * 3 + c) * size + oy) * size + ox] = v[c];
+    }
     uint4 pk; __half2* ph = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
     for (int j = 0; j < 4; ++j) ph[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
@@ -1302,18 +1344,23 @@ __global__ void resize_nhwc_to_f16_kernel(const float* __restrict__ x, int N, in
     *reinterpret_cast<uint4*>(y + pix + Cp + c8 * 8) = pl;
 }
 
-static int input_nhwc_impl(const float* x_nhwc, int N, int C, int h, int w, int size, void* y_f16, int split, r3dp_stream_t stream) {
+static int input_nhwc_impl(const float* x_nhwc, int N, int C, int h, int w, int size, void* y_f16, float* rgb_out, int split, r3dp_stream_t stream) {
     R3DP_REQUIRE(x_nhwc && y_f16, "sr_tc_input_nhwc: null pointer");
     R3DP_REQUIRE(N > 0 && C > 0 && C % 8 == 0 && h > 0 && w > 0 && size >= h && size >= w, "sr_tc_input_nhwc: bad shape (C %% 8 == 0, up-scaling only)");
     const int Cp = (C + 63) / 64 * 64;
     const long long total = (long long)N * size * size * (Cp / 8);
-    resize_nhwc_to_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x_nhwc, N, C, h, w, size, Cp, split, reinterpret_cast<__half*>(y_f16));
+    resize_nhwc_to_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x_nhwc, N, C, h, w, size, Cp, split, reinterpret_cast<__half*>(y_f16), rgb_out);
     R3DP_LAUNCH_CHECK();
     count_launches(1);
     return 0;
 }
-extern "C" int r3dp_sr_tc_input_nhwc(const float* x_nhwc, int N, int C, int h, int w, int size, void* y_f16, r3dp_stream_t stream) { return input_nhwc_impl(x_nhwc, N, C, h, w, size, y_f16, 0, stream); }
-extern "C" int r3dp_sr_tcx_input_nhwc(const float* x_nhwc, int N, int C, int h, int w, int size, void* y_f16, r3dp_stream_t stream) { return input_nhwc_impl(x_nhwc, N, C, h, w, size, y_f16, 1, stream); }
+extern "C" int r3dp_sr_tc_input_nhwc(const float* x_nhwc, int N, int C, int h, int w, int size, void* y_f16, r3dp_stream_t stream) { return input_nhwc_impl(x_nhwc, N, C, h, w, size, y_f16, nullptr, 0, stream); }
+extern "C" int r3dp_sr_tcx_input_nhwc(const float* x_nhwc, int N, int C, int h, int w, int size, void* y_f16, r3dp_stream_t stream) { return input_nhwc_impl(x_nhwc, N, C, h, w, size, y_f16, nullptr, 1, stream); }
+// the same, plus rgb_out [N,3,size,size] fp32 = the bilinear resize of channels 0..2 (the raw RGB image of the render head, secc_img2plane.py:126)
+extern "C" int r3dp_sr_tc_input_nhwc_rgb(const float* x_nhwc, int N, int C, int h, int w, int size, void* y_f16, float* rgb_out, int split, r3dp_stream_t stream) {
+    R3DP_REQUIRE(rgb_out != nullptr && C >= 3, "sr_tc_input_nhwc_rgb: needs rgb_out and at least 3 channels");
+    return input_nhwc_impl(x_nhwc, N, C, h, w, size, y_f16, rgb_out, split != 0, stream);
+}
 
 // ---- composed up-convolution for small Cin -------------------------------------------------------------------------------
 // FIR(conv_transpose(x, w)) == four 3x3 correlations on the low-resolution input, one per output parity (p,q), with weights

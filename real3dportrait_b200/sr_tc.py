@@ -126,8 +126,8 @@ class Prepared:
         self.wrgb0, self.wrgb1 = b0.torgb.folded_weight(wsel[:, 2]), b1.torgb.folded_weight(wsel[:, 2])
 
 
-def forward(sr, rgb: torch.Tensor, x: torch.Tensor, ws3: torch.Tensor, shared_styles: Optional[bool] = None,
-            x_nhwc: Optional[torch.Tensor] = None, out_clamp: bool = False, out_uint8: bool = False) -> torch.Tensor:
+def forward(sr, rgb: Optional[torch.Tensor], x: torch.Tensor, ws3: Optional[torch.Tensor], shared_styles: Optional[bool] = None,
+            x_nhwc: Optional[torch.Tensor] = None, out_clamp: bool = False, out_uint8: bool = False, rgb_from_x: bool = False) -> torch.Tensor:
     """rgb [N,3,h,w], x [N,C,h,w] (fp32 NCHW, h <= 128), ws3 [N,3,512] -> [N,3,512,512] fp32.
     x_nhwc: the same features channels-last [N,h,w,C] (the renderer's native output) - skips a layout round trip.
     out_clamp: the image leaves the last epilogue clamped to [-1,1]; out_uint8: it leaves as uint8 HWC frames [N,512,512,3]
@@ -153,10 +153,16 @@ def forward(sr, rgb: torch.Tensor, x: torch.Tensor, ws3: torch.Tensor, shared_st
             xn = capi.f32(x_nhwc)
             _, h, w, Cc = xn.shape
             x0 = torch.empty(N, sr.input_resolution, sr.input_resolution, (Cc + 63) // 64 * 64 * wide, device=xn.device, dtype=torch.float16)
-            capi.check(_fn('input_nhwc', split)(capi.ptr(xn), N, Cc, h, w, sr.input_resolution, capi.ptr(x0, torch.float16), capi.stream()))
+            if rgb_from_x:                                     # rgb IS x[:, :3] (render head): its resize rides in the same launch
+                rgb0 = torch.empty(N, 3, sr.input_resolution, sr.input_resolution, device=xn.device)
+                capi.check(L.r3dp_sr_tc_input_nhwc_rgb(capi.ptr(xn), N, Cc, h, w, sr.input_resolution, capi.ptr(x0, torch.float16), capi.ptr(rgb0), int(split),
+                                                       capi.stream()))
+            else:
+                capi.check(_fn('input_nhwc', split)(capi.ptr(xn), N, Cc, h, w, sr.input_resolution, capi.ptr(x0, torch.float16), capi.stream()))
         else:
             x0 = to_nhwc_f16(x, sr.input_resolution, split)
-        rgb0 = SuperresolutionHybrid8XDC._resize(rgb, sr.input_resolution) if rgb.shape[-1] != sr.input_resolution else capi.f32(rgb)
+        if not (rgb_from_x and x_nhwc is not None):
+            rgb0 = SuperresolutionHybrid8XDC._resize(rgb, sr.input_resolution) if rgb.shape[-1] != sr.input_resolution else capi.f32(rgb)
     (b0, b1), Nw, wp = _sblocks(sr), prep.Nw, prep.wp
     a0 = layer(x0, b0.conv0, wp[0], 2, split)
     a1 = torch.empty(N, 256, 256, 256 * wide, device=x.device, dtype=torch.float16)

@@ -219,13 +219,16 @@ class SuperresolutionHybrid8XDC(torch.nn.Module):
         out_clamp, out_uint8 = bool(block_kwargs.pop('out_clamp', False)), bool(block_kwargs.pop('out_uint8', False))
         if (out_clamp or out_uint8) and self.sr_mode not in ('tc', 'tc_exact'):
             raise NotImplementedError('fused clamp / uint8 output is an option of the tensor-core SR path')
+        rgb_from_x = bool(block_kwargs.pop('rgb_from_x', False))   # tensor-core path: the caller states rgb == x[:, :3] (one fused input launch)
         block_kwargs = {k: v for k, v in block_kwargs.items() if k != 'sr_mode'}
-        ws = ws[:, -1:, :].repeat(1, 3, 1)
+        prep = self.static_prepared
+        if not (self.sr_mode in ('tc', 'tc_exact') and prep is not None and prep.split == (self.sr_mode == 'tc_exact')):     # prepared weights: the styles are not read again
+            ws = ws[:, -1:, :].repeat(1, 3, 1)
         if x.shape[-1] > self.input_resolution:
             raise NotImplementedError('down-scaling inputs (antialiased) is not on the Real3D path')
         if self.sr_mode in ('tc', 'tc_exact'):
             from . import sr_tc
-            return sr_tc.forward(self, rgb, x, ws, x_nhwc=x_nhwc, out_clamp=out_clamp, out_uint8=out_uint8)
+            return sr_tc.forward(self, rgb, x, ws, x_nhwc=x_nhwc, out_clamp=out_clamp, out_uint8=out_uint8, rgb_from_x=rgb_from_x)
         if x.shape[-1] != self.input_resolution:
             x = self._resize(x, self.input_resolution)
             rgb = self._resize(rgb, self.input_resolution)

@@ -73,7 +73,7 @@ class RenderHead(torch.nn.Module):
                 self._ones_ws = torch.ones(N, 14, self.hparams['w_dim'], device=feat.device)
             # the clamp (and, if asked, the uint8 HWC conversion of real3d_infer.py:519) happen in the last SR epilogue
             sr_image = self.superresolution(x_nhwc[..., :3].permute(0, 3, 1, 2), x_nhwc.permute(0, 3, 1, 2), self._ones_ws, noise_mode='none',
-                                            x_nhwc=x_nhwc, out_clamp=True, out_uint8=out_uint8)
+                                            x_nhwc=x_nhwc, out_clamp=True, out_uint8=out_uint8, rgb_from_x=True)
             ret.update({'image': sr_image, 'is_ray_valid': valid})
             return ret
         if out_uint8:

@@ -1,7 +1,7 @@
 """Small end-to-end case for compute-sanitizer (memcheck / racecheck are ~100x slower: tiny shapes).
     compute-sanitizer --tool memcheck python tools/sanitize_case.py
 Covers: streaming render kernel (single pass), two-pass tcgen05 render kernel, tri-grid variant, tensor-core SR (all four conv launches,
-FIR, edge), uint8 epilogue."""
+FIR, edge) with fp16 and with split operands, uint8 epilogue, stand-alone sampler."""
 import os
 import sys
 
@@ -37,15 +37,21 @@ def main():
         out = r3.ImportanceRenderer(hp=hp)(grids, dec, o, d, dict(syn.RENDERING_OPTIONS, depth_resolution=12, u_coarse=u_c.to(dev)))
         torch.cuda.synchronize()
         print('trigrid', float(out[0].abs().mean()))
-    if what in ('all', 'sr'):
-        sr = r3.SuperresolutionHybrid8XDC(channels=32, img_resolution=512, sr_num_fp16_res=0, sr_antialias=True, sr_mode='tc')
+    if what in ('all', 'sample'):
+        planes = torch.randn(2, 3, 32, 24, 24, generator=g).to(dev)
+        coords = (torch.rand(2, 1000, 3, generator=g) * 1.4 - 0.7).to(dev)                 # some points outside the box
+        f = r3.sample_from_planes(None, planes, coords, box_warp=1.0)
+        torch.cuda.synchronize()
+        print('sample', float(f.abs().mean()))
+    for mode in (('tc', 'tc_exact') if what == 'all' else (('tc',) if what == 'sr' else (('tc_exact',) if what == 'sr_exact' else ()))):
+        sr = r3.SuperresolutionHybrid8XDC(channels=32, img_resolution=512, sr_num_fp16_res=0, sr_antialias=True, sr_mode=mode)
         sr.load_state_dict(syn.make_sr_params(seed=5), strict=True)
         sr = sr.to(dev).eval()
         fimg = (torch.rand(1, 32, 64, 64, generator=g) * 2 - 1).to(dev)
         for u8 in (False, True):
             img = sr(fimg[:, :3].contiguous(), fimg, torch.ones(1, 14, 512, device=dev), noise_mode='none', out_uint8=u8)
             torch.cuda.synchronize()
-            print('sr', u8, float(img.float().abs().mean()))
+            print('sr', mode, u8, float(img.float().abs().mean()))
 
 
 if __name__ == '__main__':

@@ -9,7 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'real3dportrait_b200', 'lib', 'libr3dp_b200.so')
-PAT = ['UTCHMMA', 'UTCHMMA.2CTA', 'LDTM', 'STTM', 'UTMALDG', 'UTCBAR', 'SYNCS', 'LDGSTS', 'HMMA', 'FFMA2', 'MUFU', 'LDG.E.128', 'ELECT']
+PAT = ['UTCHMMA', 'UTCHMMA.2CTA', 'LDTM', 'STTM', 'UTMALDG', 'UBLKPF', 'USETMAXREG', 'UTCBAR', 'SYNCS', 'LDGSTS', 'HMMA', 'FFMA2', 'MUFU', 'LDG.E.128', 'ELECT']
 
 
 def main():
@@ -24,7 +24,7 @@ def main():
             funcs[cur].append(ln)
     out = ['# r2 - SASS evidence (cuobjdump -sass real3dportrait_b200/lib/libr3dp_b200.so, built by __graft_entry__.build())', '',
            'Counts of instructions per kernel (`tools/sass_evidence.py`).  `UTCHMMA` = `tcgen05.mma` (`.2CTA` = `cta_group::2`), `LDTM` = `tcgen05.ld`,',
-           '`UTMALDG` = `cp.async.bulk.tensor` (TMA), `UTCBAR` = `tcgen05.commit`, `SYNCS` = mbarrier ops, `LDGSTS` = `cp.async`; `HMMA` (legacy `mma.sync`) must be 0.', '',
+           '`UTMALDG` = `cp.async.bulk.tensor` (TMA), `UBLKPF` = `cp.async.bulk.prefetch.L2`, `USETMAXREG` = `setmaxnreg`, `UTCBAR` = `tcgen05.commit`, `SYNCS` = mbarrier ops, `LDGSTS` = `cp.async`; `HMMA` (legacy `mma.sync`) must be 0.', '',
            '| kernel | ' + ' | '.join(PAT) + ' |', '|---|' + '---:|' * len(PAT)]
     for name, lines in funcs.items():
         body = '\n'.join(lines)

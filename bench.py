@@ -463,6 +463,20 @@ def main():
                         'bg_encoder(ref_bg) and the 512->256 resizes (sr_with_ref.py:77-90); TFLOP/s counts the reference\'s 782 GFLOP/frame conv stack over the UNCACHED step'}
             del head5
 
+    # ---- the fp32-grade tensor-core SR (sr_mode='tc_exact': split fp16 operands, three MMAs per product) on the same step, beside the fp16 headline
+    if not args.no_extra_configs and sr_mode == 'tc':
+        ex = engine.FrameEngine(batch=B, sr_mode='tc_exact', device=dev, world=world, rank=rank, dist=dist, use_graph=not args.no_graph,
+                                hp={'num_samples_fine': 0}, exchange='none')
+        ex.load_params(syn.make_decoder_params(seed=4), syn.make_sr_params(seed=5))
+        ex.prepare(resident[:min(nb, 4)])
+        kx = max(6, args.steps // 2)
+        ms_x = timed_loop(lambda i: ex.step(*resident[i % min(nb, 4)]), kx, 3, barrier, dist, dev) / kx
+        extra_cfg["sr_mode='tc_exact' (fp32-grade SR on tcgen05)"] = {
+            'value': world * B / (ms_x / 1e3), 'unit': 'frames/s', 'ms_per_step': ms_x,
+            'note': 'same step as the headline with split fp16 operands in every SR convolution (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32 accumulation): '
+                    'image within 1e-3*range of the fp32 reference (tests/test_gpu_parity.py::test_sr_full_tc_exact_vs_reference) instead of 2.3e-3 absolute'}
+        del ex
+
     # ---- north_star's HBM roofline: the stand-alone sample_from_planes op on one step's render samples (L2 flushed between iterations)
     hbm = None
     if rank == 0:

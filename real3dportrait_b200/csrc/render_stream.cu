@@ -41,7 +41,7 @@ constexpr int kOffW = kOffA2 + 32768;
 constexpr int kOffRows = kOffW + 21504;                         // MlpTcImage (20 928 B) padded
 constexpr int kOffDep = kOffRows + NR * 128 * kRowF * 4;
 constexpr int kOffDsc = kOffDep + ND * 128 * 4;
-constexpr int kDscF = 32;                                       // floats per sample descriptor row (15 used by tri-planes, 27 by tri-grids)
+constexpr int kDscF = 36;                                       // floats per sample descriptor row (28 used by tri-planes, 27 by tri-grids; 36: the four 8-lane groups of a warp read different banks)
 constexpr int kOffRay = kOffDsc + kGatherWarps * kSPW * kDscF * 4;
 constexpr int kOffBar = kOffRay + kGatherWarps * 8 * 8 * 4;
 constexpr int kSmem = kOffBar + 512 + 1024;                     // + alignment slack
@@ -51,7 +51,7 @@ struct Bars {
     uint64_t l1_done[2], l2_done[2], acc2_empty[2];
     uint64_t a2_full;
     uint64_t rows_full[NR], rows_empty[NR];
-    uint64_t dep_empty[ND];
+    uint64_t dep_empty[ND], dep_full[ND];
     uint32_t tmem_slot;
 };
 static_assert(sizeof(Bars) <= 512, "barrier block");
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&B.l1_done[i], 1); tc::mbar_init(&B.l2_done[i], 1); tc::mbar_init(&B.acc2_empty[i], 4); }
         tc::mbar_init(&B.a2_full, 4);
         for (int i = 0; i < NR; ++i) { tc::mbar_init(&B.rows_full[i], 4); tc::mbar_init(&B.rows_empty[i], 4); }
-        for (int i = 0; i < ND; ++i) tc::mbar_init(&B.dep_empty[i], 4);
+        for (int i = 0; i < ND; ++i) { tc::mbar_init(&B.dep_empty[i], 4); tc::mbar_init(&B.dep_full[i], kGatherWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {
@@ -195,11 +195,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
                         else sample_desc_split(a.p0, a.H, a.W, scale * x, scale * y, scale * z, row);
                     } else {
 #pragma unroll
-                        for (int e = 0; e < (GRID ? 27 : 15); ++e) row[e] = 0.f;                   // offset 0, weights 0: a harmless tap
+                        for (int e = 0; e < 28; ++e) row[e] = 0.f;                                 // offset 0, weights 0: a harmless tap
                     }
                     dep[dslot * 128 + gw * kSPW + lane] = d;
                 }
                 __syncwarp();
+                if (lane == 0) mbar_arrive(&B.dep_full[dslot]);                // the depths have their own full barrier: the march warps acquire them directly
                 tc::mbar_wait(&B.a1_empty[stage], ((q / NS) & 1) ^ 1);
                 uint8_t* a1s = a1 + stage * 16384;
 #pragma unroll 1
@@ -308,8 +309,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
             float* out = rows + (rb * 128 + trow) * kRowF;
             out[0] = __uint_as_float(v[0]) + b2s[0];
 #pragma unroll
-            for (int o = 1; o < 32; ++o) out[o] = sigmoid_fast(__uint_as_float(v[o]) + b2s[o]) * 1.002f - 0.001f;
-            out[32] = sigmoid_fast(__uint_as_float(v2[0]) + b2s[32]) * 1.002f - 0.001f;
+            for (int o = 1; o < 33; o += 2) {                                  // outputs 1..32 in pairs (o, o+1); output 32 comes from the second TMEM load
+                const float x1 = o + 1 < 32 ? __uint_as_float(v[o + 1]) : __uint_as_float(v2[0]);
+                const float2 sg = sigmoid_scaled2(pk_add(make_float2(__uint_as_float(v[o]), x1), make_float2(b2s[o], b2s[o + 1])));
+                out[o] = sg.x; out[o + 1] = sg.y;
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&B.rows_full[rb]);
         };
@@ -324,11 +328,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float h0 = softplus_fast(__uint_as_float(v[2 * i]) + b1s[32 * h + 2 * i]);
-                    const float h1 = softplus_fast(__uint_as_float(v[2 * i + 1]) + b1s[32 * h + 2 * i + 1]);
-                    const __half2 hh = __floats2half2_rn(h0, h1);
+                    const float2 bb = *reinterpret_cast<const float2*>(b1s + 32 * h + 2 * i);
+                    const float2 hv = softplus2(pk_add(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bb));
+                    const __half2 hh = __floats2half2_rn(hv.x, hv.y);
                     const float2 hf = __half22float2(hh);
-                    const __half2 ll = __floats2half2_rn(h0 - hf.x, h1 - hf.y);
+                    const __half2 ll = __floats2half2_rn(hv.x - hf.x, hv.y - hf.y);
                     hi[i] = *reinterpret_cast<const uint32_t*>(&hh); lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
                 }
                 if (h == 0 && q >= 1) tc::mbar_wait(&B.l2_done[(q - 1) & 1u], ((q - 1) >> 1) & 1u);     // layer 2 of the previous tile has read A2
@@ -367,6 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
             for (int t = 0; t < NT; ++t, ++q) {
                 const uint32_t rb = q % NR, dslot = q % ND;
                 tc::mbar_wait(&B.rows_full[rb], (q / NR) & 1u);
+                tc::mbar_wait(&B.dep_full[dslot], (q / ND) & 1u);
                 const float* rbuf = rows + (rb * 128 + mw * 32) * kRowF;
                 const int k = (t << LOG2D) + lj;
                 const float s = rbuf[lane * kRowF], d = dep[dslot * 128 + mw * 32 + lane];
@@ -375,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_stream_kernel(const Render
                 if (lj == 0) { ps = cs; pd = cd; }
                 float alpha = 0.f, om = 1.f, dmid = 0.f;
                 if (k > 0 && k < a.S) {
-                    const float smid = softplus_fast((ps + s) * 0.5f - 1.0f);         // ray_marcher.py:33
+                    const float smid = softplus2(make_float2((ps + s) * 0.5f - 1.0f, 0.f)).x;    // ray_marcher.py:33
                     alpha = 1.0f - __expf(-(smid * (d - pd)));
                     om = 1.0f - alpha + 1e-10f;
                     dmid = 0.5f * (pd + d);

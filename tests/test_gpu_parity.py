@@ -618,3 +618,17 @@ def test_large_sr_tc_vs_reference(golden):
     err, psnr, rng = _maxdiff(img, ref), _psnr(img, ref), float(ref.max() - ref.min())
     print(f'large_sr (tc): max-abs {err:.3e} on range {rng:.1f}, PSNR {psnr:.1f} dB')
     assert err < 2e-3 * rng and psnr > 68.0, (err, psnr)
+
+
+def test_peer_copy_same_device_and_set_options():
+    """r3dp_peer_copy (the clip push of FrameEngine(exchange='p2p')) with source and destination on one device; option keys are validated."""
+    from real3dportrait_b200 import _capi
+    L = _capi.lib()
+    src = torch.arange(1 << 16, dtype=torch.uint8, device=DEV)
+    dst = torch.zeros_like(src)
+    dev_i = torch.cuda.current_device()
+    _capi.check(L.r3dp_peer_copy(dst.data_ptr(), dev_i, src.data_ptr(), dev_i, src.numel(), _capi.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(src, dst)
+    assert L.r3dp_set_option(b'rs_prefetch', 3) == 0 and L.r3dp_set_option(b'rs_prefetch', 2) == 0
+    assert L.r3dp_set_option(b'no_such_key', 1) != 0 and b'unknown key' in L.r3dp_last_error()

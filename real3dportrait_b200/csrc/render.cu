@@ -10,18 +10,6 @@
 namespace r3dp {
 
 
-// writes the scaled decoder weights into the constant bank's backing store (visible to every later launch)
-__global__ void mlp_to_const_kernel(const r3dp_mlp_t m, MlpConst* dst) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
-    const float g1 = 0.17677669529663687f, g2 = 0.125f;        // 1/sqrt(32), 1/sqrt(64)  (networks_stylegan2.py:113)
-    for (int i = tid; i < kHidden * kC; i += nt) dst->w1[i] = m.w1[i] * g1;
-    for (int i = tid; i < kHidden * kW2Row; i += nt) { const int j = i / kW2Row, o = i - j * kW2Row; dst->w2[i] = o < kOut ? m.w2[o * kHidden + j] * g2 : 0.f; }
-    for (int i = tid; i < kHidden; i += nt) dst->b1[i] = m.b1[i];
-    for (int i = tid; i < kOut; i += nt) dst->b2[i] = m.b2[i];
-}
-
-
-
 struct RenderWs;
 __device__ __forceinline__ void init_ws(RenderWs* ws);
 // decoder operand image for tcgen05 (+ the call's workspace header, so that a render needs one set-up launch instead of two)
@@ -116,18 +104,17 @@ __device__ __forceinline__ int ray_of(const RenderArgs& a, int tile, int r) {
     return tile * R + r;
 }
 
-// CONST = decoder weights from the constant bank (1 sample/thread, 4 CTAs/SM); else staged in smem (2 samples/thread, 2 CTAs/SM)
-// PAIR (CONST only) = two samples per thread in the decoder (halves the constant-load traffic; ~160 regs, 2 CTAs/SM) - used when every
-// pass gives each thread a full pair; otherwise one sample per thread at 80 regs, 4 CTAs/SM
+// TC = false: decoder weights staged in smem, CUDA-core decoder, two samples per thread (odd shapes that do not fit the tensor-core tiles)
+// (the round-1 constant-bank decoder variants - process-wide state - were removed in round 2; git history keeps them)
 // TC = decoder on tcgen05 (single-pass renders with R*S <= 384; 256 threads, 2 CTAs/SM); see the MlpTcImage comment
 constexpr int kPfCtas = 32;                            // CTAs of a frame that issue its L2 prefetches
-template <int R, bool CONST, bool PAIR, bool TC = false>
-__global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((CONST && !PAIR) ? 4 : 2)) render_kernel(const RenderArgs a) {
+template <int R, bool TC>
+__global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, 2) render_kernel(const RenderArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int kRenderThreads = TC ? kTcThreads : r3dp::kRenderThreads;     // shadows the namespace constant inside this kernel
     const int ST = a.S + a.S_imp;                         // samples per ray after the optional importance pass
     MlpSmem& mlp = *reinterpret_cast<MlpSmem*>(smem);
-    float* rows = smem + (CONST ? 0 : sizeof(MlpSmem) / 4); // [R*ST][kRow]   features -> (sigma, colours)
+    float* rows = smem + sizeof(MlpSmem) / 4;               // [R*ST][kRow]   features -> (sigma, colours)
     float* dep = rows + R * ST * kRow;                     // [R*ST]          sample depths
     float* wts = dep + R * ST;                             // [R*ST]          coarse interval weights
     float* cdf = wts + R * ST;                             // [R*ST]          importance cdf
@@ -177,7 +164,7 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
             for (int f = 0; f < a.lookahead && f < a.N; ++f) { prefetch_frame_l2(a.p0, a.H, a.W, f, tile, kPfCtas); prefetch_frame_l2(a.p1, a.H, a.W, f, tile, kPfCtas); }
         if (n + a.lookahead < a.N) { prefetch_frame_l2(a.p0, a.H, a.W, n + a.lookahead, tile, kPfCtas); prefetch_frame_l2(a.p1, a.H, a.W, n + a.lookahead, tile, kPfCtas); }
     }
-    if (!CONST) load_mlp_smem(mlp, a.mlp, tid, kRenderThreads);
+    if (!TC) load_mlp_smem(mlp, a.mlp, tid, kRenderThreads);
     uint32_t tmem_base = 0;
     uint32_t tc_par = 0;                                   // bit t = parity of the phase bar1[t] / bar2[t] complete next (one use per pass)
     if (TC) {
@@ -409,29 +396,6 @@ __global__ void __launch_bounds__(TC ? kTcThreads : kRenderThreads, TC ? 2 : ((C
             return;
         }
         __syncthreads();
-        if (CONST) {
-            if (PAIR) {
-                const int halfc = (nsamp + 1) >> 1;
-                for (int p = tid; p < halfc; p += kRenderThreads) {
-                    const int qa = p, qb = p + halfc;
-                    const int ra = qa / kn, ka = k0 + (qa - ra * kn);
-                    float* rowa = rows + (size_t)(ra * ST + ka) * kRow;
-                    if (qb < nsamp) {
-                        const int rb = qb / kn, kb = k0 + (qb - rb * kn);
-                        decode_two_const(rowa, rows + (size_t)(rb * ST + kb) * kRow);
-                    } else {
-                        decode_one_const(rowa);
-                    }
-                }
-            } else {
-                for (int q = tid; q < nsamp; q += kRenderThreads) {
-                    const int r = q / kn, k = k0 + (q - r * kn);
-                    decode_one_const(rows + (size_t)(r * ST + k) * kRow);
-                }
-            }
-            __syncthreads();
-            return;
-        }
         // decode: two samples per thread
         const int half = (nsamp + 1) >> 1;
         for (int p = tid; p < half; p += kRenderThreads) {
@@ -608,16 +572,15 @@ __global__ void ray_march_kernel(const float* __restrict__ colors, const float* 
     if (lane == 0 && dmin <= dmax) { atomicMin(&ws->d_min, f2ord(dmin)); atomicMax(&ws->d_max, f2ord(dmax)); }
 }
 
-static size_t render_smem_bytes(int R, int ST, bool cst) {
-    return (cst ? 0 : sizeof(MlpSmem)) + (size_t)R * ST * kRow * 4 + 3 * (size_t)R * ST * 4 + (size_t)R * 8 * 4 + (size_t)R * ST * 4;
+static size_t render_smem_bytes(int R, int ST) {
+    return sizeof(MlpSmem) + (size_t)R * ST * kRow * 4 + 3 * (size_t)R * ST * 4 + (size_t)R * 8 * 4 + (size_t)R * ST * 4;
 }
 
-static int mlp_variant() {                         // R3DP_MLP = tc (default) | const | smem: decoder variant, for A/B comparison
+static int mlp_variant() {                         // R3DP_MLP = tc (default) | smem: decoder variant, for A/B comparison
     static int v = -1;
-    if (v < 0) { const char* e = getenv("R3DP_MLP"); v = !e ? 2 : e[0] == 's' ? 0 : e[0] == 'c' ? 1 : 2; }
+    if (v < 0) { const char* e = getenv("R3DP_MLP"); v = (e && e[0] == 's') ? 0 : 2; }
     return v;
 }
-static bool mlp_in_const() { return mlp_variant() != 0; }
 
 static size_t render_tc_smem(int R, int S, int S_imp) {
     const int ST = S + S_imp;
@@ -634,37 +597,28 @@ static bool render_tc_fits(int R, int S, int S_imp) {
 template <int R>
 static int launch_render_tc(const RenderArgs& a, cudaStream_t st) {
     const size_t smem = render_tc_smem(R, a.S, a.S_imp);
-    R3DP_CUDA(cudaFuncSetAttribute(render_kernel<R, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    R3DP_CUDA(cudaFuncSetAttribute(render_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(a.tiles_per_frame, a.N);                     // (the decoder image was written by r3dp_render_ex's set-up launch)
-    render_kernel<R, true, false, true><<<grid, kTcThreads, smem, st>>>(a);
+    render_kernel<R, true><<<grid, kTcThreads, smem, st>>>(a);
     R3DP_LAUNCH_CHECK();
     return 0;
 }
 
-template <int R, bool CONST, bool PAIR>
+template <int R>
 static int launch_render_v(const RenderArgs& a, cudaStream_t st) {
-    const size_t smem = render_smem_bytes(R, a.S + a.S_imp, CONST);
-    R3DP_CUDA(cudaFuncSetAttribute(render_kernel<R, CONST, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (CONST) {
-        MlpConst* dst = nullptr;
-        R3DP_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&dst), c_mlp));
-        mlp_to_const_kernel<<<4, 256, 0, st>>>(a.mlp, dst);
-        count_launches(1);
-    }
+    const size_t smem = render_smem_bytes(R, a.S + a.S_imp);
+    R3DP_CUDA(cudaFuncSetAttribute(render_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(a.tiles_per_frame, a.N);
-    render_kernel<R, CONST, PAIR><<<grid, kRenderThreads, smem, st>>>(a);
+    render_kernel<R, false><<<grid, kRenderThreads, smem, st>>>(a);
     R3DP_LAUNCH_CHECK();
     return 0;
 }
 template <int R>
 static int launch_render(const RenderArgs& a, cudaStream_t st) {
-    // default: tcgen05 decoder when the tile fits, else the smem-weights CUDA-core decoder (both keep the decoder in per-call storage);
-    // the constant-bank variants hold process-wide state and are reachable only through R3DP_MLP=const (A/B runs)
+    // tcgen05 decoder when the tile fits, else the smem-weights CUDA-core decoder; both keep the decoder in per-call storage
     const bool grid_single = a.p0.depth > 1 && a.S_imp == 0;      // tri-grid descriptors (27 floats) do not fit the single-pass [nsamp][16] layout
     if (mlp_variant() == 2 && !grid_single && render_tc_fits(R, a.S, a.S_imp)) return launch_render_tc<R>(a, st);
-    if (mlp_variant() != 1) return launch_render_v<R, false, false>(a, st);
-    const int per_pass = R * (a.S_imp > 0 && a.S_imp < a.S ? a.S_imp : a.S);          // the smaller pass decides
-    return per_pass >= 2 * kRenderThreads ? launch_render_v<R, true, true>(a, st) : launch_render_v<R, true, false>(a, st);
+    return launch_render_v<R>(a, st);
 }
 
 int g_render_variant = -1;                         // R3DP_RENDER = stream (default for single-pass renders) | tile: A/B knob

@@ -208,127 +208,5 @@ __device__ __forceinline__ void decode_pair(const MlpSmem& w, float* __restrict_
     }
 }
 
-// ---- OSG decoder, constant-bank variant ------------------------------------------------------------------------------
-// The 4 257 scaled weights live in __constant__ memory (render.cu fills them with a tiny kernel before every render call).
-// Fully unrolled, every FFMA takes its weight as a constant-bank operand: no weight loads at all, one sample per thread,
-// ~80 registers.  hidden unit j is consumed immediately (32 FMAs -> softplus -> 33 FMAs into the outputs).
-constexpr int kW2Row = 36;
-struct alignas(16) MlpConst {
-    float w1[kHidden * kC];      // [j][c]   W1 * 1/sqrt(32)
-    float b1[kHidden];
-    float w2[kHidden * kW2Row];       // [j][o]   (W2 * 1/sqrt(64))^T, rows padded to 36 floats (float4 / f32x2 pairs)
-    float b2[kOut];
-};
-static __constant__ MlpConst c_mlp;      // one copy per translation unit; only render.cu uses it
-
-// packed 2 x fp32 FMA (sm_100 fma.rn.f32x2): (d0,d1) += (a0,a1) * (b0,b1); ptxas keeps the pairs in aligned register pairs
-__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-    asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
-        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
-        "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
-        "mov.b64 {%0, %1}, rc;\n\t}"
-        : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
-
-#ifndef R3DP_MLP_FFMA2
-#define R3DP_MLP_FFMA2 1
-#endif
-
-__device__ __forceinline__ void decode_one_const(float* __restrict__ row) {
-    float x[kC], y[kW2Row];
-#pragma unroll
-    for (int c = 0; c < kC; ++c) x[c] = row[c];
-#pragma unroll
-    for (int o = 0; o < kW2Row; ++o) y[o] = o < kOut ? c_mlp.b2[o] : 0.f;
-    // 16 rolled iterations x 4 hidden units: the body stays in the instruction cache (fully unrolled it is ~100 KB and ncu shows
-    // no_instruction stalls), and the four independent softplus chains overlap their MUFU latencies.  With R3DP_MLP_FFMA2 the dot
-    // products run as packed f32x2 FMAs: even/odd-channel partial sums for layer 1, adjacent output pairs for layer 2.
-#pragma unroll 1
-    for (int j0 = 0; j0 < kHidden; j0 += 4) {
-        float h[4];
-#if R3DP_MLP_FFMA2
-        float he[4], ho[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { he[u] = c_mlp.b1[j0 + u]; ho[u] = 0.f; }
-        // weights fetched as float4 (one LDCU.128 per TWO packed FMAs; ncu showed LDCU.64 : FFMA2 = 1 : 1 with scalar indexing)
-#pragma unroll
-        for (int c = 0; c < kC; c += 4) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float4 w = *reinterpret_cast<const float4*>(&c_mlp.w1[(j0 + u) * kC + c]);
-                ffma2(he[u], ho[u], x[c], x[c + 1], w.x, w.y);
-                ffma2(he[u], ho[u], x[c + 2], x[c + 3], w.z, w.w);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) h[u] = softplus_fast(he[u] + ho[u]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-#pragma unroll
-            for (int o = 0; o < kW2Row; o += 4) {
-                const float4 w = *reinterpret_cast<const float4*>(&c_mlp.w2[(j0 + u) * kW2Row + o]);
-                ffma2(y[o], y[o + 1], h[u], h[u], w.x, w.y);
-                ffma2(y[o + 2], y[o + 3], h[u], h[u], w.z, w.w);
-            }
-        }
-#else
-#pragma unroll
-        for (int u = 0; u < 4; ++u) h[u] = c_mlp.b1[j0 + u];
-#pragma unroll
-        for (int c = 0; c < kC; ++c) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) h[u] = fmaf(x[c], c_mlp.w1[(j0 + u) * kC + c], h[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) h[u] = softplus_fast(h[u]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-#pragma unroll
-            for (int o = 0; o < kOut; ++o) y[o] = fmaf(h[u], c_mlp.w2[(j0 + u) * kW2Row + o], y[o]);
-        }
-#endif
-    }
-    row[0] = y[0];
-#pragma unroll
-    for (int o = 1; o < kOut; ++o) row[o] = sigmoid_fast(y[o]) * 1.002f - 0.001f;
-}
-
-// Two samples per thread: every LDCU'd weight pair feeds two packed FMAs (ncu: with one sample per thread the constant loads are 1:1
-// with the FFMA2s and the warps stall on mio_throttle).  ~170 registers -> 2 CTAs of 192 threads per SM.
-__device__ __forceinline__ void decode_two_const(float* __restrict__ ra, float* __restrict__ rb) {
-    float xa[kC], xb[kC], ya[kW2Row], yb[kW2Row];
-#pragma unroll
-    for (int c = 0; c < kC; ++c) { xa[c] = ra[c]; xb[c] = rb[c]; }
-#pragma unroll
-    for (int o = 0; o < kW2Row; ++o) { ya[o] = o < kOut ? c_mlp.b2[o] : 0.f; yb[o] = ya[o]; }
-#pragma unroll 1
-    for (int j0 = 0; j0 < kHidden; j0 += 2) {
-        float hea[2], hoa[2], heb[2], hob[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) { hea[u] = c_mlp.b1[j0 + u]; hoa[u] = 0.f; heb[u] = hea[u]; hob[u] = 0.f; }
-#pragma unroll
-        for (int c = 0; c < kC; c += 2) {
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const float w0 = c_mlp.w1[(j0 + u) * kC + c], w1 = c_mlp.w1[(j0 + u) * kC + c + 1];
-                ffma2(hea[u], hoa[u], xa[c], xa[c + 1], w0, w1);
-                ffma2(heb[u], hob[u], xb[c], xb[c + 1], w0, w1);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const float sa = softplus_fast(hea[u] + hoa[u]), sb = softplus_fast(heb[u] + hob[u]);
-#pragma unroll
-            for (int o = 0; o < kW2Row; o += 2) {
-                const float w0 = c_mlp.w2[(j0 + u) * kW2Row + o], w1 = c_mlp.w2[(j0 + u) * kW2Row + o + 1];
-                ffma2(ya[o], ya[o + 1], sa, sa, w0, w1);
-                ffma2(yb[o], yb[o + 1], sb, sb, w0, w1);
-            }
-        }
-    }
-    ra[0] = ya[0]; rb[0] = yb[0];
-#pragma unroll
-    for (int o = 1; o < kOut; ++o) { ra[o] = sigmoid_fast(ya[o]) * 1.002f - 0.001f; rb[o] = sigmoid_fast(yb[o]) * 1.002f - 0.001f; }
-}
 
 }  // namespace r3dp

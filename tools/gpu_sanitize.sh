@@ -1,5 +1,5 @@
 #!/bin/bash
-# compute-sanitizer: memcheck over every kernel family, racecheck + synccheck over the mbarrier / TMEM render kernels (small shapes).
+# One GPU: compute-sanitizer memcheck over every kernel family, racecheck + synccheck over the render kernels (tools/sanitize_case.py, small shapes).
 mkdir -p gpurun_out
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_case.py all > gpurun_out/san_memcheck.log 2>&1; echo "memcheck exit $?" >> gpurun_out/san_memcheck.log
 timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_case.py render > gpurun_out/san_racecheck_render.log 2>&1; echo "racecheck exit $?" >> gpurun_out/san_racecheck_render.log

@@ -684,7 +684,7 @@ __global__ void resize_to_nhwc_f16_kernel(const float* __restrict__ x, int N, in
 // cover): yb[n][Y][2W][co] = sum_{ci, ky == Y (mod 2)} x[(Y-ky)/2][W-1][ci] * w[ky*3+2][co][ci].
 // CTA = 32 couts x 16 rows of one image.  The kx = 2 column of the kernel for these couts ([3][32][Cp] fp16) and the <= 10 input
 // pixels are staged in smem; thread (co, row pair) then runs plain dot products - no cross-lane reductions.  Cp <= 256.
-constexpr int kEdgeRows = 16, kEdgeCo = 32;
+constexpr int kEdgeRows = 64, kEdgeRowsSplit = 16, kEdgeCo = 32;      // 64 rows per CTA: the 50 KB weight column is staged 9 times per image instead of 33
 __global__ void __launch_bounds__(256) upconv_edge_kernel(const __half* __restrict__ x, const __half* __restrict__ wp, int H, int W, int Cp, int O,
                                                           int w_shared, __half* __restrict__ yb) {
     extern __shared__ __align__(16) uint8_t edge_smem[];
@@ -711,9 +711,10 @@ __global__ void __launch_bounds__(256) upconv_edge_kernel(const __half* __restri
     __syncthreads();
     const int co = threadIdx.x & 31, yp = threadIdx.x >> 5;                  // 8 warps x 2 rows each; lanes = couts
     if (co0 + co >= O) return;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int yy = yp * 2 + half, Y = Y0 + yy;
+    constexpr int RPW = kEdgeRows / 8;                                        // rows per warp
+#pragma unroll 2
+    for (int hh = 0; hh < RPW; ++hh) {
+        const int yy = yp * RPW + hh, Y = Y0 + yy;
         if (Y >= BH) continue;
         float acc = 0.f;
         for (int ky = (yy & 1); ky < 3; ky += 2) {                           // Y0 is even: parity of Y == parity of yy
@@ -871,13 +872,13 @@ __global__ void __launch_bounds__(256) upconv_edge_split_kernel(const __half* __
                                                                 int w_shared, __half* __restrict__ yb) {
     extern __shared__ __align__(16) uint8_t edge_smem[];
     float* s_x = reinterpret_cast<float*>(edge_smem);                        // [10][Cp]
-    float* s_w = s_x + (kEdgeRows / 2 + 2) * Cp;                             // [3][32][Cp + 4]
+    float* s_w = s_x + (kEdgeRowsSplit / 2 + 2) * Cp;                             // [3][32][Cp + 4]
     const int WS = Cp + 4;
-    const int n = blockIdx.z, Y0 = blockIdx.x * kEdgeRows, co0 = blockIdx.y * kEdgeCo;
+    const int n = blockIdx.z, Y0 = blockIdx.x * kEdgeRowsSplit, co0 = blockIdx.y * kEdgeCo;
     const int BH = 2 * H + 1, BW = 2 * W + 1;
     const int wn = w_shared ? 0 : n;
     const int iy0 = Y0 / 2 - 1;
-    for (int e = threadIdx.x; e < (kEdgeRows / 2 + 2) * Cp; e += 256) {
+    for (int e = threadIdx.x; e < (kEdgeRowsSplit / 2 + 2) * Cp; e += 256) {
         const int r = e / Cp, c = e - r * Cp, iy = iy0 + r;
         float v = 0.f;
         if (iy >= 0 && iy < H) { const __half* px = x + (((size_t)n * H + iy) * W + (W - 1)) * 2 * Cp; v = __half2float(px[c]) + __half2float(px[Cp + c]); }
@@ -1175,15 +1176,16 @@ static int layer_impl(const void* x_f16, const void* wp_f16, const float* bias, 
     if (launch_upconv2(x_f16, N, H, W, Ip, wp_f16, Nw, O, yb, bias, split, st)) return 1;
     {
         R3DP_REQUIRE(Ip <= 256, "sr_tc_layer: up=2 supports at most 256 input channels");
-        dim3 grid((2 * H + 1 + kEdgeRows - 1) / kEdgeRows, (O + kEdgeCo - 1) / kEdgeCo, N);
+        const int erows = split ? kEdgeRowsSplit : kEdgeRows;
+        dim3 grid((2 * H + 1 + erows - 1) / erows, (O + kEdgeCo - 1) / kEdgeCo, N);
         const size_t esmem = ((size_t)(kEdgeRows / 2 + 2) * Ip + 3 * (size_t)kEdgeCo * (Ip + 8)) * sizeof(__half);
         if (split) {
-            const size_t ssmem = ((size_t)(kEdgeRows / 2 + 2) * Ip + 3 * (size_t)kEdgeCo * (Ip + 4)) * sizeof(float);
+            const size_t ssmem = ((size_t)(kEdgeRowsSplit / 2 + 2) * Ip + 3 * (size_t)kEdgeCo * (Ip + 4)) * sizeof(float);
             R3DP_CUDA(cudaFuncSetAttribute(upconv_edge_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
             upconv_edge_split_kernel<<<grid, 256, ssmem, st>>>(reinterpret_cast<const __half*>(x_f16), reinterpret_cast<const __half*>(wp_f16), H, W, Ip, O,
                                                            Nw == 1, yb);
         } else {
-        R3DP_CUDA(cudaFuncSetAttribute(upconv_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        R3DP_CUDA(cudaFuncSetAttribute(upconv_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         upconv_edge_kernel<<<grid, 256, esmem, st>>>(reinterpret_cast<const __half*>(x_f16), reinterpret_cast<const __half*>(wp_f16), H, W, Ip, O,
                                                  Nw == 1, yb);
         }

@@ -684,7 +684,7 @@ __global__ void resize_to_nhwc_f16_kernel(const float* __restrict__ x, int N, in
 // cover): yb[n][Y][2W][co] = sum_{ci, ky == Y (mod 2)} x[(Y-ky)/2][W-1][ci] * w[ky*3+2][co][ci].
 // CTA = 32 couts x 16 rows of one image.  The kx = 2 column of the kernel for these couts ([3][32][Cp] fp16) and the <= 10 input
 // pixels are staged in smem; thread (co, row pair) then runs plain dot products - no cross-lane reductions.  Cp <= 256.
-constexpr int kEdgeRows = 64, kEdgeRowsSplit = 16, kEdgeCo = 32;      // 64 rows per CTA: the 50 KB weight column is staged 9 times per image instead of 33
+constexpr int kEdgeRows = 16, kEdgeRowsSplit = 16, kEdgeCo = 32;      // (64 rows per CTA - the weight column staged 9 instead of 33 times per image - measured slower: 28.3 vs 25.3 us, 144 CTAs are too few)
 __global__ void __launch_bounds__(256) upconv_edge_kernel(const __half* __restrict__ x, const __half* __restrict__ wp, int H, int W, int Cp, int O,
                                                           int w_shared, __half* __restrict__ yb) {
     extern __shared__ __align__(16) uint8_t edge_smem[];
@@ -756,7 +756,8 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
 // Work item = a strip of FIR_TW px x FIR_SEG output rows of one 64-channel group, streamed as FIR_SEG / FIR_TH chunks: the first box has the
 // 3 halo rows (35 px x 11 rows), the following boxes only new rows (35 x 8) - the 4-row register window simply keeps rolling across the
 // chunks, so only 35 input rows are loaded and converted per 32 output rows (ncu on the one-box-per-tile form: 386 MB read for 270 MB of
-// input, the vertical halo rows came from DRAM twice).
+// input, the vertical halo rows came from DRAM twice).  A two-output-pixels-per-thread variant (2.5 LDS.128 and 20 converts per output vector
+// instead of 4 and 32) was measured at 122-124 us against 124.5-126 us and dropped: the pass is not bound by instruction issue alone.
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) fir_tma_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmY8,
                                                       const float* __restrict__ bias, int N, int OH, int OW, int C, __half* __restrict__ y) {

@@ -5,14 +5,16 @@
 // Work item   = a group of G rays of one frame (G rows of one image column when the rays form an image: planes 1 and 2 are indexed by
 //               (x,z)/(z,x) only, so these rays walk the same texels), streamed front to back in depth chunks of D = 128/G samples per ray.
 // Tile        = the G x D = 128 samples of one chunk = one UMMA M-tile; row = ray_local * D + k_local.
-// Roles (17 warps, mbarrier hand-offs, every ring is filled and drained in tile order):
-//   gather  x8  sample depths (renderer.py:223-226) -> positions -> bilinear tap descriptors -> 12 x LDG.128 per lane group -> mean feature as
-//               fp16 hi|lo halves straight into the swizzled A1 stage (3-stage ring); depths into a small ring for the marcher
+// Roles (17 warps = 4 whole warpgroups + the MMA warp, mbarrier hand-offs, every ring is filled and drained in tile order):
+//   decode  x4  TMEM -> +bias, softplus (packed f32x2) -> re-split into the A2 atoms; TMEM -> +bias, scaled sigmoid -> fp32 rows (2-deep ring)
+//   march   x4  MipRayMarcher2 (ray_marcher.py:26-57) incrementally: alpha / transmittance once per sample (lane = tile row, segmented product
+//               scan), colours with lane = channel; accumulators live in registers across the tiles of an item; only the final [32] features,
+//               weight sum and depth leave the SM.  setmaxnreg: 48 registers
+//   gather  x8  sample depths (renderer.py:223-226) -> positions -> bilinear tap descriptors (smem) -> all 12 x LDG.128 of a sample in flight ->
+//               packed FMAs -> mean feature as fp16 hi|lo halves straight into the swizzled A1 stage (3-stage ring); depths into a small ring
+//               for the marcher; L2 look-ahead prefetch of the next frames' planes.  setmaxnreg: 120 registers
 //   mma     x1  layer 1: A1 x W1 (3 partial products x 2 k-steps, M128 N64 K16) -> TMEM; layer 2: A2 x W2 (3 x 4, M128 N48) -> TMEM
-//   decode  x4  TMEM -> +bias, softplus -> re-split into the A2 atoms; TMEM -> +bias, scaled sigmoid -> fp32 rows (2-deep ring)
-//   march   x4  MipRayMarcher2 (ray_marcher.py:26-57) incrementally: per-ray transmittance / colour / depth accumulators live in registers
-//               across the tiles of an item (lane = colour channel); nothing but the final [32] features, weight sum and depth leaves the SM
-// Decoder arithmetic is the split-fp16 scheme of render_shared.cuh (fp32-grade results).
+// Decoder arithmetic is the split-fp16 scheme of render_shared.cuh (fp32-grade results).  Measured history and ncu tables: profiles/r2_render_ab.md.
 #include "render_shared.cuh"
 #include <stdlib.h>
 

@@ -262,6 +262,11 @@ int r3dp_sr_tcx_last_layer(const void* x_f16, const void* wp_f16, const float* b
                            const float* img_prev, int N, int Nw, int I, int H, int W, float* img_out, uint8_t* img_out_u8, int clamp,
                            r3dp_stream_t stream);
 
+/* r3dp_sr_tc_conv with split fp16 operands (x [N,H,W,2*Ipad], weights from r3dp_sr_tcx_pack_weights, y [N,H,W,2*O] = [hi | lo]); used for the small
+ * head_torso_alpha_predictor of fuse mode v3, whose output is thresholded (sr_with_ref.py:129-143) and therefore wants fp32-grade arithmetic. */
+int r3dp_sr_tcx_conv(const void* x_f16, const void* wp_f16, const float* bias, int N, int Nw, int I, int O, int H, int W, int ksize,
+                     int act, void* y_f16, r3dp_stream_t stream);
+
 /* Measurement hooks (bench.py): time every tensor-core conv launch with a CUDA-event pair on its launching stream. */
 int r3dp_sr_tc_prof(int enable);
 int r3dp_sr_tc_prof_read(float* total_ms, int* launches);
@@ -287,6 +292,13 @@ int r3dp_sr_tc_conv_res(const void* x_f16, const void* wp_f16, const float* bias
                         int act, const void* residual_f16, void* y_f16, r3dp_stream_t stream);
 int r3dp_sr_tc_torgb_ex(const void* x_f16, const float* wrgb, const float* brgb, const float* img_prev, int same_res, int N, int Nw, int C,
                         int H, int W, float* img_out, r3dp_stream_t stream);
+/* htbsr_head_weight_fuse_mode v1 / v3 (sr_with_ref.py:96-104,126-152):
+ * r3dp_sr_alpha_mix   out[...,0:C] = xa * alpha + xb * (1 - alpha), fp16 NHWC with pixel strides stride_a / stride_b (v1's feature blend)
+ * r3dp_sr_alpha_gate  out [N,1,H,W] fp32 = min(sigmoid(logit), cap): logit = channel 0 of an NHWC fp16 tensor (+ channel lo_off when lo_off > 0: split
+ *                     output of r3dp_sr_tcx_conv) = tail of head_torso_alpha_predictor + the cap by the head weights (v3) */
+int r3dp_sr_alpha_mix(const void* xa_f16, int stride_a, const void* xb_f16, int stride_b, const float* alpha, int C, int N, int H, int W,
+                      void* out_f16, r3dp_stream_t stream);
+int r3dp_sr_alpha_gate(const void* logits_f16, int stride, int lo_off, const float* cap, int N, int H, int W, float* out, r3dp_stream_t stream);
 int r3dp_sr_tc_layer_torgb_noup(const void* x_f16, const void* wp_f16, const float* bias, const float* wrgb, const float* brgb,
                                 const float* img_prev, int N, int Nw, int I, int O, int H, int W, void* y_f16, float* img_out,
                                 r3dp_stream_t stream);

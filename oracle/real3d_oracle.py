@@ -473,8 +473,10 @@ def synthesis_block_noup(x, img, ws3, p, prefix):
     return x, img + to_rgb(x, ws3[:, 2], p, prefix + 'torgb.')
 
 
-def superres_warp(rgb, x, ws, ref_torso_rgb, ref_bg_rgb, weights_img, segmap, kp_s, kp_d, p: Dict[str, Tensor], torso_model, head_threshold=0.9):
-    """SuperresolutionHybrid8XDC_Warp.forward, htbsr_head_weight_fuse_mode 'v2', torso_model_version 'v2' (sr_with_ref.py:67-136)."""
+def superres_warp(rgb, x, ws, ref_torso_rgb, ref_bg_rgb, weights_img, segmap, kp_s, kp_d, p: Dict[str, Tensor], torso_model, head_threshold=0.9,
+                  mode: str = 'v2'):
+    """SuperresolutionHybrid8XDC_Warp.forward, torso_model_version 'v2', eval mode; `mode` = htbsr_head_weight_fuse_mode:
+    'v1' sr_with_ref.py:96-104, 'v2' (the released configuration) :106-124, 'v3' :126-152."""
     ws3 = ws[:, -1:, :].expand(rgb.shape[0], 3, -1)
     if x.shape[-1] != 128:
         x, rgb = resize_bilinear(x, 128), resize_bilinear(rgb, 128)
@@ -485,13 +487,28 @@ def superres_warp(rgb, x, ws, ref_torso_rgb, ref_bg_rgb, weights_img, segmap, kp
     rgb_torso, ret = torso_model(ref_torso_256, segmap, kp_s, kp_d, rgb_256, weights_256, cal_loss=True, target_torso_mask=None)
     x_torso = conv_plain(ret['deformed_torso_hid'], p, 'torso_encoder.0')
     x_bg = conv_plain(conv_plain(conv_plain(ref_bg_256, p, 'bg_encoder.0', 0.01), p, 'bg_encoder.2', 0.01), p, 'bg_encoder.4')
-    alpha = weights_256                                                                    # :108-109 (the masked assignment is a no-op)
-    rgb = rgb * alpha + rgb_torso * (1 - alpha)
-    x = torch.cat([x * alpha, x_torso * (1 - alpha)], dim=1)
-    x = conv_plain(conv_plain(x, p, 'fuse_head_torso_convs.0', 0.01), p, 'fuse_head_torso_convs.2')
-    x, rgb = synthesis_block_noup(x, rgb, ws3, p, 'head_torso_block.')
-    head_occ = torch.where(alpha > head_threshold, torch.ones_like(alpha), alpha)
     torso_occ = ret['occlusion_2'] if ret['occlusion_2'].shape[-1] == 256 else resize_bilinear(ret['occlusion_2'], 256)
+    if mode == 'v1':                                                                       # :96-104: plain alpha blend of rgb AND features, no head/torso convs
+        alpha = weights_256
+        rgb = rgb * alpha + rgb_torso * (1 - alpha)
+        x = x * alpha + x_torso * (1 - alpha)
+    else:
+        if mode == 'v3':                                                                   # :129-132: a small conv net post-processes the head mask, capped by the weights
+            inp = torch.cat([rgb.clamp(-1, 1) / 2 + 0.5, weights_256, rgb_torso.clamp(-1, 1) / 2 + 0.5], dim=1)
+            a_ = conv_plain(conv_plain(conv_plain(inp, p, 'head_torso_alpha_predictor.0', 0.01), p, 'head_torso_alpha_predictor.2', 0.01), p,
+                            'head_torso_alpha_predictor.4')
+            alpha = torch.minimum(torch.sigmoid(a_), weights_256)
+        else:
+            alpha = weights_256                                                            # :108-109 (the masked assignment is a no-op)
+        rgb = rgb * alpha + rgb_torso * (1 - alpha)
+        x = torch.cat([x * alpha, x_torso * (1 - alpha)], dim=1)
+        x = conv_plain(conv_plain(x, p, 'fuse_head_torso_convs.0', 0.01), p, 'fuse_head_torso_convs.2')
+        x, rgb = synthesis_block_noup(x, rgb, ws3, p, 'head_torso_block.')
+    thr = head_threshold
+    if mode == 'v3':                                                                       # :141-143 (eval): batch-wide 5 % quantile of the mask values above 0.05
+        sel = alpha[alpha > 0.05]
+        thr = max(float(sel.quantile(0.05)), head_threshold)
+    head_occ = torch.where(alpha > thr, torch.ones_like(alpha), alpha)
     person = (torso_occ + head_occ).clamp(0, 1)
     rgb = rgb * person + ref_bg_256 * (1 - person)
     x = torch.cat([x * person, x_bg * (1 - person)], dim=1)

@@ -78,7 +78,7 @@ def to_nhwc_f16(x: torch.Tensor, size: int, split: bool = False) -> torch.Tensor
     return y
 
 
-def pack_plain(conv: torch.nn.Conv2d, in_tensor_channels: int, out_pad: int = 128):
+def pack_plain(conv: torch.nn.Conv2d, in_tensor_channels: int, out_pad: int = 128, split: bool = False):
     """nn.Conv2d (k = 1|3) -> packed fp16 weights [1,9,Opad,Ipad] + fp32 bias [Opad]; output channels padded to a multiple of
     `out_pad` with zero filters, input channels padded (zero weights) to the channel count of the activation tensor it reads."""
     w = conv.weight.detach().float()
@@ -90,8 +90,8 @@ def pack_plain(conv: torch.nn.Conv2d, in_tensor_channels: int, out_pad: int = 12
     else:
         w9[0, :O, :I, 1, 1] = w[:, :, 0, 0]
     Ip = (in_tensor_channels + 63) // 64 * 64
-    packed = torch.empty(1, 9, Op, Ip, device=w.device, dtype=torch.float16)
-    capi.check(capi.lib().r3dp_sr_tc_pack_weights(capi.ptr(w9), 1, Op, in_tensor_channels, capi.ptr(packed, torch.float16), capi.stream()))
+    packed = torch.empty(1, 9, Op, Ip * (2 if split else 1), device=w.device, dtype=torch.float16)
+    capi.check(_fn('pack_weights', split)(capi.ptr(w9), 1, Op, in_tensor_channels, capi.ptr(packed, torch.float16), capi.stream()))
     bias = torch.zeros(Op, device=w.device)
     bias[:O] = conv.bias.detach().float()
     return packed, bias, k

@@ -48,20 +48,22 @@ class SuperresolutionHybrid8XDC_Warp(SuperresolutionHybrid8XDC):
         hp = dict(hp or {})
         self.hparams = {'torso_model_version': hp.get('torso_model_version', 'v2'), 'htbsr_head_weight_fuse_mode': hp.get('htbsr_head_weight_fuse_mode', 'v2'),
                         'htbsr_head_threshold': float(hp.get('htbsr_head_threshold', 0.9)), 'weight_fuse': hp.get('weight_fuse', True)}
-        if self.hparams['torso_model_version'] != 'v2' or self.hparams['htbsr_head_weight_fuse_mode'] != 'v2' or not self.hparams['weight_fuse']:
-            raise NotImplementedError('only torso_model_version=v2 with htbsr_head_weight_fuse_mode=v2 (the released Real3D torso config) is built')
+        self.fuse_mode = self.hparams['htbsr_head_weight_fuse_mode']
+        if self.hparams['torso_model_version'] != 'v2' or self.fuse_mode not in ('v1', 'v2', 'v3') or not self.hparams['weight_fuse']:
+            raise NotImplementedError('built: torso_model_version=v2 with htbsr_head_weight_fuse_mode v1 | v2 (the released Real3D torso config) | v3, weight_fuse=True')
         if torso_model is not None:
             self.torso_model = torso_model                      # the reference's WarpBasedTorsoModelMediaPipe('standard'), supplied by the caller
         nn = torch.nn
         self.torso_encoder = nn.Sequential(nn.Conv2d(64, 256, 1, 1, padding=0))
         self.bg_encoder = nn.Sequential(nn.Conv2d(3, 64, 3, 1, padding=1), nn.LeakyReLU(), nn.Conv2d(64, 256, 3, 1, padding=1), nn.LeakyReLU(),
                                         nn.Conv2d(256, 256, 3, 1, padding=1))
-        self.head_torso_alpha_predictor = nn.Sequential(nn.Conv2d(7, 32, 3, 1, padding=1), nn.LeakyReLU(), nn.Conv2d(32, 32, 3, 1, padding=1),
-                                                        nn.LeakyReLU(), nn.Conv2d(32, 1, 3, 1, padding=1), nn.Sigmoid())   # v3 only; kept for state_dict parity
-        self.fuse_head_torso_convs = nn.Sequential(nn.Conv2d(512, 256, 3, 1, padding=1), nn.LeakyReLU(), nn.Conv2d(256, 256, 3, 1, padding=1))
-        bk = {k: v for k, v in block_kwargs.items() if k not in ('sr_mode', 'channel_base', 'channel_max')}
-        self.head_torso_block = SynthesisBlockNoUp(256, 256, w_dim=512, resolution=256, img_channels=3, is_last=False, use_fp16=False,
-                                                   conv_clamp=None, **bk)
+        if self.fuse_mode != 'v1':                              # the reference builds these children for every mode but v1 (sr_with_ref.py:36-55)
+            self.head_torso_alpha_predictor = nn.Sequential(nn.Conv2d(7, 32, 3, 1, padding=1), nn.LeakyReLU(), nn.Conv2d(32, 32, 3, 1, padding=1),
+                                                            nn.LeakyReLU(), nn.Conv2d(32, 1, 3, 1, padding=1), nn.Sigmoid())   # used by v3 only
+            self.fuse_head_torso_convs = nn.Sequential(nn.Conv2d(512, 256, 3, 1, padding=1), nn.LeakyReLU(), nn.Conv2d(256, 256, 3, 1, padding=1))
+            bk = {k: v for k, v in block_kwargs.items() if k not in ('sr_mode', 'channel_base', 'channel_max')}
+            self.head_torso_block = SynthesisBlockNoUp(256, 256, w_dim=512, resolution=256, img_channels=3, is_last=False, use_fp16=False,
+                                                       conv_clamp=None, **bk)
         self.fuse_fg_bg_convs = nn.Sequential(nn.Conv2d(512, 64, 1, 1, padding=0), nn.LeakyReLU(), nn.Conv2d(64, 256, 3, 1, padding=1),
                                               nn.LeakyReLU(), nn.Conv2d(256, 256, 3, 1, padding=1))
         self._plain_cache = None
@@ -71,12 +73,18 @@ class SuperresolutionHybrid8XDC_Warp(SuperresolutionHybrid8XDC):
     # ---- weight preparation ------------------------------------------------------------------------------------------------
     def _plain(self) -> Dict[str, tuple]:
         if self._plain_cache is None:
-            te, bg, fh, ff = self.torso_encoder, self.bg_encoder, self.fuse_head_torso_convs, self.fuse_fg_bg_convs
+            te, bg, ff = self.torso_encoder, self.bg_encoder, self.fuse_fg_bg_convs
             self._plain_cache = {
                 'te': _pack_plain(te[0], 64), 'bg0': _pack_plain(bg[0], 64), 'bg2': _pack_plain(bg[2], 128), 'bg4': _pack_plain(bg[4], 256),
-                'fh0': _pack_plain(fh[0], 512), 'fh2': _pack_plain(fh[2], 256),
                 'ff0': _pack_plain(ff[0], 512), 'ff2': _pack_plain(ff[2], 128), 'ff4': _pack_plain(ff[4], 256),
             }
+            if self.fuse_mode != 'v1':
+                fh = self.fuse_head_torso_convs
+                self._plain_cache.update({'fh0': _pack_plain(fh[0], 512), 'fh2': _pack_plain(fh[2], 256)})
+            if self.fuse_mode == 'v3':                             # the mask predictor runs with split fp16 operands (its output is thresholded)
+                ap = self.head_torso_alpha_predictor
+                self._plain_cache.update({'ap0': sr_tc.pack_plain(ap[0], 64, split=True), 'ap2': sr_tc.pack_plain(ap[2], 128, split=True),
+                                          'ap4': sr_tc.pack_plain(ap[4], 128, split=True)})
         return self._plain_cache
 
     def _load_from_state_dict(self, *a, **k):
@@ -88,14 +96,16 @@ class SuperresolutionHybrid8XDC_Warp(SuperresolutionHybrid8XDC):
         return super()._load_from_state_dict(*a, **k)
 
     @staticmethod
-    def _conv(x16: torch.Tensor, packed, act: int) -> torch.Tensor:
-        """x16 [N,H,W,Ct] fp16 -> [N,H,W,Opad] fp16; act 0 linear, 2 nn.LeakyReLU(0.01)."""
+    def _conv(x16: torch.Tensor, packed, act: int, split: bool = False) -> torch.Tensor:
+        """x16 [N,H,W,Ct] fp16 -> [N,H,W,Opad] fp16; act 0 linear, 2 nn.LeakyReLU(0.01).  split: [hi | lo] tensors of twice the channels (fp32-grade)."""
         wp, bias, k = packed
         N, H, W, Ct = x16.shape
-        y = torch.empty(N, H, W, wp.shape[2], device=x16.device, dtype=torch.float16)
+        wide = 2 if split else 1
+        y = torch.empty(N, H, W, wp.shape[2] * wide, device=x16.device, dtype=torch.float16)
+        fn = capi.lib().r3dp_sr_tcx_conv if split else capi.lib().r3dp_sr_tc_conv
         with capi.region('sr_conv'):
-            capi.check(capi.lib().r3dp_sr_tc_conv(capi.ptr(x16, torch.float16), capi.ptr(wp, torch.float16), capi.ptr(bias), N, 1, Ct, wp.shape[2], H, W, k, act,
-                                                  capi.ptr(y, torch.float16), capi.stream()))
+            capi.check(fn(capi.ptr(x16, torch.float16), capi.ptr(wp, torch.float16), capi.ptr(bias), N, 1, Ct // wide, wp.shape[2], H, W, k, act,
+                          capi.ptr(y, torch.float16), capi.stream()))
         return y
 
     @staticmethod
@@ -157,9 +167,10 @@ class SuperresolutionHybrid8XDC_Warp(SuperresolutionHybrid8XDC):
             if prep is None:
                 shared = N == 1 or getattr(self, 'assume_shared_styles', False)
                 wsel = ws3[:1] if shared else ws3
-                prep = {'main': sr_tc.Prepared(self, wsel),
-                        'ht0': sr_tc.pack_for(self.head_torso_block.conv0, wsel[:, 0]), 'ht1': sr_tc.pack_for(self.head_torso_block.conv1, wsel[:, 1]),
-                        'htrgb': self.head_torso_block.torgb.folded_weight(wsel[:, 2])}
+                prep = {'main': sr_tc.Prepared(self, wsel)}
+                if self.fuse_mode != 'v1':
+                    prep.update({'ht0': sr_tc.pack_for(self.head_torso_block.conv0, wsel[:, 0]), 'ht1': sr_tc.pack_for(self.head_torso_block.conv1, wsel[:, 1]),
+                                 'htrgb': self.head_torso_block.torgb.folded_weight(wsel[:, 2])})
             plain = self._plain()
             x0 = sr_tc.to_nhwc_f16(x, self.input_resolution)
             rgb0 = self._resize(rgb, self.input_resolution) if rgb.shape[-1] != self.input_resolution else capi.f32(rgb)
@@ -171,7 +182,7 @@ class SuperresolutionHybrid8XDC_Warp(SuperresolutionHybrid8XDC):
             else:                                                        # per-clip constants, one frame broadcast over the batch (0.8 MB copies)
                 ref_torso_256, ref_bg_256 = cc['ref_torso_256'].expand(N, -1, -1, -1).contiguous(), cc['ref_bg_256'].expand(N, -1, -1, -1).contiguous()
         main, Nw = prep['main'], prep['main'].Nw
-        b0, b1, hb = self.block0, self.block1, self.head_torso_block
+        b0, b1, hb = self.block0, self.block1, getattr(self, 'head_torso_block', None)
         # block0: 128^2 -> 256^2 head features + head rgb
         a0 = sr_tc.layer(x0, b0.conv0, main.wp[0], 2)
         xh = torch.empty(N, 256, 256, 256, device=x.device, dtype=torch.float16)
@@ -189,22 +200,45 @@ class SuperresolutionHybrid8XDC_Warp(SuperresolutionHybrid8XDC):
             x_bg = self._conv(self._conv(self._conv(sr_tc.to_nhwc_f16(ref_bg_256, 256), plain['bg0'], 2), plain['bg2'], 2), plain['bg4'], 0)
         else:
             x_bg = cc['x_bg']                                            # [1,256,256,256] fp16, read by every frame of the batch
-        # head/torso fusion (v2: alpha-cat), sr_with_ref.py:106-113
-        alpha = weights_256
-        rgb_p = self._blend(rgb_h, rgb_torso, alpha)
-        xf = self._conv(self._conv(self._alpha_cat(xh, 256, x_torso, 256, alpha), plain['fh0'], 2), plain['fh2'], 0)
-        c0 = sr_tc.layer(xf, hb.conv0, prep['ht0'], 1)
-        xp = torch.empty(N, 256, 256, 256, device=x.device, dtype=torch.float16)
-        rgb_p2 = torch.empty(N, 3, 256, 256, device=x.device)
-        with capi.region('sr_conv'):
-            capi.check(L.r3dp_sr_tc_layer_torgb_noup(capi.ptr(c0, torch.float16), capi.ptr(prep['ht1'], torch.float16), capi.ptr(capi.f32(hb.conv1.bias)),
-                                                     capi.ptr(prep['htrgb']), capi.ptr(capi.f32(hb.torgb.bias)), capi.ptr(rgb_p), N, Nw, 256, 256, 256, 256,
-                                                     capi.ptr(xp, torch.float16), capi.ptr(rgb_p2), capi.stream()))
+        thr = float(self.hparams['htbsr_head_threshold'])
+        if self.fuse_mode == 'v1':
+            # head/torso fusion v1 (sr_with_ref.py:96-98): plain alpha blend of the rgb images AND of the feature maps; no fusing convs, no head_torso_block
+            alpha = weights_256
+            rgb_p2 = self._blend(rgb_h, rgb_torso, alpha)
+            xp = torch.empty(N, 256, 256, 256, device=x.device, dtype=torch.float16)
+            capi.check(L.r3dp_sr_alpha_mix(capi.ptr(xh, torch.float16), xh.shape[-1], capi.ptr(x_torso, torch.float16), x_torso.shape[-1], capi.ptr(alpha), 256,
+                                           N, 256, 256, capi.ptr(xp, torch.float16), capi.stream()))
+        else:
+            if self.fuse_mode == 'v3':
+                # sr_with_ref.py:129-132: a 3-conv net post-processes the head mask from (head rgb, weights, torso rgb); capped by the weights.  The net runs
+                # on the tensor cores with SPLIT fp16 operands (fp32-grade): its output is compared with thresholds below, fp16 noise would flip pixels
+                inp7 = torch.cat([rgb_h.clamp(-1, 1) / 2 + 0.5, weights_256, capi.f32(rgb_torso).clamp(-1, 1) / 2 + 0.5], dim=1)
+                t = sr_tc.to_nhwc_f16(inp7, 256, split=True)
+                t = self._conv(self._conv(self._conv(t, plain['ap0'], 2, split=True), plain['ap2'], 2, split=True), plain['ap4'], 0, split=True)
+                alpha = torch.empty(N, 1, 256, 256, device=x.device)
+                capi.check(L.r3dp_sr_alpha_gate(capi.ptr(t, torch.float16), t.shape[-1], t.shape[-1] // 2, capi.ptr(weights_256), N, 256, 256, capi.ptr(alpha),
+                                                capi.stream()))
+                if not self.training:                              # :141-143: batch-wide 5 % quantile of the mask values above 0.05 (a host-side scalar, as in the reference)
+                    sel = alpha[alpha > 0.05]
+                    if sel.numel() > 0:
+                        thr = max(float(sel.quantile(0.05)), thr)
+            else:
+                alpha = weights_256                                 # v2, sr_with_ref.py:108-109 (the masked assignment is a no-op)
+            # alpha-cat fusion of the head and torso features (sr_with_ref.py:110-113 | 133-136)
+            rgb_p = self._blend(rgb_h, rgb_torso, alpha)
+            xf = self._conv(self._conv(self._alpha_cat(xh, 256, x_torso, 256, alpha), plain['fh0'], 2), plain['fh2'], 0)
+            c0 = sr_tc.layer(xf, hb.conv0, prep['ht0'], 1)
+            xp = torch.empty(N, 256, 256, 256, device=x.device, dtype=torch.float16)
+            rgb_p2 = torch.empty(N, 3, 256, 256, device=x.device)
+            with capi.region('sr_conv'):
+                capi.check(L.r3dp_sr_tc_layer_torgb_noup(capi.ptr(c0, torch.float16), capi.ptr(prep['ht1'], torch.float16), capi.ptr(capi.f32(hb.conv1.bias)),
+                                                         capi.ptr(prep['htrgb']), capi.ptr(capi.f32(hb.torgb.bias)), capi.ptr(rgb_p), N, Nw, 256, 256, 256, 256,
+                                                         capi.ptr(xp, torch.float16), capi.ptr(rgb_p2), capi.stream()))
         # person / background fusion, sr_with_ref.py:115-124
         occ = capi.f32(facev2v_ret['occlusion_2'])
         torso_occ = occ if occ.shape[-1] == 256 else self._resize(occ, 256)
         person = torch.empty(N, 1, 256, 256, device=x.device)
-        capi.check(L.r3dp_sr_person_occlusion(capi.ptr(alpha), capi.ptr(torso_occ), float(self.hparams['htbsr_head_threshold']), N, 256, 256,
+        capi.check(L.r3dp_sr_person_occlusion(capi.ptr(alpha), capi.ptr(torso_occ), thr, N, 256, 256,
                                               capi.ptr(person), capi.stream()))
         rgb_f = self._blend(rgb_p2, ref_bg_256, person)
         xg = self._conv(self._conv(self._conv(self._alpha_cat(xp, 256, x_bg, 256, person), plain['ff0'], 2), plain['ff2'], 2), plain['ff4'], 0)

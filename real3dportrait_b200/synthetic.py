@@ -140,8 +140,9 @@ class StubTorsoModel(torch.nn.Module):
         return rgb_torso, {'deformed_torso_hid': hid, 'occlusion_2': occ}
 
 
-def make_sr_warp_params(seed: int = 6) -> Dict[str, torch.Tensor]:
-    """state_dict of SuperresolutionHybrid8XDC_Warp WITHOUT its torso_model child (sr_with_ref.py:16-66, fuse mode v2)."""
+def make_sr_warp_params(seed: int = 6, fuse_mode: str = 'v2') -> Dict[str, torch.Tensor]:
+    """state_dict of SuperresolutionHybrid8XDC_Warp WITHOUT its torso_model child (sr_with_ref.py:16-66).  The same random values for every fuse mode;
+    mode 'v1' has no head_torso_alpha_predictor / fuse_head_torso_convs / head_torso_block children (sr_with_ref.py:36-55), so their keys are dropped."""
     p = make_sr_params(seed=seed)
     g = torch.Generator().manual_seed(seed + 100)
     f = p['block0.resample_filter']
@@ -171,6 +172,8 @@ def make_sr_warp_params(seed: int = 6) -> Dict[str, torch.Tensor]:
     p[pre + 'bias'] = 0.1 * torch.randn(3, generator=g)
     p[pre + 'affine.weight'] = torch.randn(256, 512, generator=g)
     p[pre + 'affine.bias'] = 1.0 + 0.1 * torch.randn(256, generator=g)
+    if fuse_mode == 'v1':
+        p = {k: v for k, v in p.items() if not k.startswith(('head_torso_alpha_predictor.', 'fuse_head_torso_convs.', 'head_torso_block.'))}
     return p
 
 

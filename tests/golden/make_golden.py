@@ -163,25 +163,33 @@ def layer_cases():
     save('sr_layers', **out)
 
 
-def warp_case():
-    """BASELINE config 5's SR head (SuperresolutionHybrid8XDC_Warp, fuse mode v2) at N=1 with the reference class; its torso_model child is
-    replaced by synthetic.StubTorsoModel (the real warper is an opaque child outside the hot path)."""
+def warp_case(mode='v2'):
+    """BASELINE config 5's SR head (SuperresolutionHybrid8XDC_Warp) at N=1 with the reference class; its torso_model child is replaced by
+    synthetic.StubTorsoModel (the real warper is an opaque child outside the hot path).  mode = htbsr_head_weight_fuse_mode: 'v2' (the released
+    configuration) -> sr_warp_full.npz; 'v1' / 'v3' (sr_with_ref.py:96-104,126-152) -> sr_warp_v1.npz / sr_warp_v3.npz."""
     import types
     sys.modules.setdefault('imageio', types.ModuleType('imageio'))
-    hparams.update(syn.WARP_HPARAMS)
+    hparams.update(dict(syn.WARP_HPARAMS, htbsr_head_weight_fuse_mode=mode))
     from modules.real3d.super_resolution.sr_with_ref import SuperresolutionHybrid8XDC_Warp
     m = SuperresolutionHybrid8XDC_Warp(channels=32, img_resolution=512, sr_num_fp16_res=0, sr_antialias=True, channel_base=32768,
                                        channel_max=512, fused_modconv_default='inference_only').eval()
     m.torso_model = syn.StubTorsoModel()
-    res = m.load_state_dict(syn.make_sr_warp_params(seed=6), strict=True)
+    res = m.load_state_dict(syn.make_sr_warp_params(seed=6, fuse_mode=mode), strict=True)
     g = load('render_full48')
     feat = torch.from_numpy(g['rgb'])
     fimg = feat.permute(0, 2, 1).reshape(1, 32, 64, 64).contiguous()
     wimg = torch.from_numpy(g['wsum']).permute(0, 2, 1).reshape(1, 1, 64, 64).contiguous()
+    if mode != 'v2':
+        wimg = (wimg * 3.0).clamp(0, 1)        # the random-density fixture has weights around 0.3: stretch them so that the head threshold and the v3 quantile bite
     inp = syn.make_warp_inputs(1, seed=7)
-    img, ret = m(fimg[:, :3], fimg, torch.ones(1, 14, 512), inp['ref_torso_rgb'], inp['ref_bg_rgb'], wimg, inp['segmap'], inp['kp_s'], inp['kp_d'],
-                 noise_mode='none')
-    save('sr_warp_full', image=img, seeds=np.array([6, 7]))
+    with torch.no_grad():
+        img, ret = m(fimg[:, :3], fimg, torch.ones(1, 14, 512), inp['ref_torso_rgb'], inp['ref_bg_rgb'], wimg, inp['segmap'], inp['kp_s'], inp['kp_d'],
+                     noise_mode='none')
+    if mode == 'v2':
+        save('sr_warp_full', image=img, seeds=np.array([6, 7]))
+    else:
+        save('sr_warp_' + mode, image=img, weights_img=wimg, seeds=np.array([6, 7]))
+    hparams.update(syn.WARP_HPARAMS)
 
 
 def trigrid_case():
@@ -236,6 +244,7 @@ if __name__ == '__main__':
     torch.manual_seed(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'warp':
         warp_case()
+        warp_case('v1'); warp_case('v3')
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'large_sr':
         large_sr_case()
@@ -247,5 +256,6 @@ if __name__ == '__main__':
     layer_cases()
     full_cases()
     warp_case()
+    warp_case('v1'); warp_case('v3')
     trigrid_case()
     large_sr_case()

@@ -68,9 +68,15 @@ def test_torso_head_state_dict_layout():
     assert set(m.state_dict().keys()) == want, set(m.state_dict().keys()) ^ want
     m.load_state_dict(syn.make_sr_warp_params(), strict=True)
     assert sum(p.numel() for p in m.parameters()) == 6532912          # probe of the reference class (without torso_model)
+    # the other fuse modes of the reference: v1 has no head/torso fusing children (sr_with_ref.py:36-55), v3 has them all; unknown modes raise as in the reference
+    for mode in ('v1', 'v3'):
+        mm = r3.SuperresolutionHybrid8XDC_Warp(channels=32, img_resolution=512, sr_num_fp16_res=0, sr_antialias=True,
+                                               hp=dict(syn.WARP_HPARAMS, htbsr_head_weight_fuse_mode=mode))
+        assert set(mm.state_dict().keys()) == set(syn.make_sr_warp_params(fuse_mode=mode))
+    assert not any(k.startswith('head_torso') for k in syn.make_sr_warp_params(fuse_mode='v1'))
     with pytest.raises(NotImplementedError):
         r3.SuperresolutionHybrid8XDC_Warp(channels=32, img_resolution=512, sr_num_fp16_res=0, sr_antialias=True,
-                                          hp=dict(syn.WARP_HPARAMS, htbsr_head_weight_fuse_mode='v3'))
+                                          hp=dict(syn.WARP_HPARAMS, htbsr_head_weight_fuse_mode='v4'))
 
 
 def test_gpu_local_cpus_is_a_noop_without_a_gpu_and_restores_affinity():

@@ -307,6 +307,28 @@ def test_torso_head_vs_reference(golden):
     assert _maxdiff(m._aa_down2(inp['ref_bg_rgb']), lib) < 1e-5
 
 
+@pytest.mark.parametrize('mode', ['v1', 'v3'])
+def test_torso_head_other_fuse_modes_vs_reference(golden, mode):
+    """htbsr_head_weight_fuse_mode v1 (alpha blend of the features) and v3 (conv-predicted head mask capped by the weights + batch-quantile threshold),
+    sr_with_ref.py:96-104,126-152: tensor-core path vs the REFERENCE class run in that mode (fixture sr_warp_<mode>.npz, stub torso child)."""
+    g, fx = golden('render_full48'), golden('sr_warp_' + mode)
+    fimg = orc.feature_image(g['rgb'], 64).to(DEV)
+    inp = {k: v.to(DEV) for k, v in syn.make_warp_inputs(1, seed=7).items()}
+    m = r3.SuperresolutionHybrid8XDC_Warp(channels=32, img_resolution=512, sr_num_fp16_res=0, sr_antialias=True,
+                                          hp=dict(syn.WARP_HPARAMS, htbsr_head_weight_fuse_mode=mode), torso_model=syn.StubTorsoModel())
+    m.load_state_dict(syn.make_sr_warp_params(seed=6, fuse_mode=mode), strict=True)
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        img, ret = m(fimg[:, :3].contiguous(), fimg, torch.ones(1, 14, 512, device=DEV), inp['ref_torso_rgb'], inp['ref_bg_rgb'], fx['weights_img'].to(DEV),
+                     inp['segmap'], inp['kp_s'], inp['kp_d'], noise_mode='none')
+    ref = fx['image']
+    err = _maxdiff(img, ref)
+    mse = float(((img.cpu() - ref) ** 2).mean())
+    psnr = 10 * torch.log10(torch.tensor(float(ref.max() - ref.min()) ** 2 / mse)).item()
+    print(f'torso head fuse mode {mode} (tc): max-abs {err:.3e}, PSNR {psnr:.1f} dB')
+    assert err < TC_MAXABS and psnr > TC_PSNR, (err, psnr)
+
+
 def test_torso_render_head_config5_vs_oracle():
     """Config 5 path for one frame: 48+48 importance render -> torso SR head, whole head vs the oracle (stub torso child on both sides)."""
     N = 1

@@ -88,6 +88,20 @@ def test_sr_warp_full(golden):
     assert _maxdiff(img, ref) < 2e-4 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize('mode', ['v1', 'v3'])
+def test_sr_warp_other_fuse_modes(golden, mode):
+    """htbsr_head_weight_fuse_mode v1 (plain alpha blend) and v3 (conv-predicted head mask + batch quantile threshold), sr_with_ref.py:96-104,126-152,
+    vs the reference class in that mode (stub torso model; stretched weights image stored in the fixture)."""
+    g, fx = golden('render_full48'), golden('sr_warp_' + mode)
+    fimg = orc.feature_image(g['rgb'], 64)
+    inp = syn.make_warp_inputs(1, seed=7)
+    img, _ = orc.superres_warp(fimg[:, :3], fimg, torch.ones(1, 14, 512), inp['ref_torso_rgb'], inp['ref_bg_rgb'], fx['weights_img'], inp['segmap'],
+                               inp['kp_s'], inp['kp_d'], syn.make_sr_warp_params(seed=6, fuse_mode=mode), syn.StubTorsoModel(), mode=mode)
+    ref = fx['image']
+    assert _maxdiff(img, ref) < 2e-4 * float(ref.abs().max())
+
+
+
 def test_trigrid_sample_and_render(golden):
     """`trigrid_v2` (depth-3 tri-grids, 3-D grid_sample; renderer.py:78-89) against the reference's sample_from_trigrids / ImportanceRenderer."""
     g = golden('render_trigrid')

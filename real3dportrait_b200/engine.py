@@ -335,6 +335,8 @@ class FrameEngine:
             torch.cuda.ipc_collect()
         if self.world > 1 and self.dist is not None and getattr(self, '_p2p', None) is not None:
             self.dist.barrier()
+            if self.rank == 0:
+                torch.cuda.ipc_collect()                                      # the consumers' references are gone: drop the producer-side IPC bookkeeping
         return clip
 
     # ---- host-buffer entry point: H2D / compute / D2H of consecutive steps overlap on three streams -----------------------
